@@ -1,0 +1,180 @@
+/*
+ * ptmcmc_b200.h -- C ABI of the B200-native parallel-tempering MCMC engine.
+ *
+ * This is the drop-in boundary for the hot path of nanograv/PTMCMCSampler
+ * (reference PTMCMCSampler/PTMCMCSampler.py, "ref" below): the per-chain
+ * Metropolis-Hastings step, the adaptive covariance / eigen-factor update, the
+ * DE history and the inter-temperature swap, for W walkers x T temperatures
+ * resident on one GPU.  Plain C types only: no torch, no Python objects, no
+ * exceptions cross this line.  The host-side mirror of the reference API
+ * (ptmcmcsampler_b200.PTSampler) binds exactly these symbols with ctypes; see
+ * INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every call returns 0 on success, <0 on error; ptmcmc_last_error() gives
+ *     the message (engine-local; ptmcmc_create_error() for a failed create).
+ *   - all host buffers are caller-owned, C-contiguous; the engine never keeps a
+ *     host pointer after the call returns.
+ *   - chain state arrays are [T][W][d] (temperature, walker, parameter).
+ *   - one host thread per engine; calls are asynchronous on the engine's CUDA
+ *     stream unless they copy to host (getters synchronise).
+ */
+#ifndef PTMCMC_B200_H
+#define PTMCMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTMCMC_ABI_VERSION 1
+
+/* jump ids: the reference's built-in proposals; ids >= PTMCMC_JUMP_EXT0 are
+ * host-side (Python) proposals registered with addProposalToCycle (ref :988-1014) */
+enum { PTMCMC_JUMP_SCAM = 0, PTMCMC_JUMP_AM = 1, PTMCMC_JUMP_DE = 2, PTMCMC_JUMP_EXT0 = 3 };
+/* built-in log-likelihoods (ref examples/simple.py:34-36, examples/curved_likelihood.ipynb) */
+enum { PTMCMC_LOGL_EXTERNAL = 0, PTMCMC_LOGL_GAUSSIAN = 1, PTMCMC_LOGL_CURVED = 2, PTMCMC_LOGL_ROSENBROCK = 3 };
+/* built-in log-priors (ref examples/simple.py:38-44) */
+enum { PTMCMC_LOGP_EXTERNAL = 0, PTMCMC_LOGP_UNIFORM = 1, PTMCMC_LOGP_FLAT = 2 };
+
+enum {
+    PTMCMC_OK = 0,
+    PTMCMC_ERR_ARG = -1,       /* bad argument / configuration                       */
+    PTMCMC_ERR_DE_SHAPE = -2,  /* covUpdate > burn at a DE update (ref :817 ValueError) */
+    PTMCMC_ERR_CUDA = -3,
+    PTMCMC_ERR_STATE = -4,     /* call out of order (e.g. run before set_state)       */
+    PTMCMC_ERR_CAPACITY = -5   /* record window full: fetch rows and release them     */
+};
+
+#define PTMCMC_MAX_CYCLE 16
+
+/* Replaces the keyword arguments of PTSampler.__init__ (ref :75-93) and
+ * PTSampler.sample / initialize (ref :157-181, :374-399) that drive the hot path. */
+typedef struct ptmcmc_config {
+    int32_t abi_version;        /* PTMCMC_ABI_VERSION */
+    int32_t device;             /* CUDA device ordinal */
+    int32_t ndim;               /* ref ndim */
+    int32_t nwalkers;           /* W: independent ladders resident on this device */
+    int32_t ntemps;             /* T: ref nchain = comm.Get_size() (:97) */
+    int32_t walker_offset;      /* global id of local walker 0 (keys the RNG; walker sharding) */
+    int32_t temp_offset;        /* global index of local rung 0 (keys the RNG; ladder sharding) */
+    int32_t reserved0;
+    uint64_t seed;              /* ref seed (:92); Philox key */
+    const double *ladder;       /* [T] swap temperatures, ref self.ladder (:274-275, :658) */
+    const double *mh_temp;      /* [T] MH temperatures, ref self.temp (:278-282; 1e80 for hotChain); NULL = ladder */
+    const double *cov;          /* [d*d] initial proposal covariance, ref cov (:134) */
+    int32_t ngroups;            /* ref groups (:129-131); 0 = one group of all parameters */
+    int32_t reserved1;
+    const int32_t *group_offsets;  /* [ngroups+1] CSR offsets */
+    const int32_t *group_indices;  /* [group_offsets[ngroups]] parameter indices */
+    int32_t ncycle;             /* proposal-cycle segments in registration order (ref :1007-1008) */
+    int32_t de_weight;          /* ref DEweight: DE segment appended at iteration burn+1 (:563-585) */
+    int32_t cycle_jump[PTMCMC_MAX_CYCLE];
+    int32_t cycle_weight[PTMCMC_MAX_CYCLE];
+    int64_t cov_update;         /* ref covUpdate */
+    int64_t burn;               /* ref burn (DE history length, per walker) */
+    int64_t tskip;              /* ref Tskip */
+    int64_t thin;               /* ref thin */
+    int32_t logl_kind;          /* PTMCMC_LOGL_* */
+    int32_t logp_kind;          /* PTMCMC_LOGP_* */
+    const double *logl_params;  /* GAUSSIAN: mu[d], icov[d*d] row-major, offset ; others: NULL */
+    const double *logp_params;  /* UNIFORM: lo[d], hi[d], value_inside, inclusive(0/1) */
+    int32_t record_hot;         /* 0: record the T=1 rung only; 1: all rungs (ref writeHotChains) */
+    int32_t trace;              /* 1: keep a per-iteration jump/accept byte and swap maps (tests) */
+    int64_t record_rows;        /* capacity of the device-resident record window, in rows */
+    int64_t trace_iters;        /* capacity of the trace, in iterations (0 if trace == 0) */
+    int32_t timing;             /* 1: bracket every launch with CUDA events (ptmcmc_get_timing) */
+    int32_t reserved2;
+} ptmcmc_config;
+
+typedef struct ptmcmc_engine ptmcmc_engine;
+
+/* kernel classes for ptmcmc_get_timing */
+enum {
+    PTMCMC_K_MH = 0, PTMCMC_K_SWAP = 1, PTMCMC_K_ADAPT = 2, PTMCMC_K_DE = 3, PTMCMC_K_INIT = 4,
+    PTMCMC_K_PROPOSE = 5, PTMCMC_K_ACCEPT = 6, PTMCMC_K_NCLASSES = 8
+};
+typedef struct ptmcmc_timing {
+    int64_t launches[PTMCMC_K_NCLASSES]; /* kernels launched since create / last reset     */
+    double ms[PTMCMC_K_NCLASSES];        /* device time per class (only when cfg.timing=1) */
+    int64_t chain_steps;                 /* MH chain-steps executed                        */
+} ptmcmc_timing;
+
+int32_t ptmcmc_abi_version(void);
+int32_t ptmcmc_device_count(void);
+const char *ptmcmc_create_error(void);
+const char *ptmcmc_last_error(const ptmcmc_engine *e);
+
+/* PTSampler.__init__ + initialize (ref :75-155, :157-319): allocate device state, factor cov */
+ptmcmc_engine *ptmcmc_create(const ptmcmc_config *cfg);
+void ptmcmc_destroy(ptmcmc_engine *e);
+
+/* Initial point (ref sample :471-493): evaluate logp/logl on device, record row 0, fill AM slot 0.
+ * x0 is [T][W][d]. */
+int32_t ptmcmc_set_state(ptmcmc_engine *e, const double *x0);
+/* Same with host-evaluated values (Python logl/logp): lnl, lnprior are [T][W]. */
+int32_t ptmcmc_set_state_external(ptmcmc_engine *e, const double *x0, const double *lnl,
+                                  const double *lnprior);
+
+/* The hot loop (ref :495-528 driver + :530-629 PTMCMCOneStep) for niter iterations, built-in
+ * proposals and targets only, entirely on device. */
+int32_t ptmcmc_run(ptmcmc_engine *e, int64_t niter);
+
+/* Slow path for Python callables, one iteration per propose/accept pair.
+ * propose: start iteration iter+1: covariance / DE maintenance (ref :545-585), draw the jump and
+ *   the proposal for every chain (ref :601, _jump :1048-1067).  q [T][W][d] receives the proposals
+ *   (q = x for chains whose jump id >= PTMCMC_JUMP_EXT0: the host fills those), jump [T][W] the ids.
+ * accept: finish the iteration with host-supplied q, qxy, log-likelihood and log-prior of q
+ *   ([T][W] each; lnprior = -inf marks "logl not evaluated", ref :607-608): Hastings test
+ *   (ref :614-622), swap (ref :624-625, :631-697), buffers and record (ref :627). */
+int32_t ptmcmc_propose(ptmcmc_engine *e, double *q, int32_t *jump);
+int32_t ptmcmc_accept(ptmcmc_engine *e, const double *q, const double *qxy, const double *lnl,
+                      const double *lnprior);
+
+int64_t ptmcmc_iteration(const ptmcmc_engine *e);
+int32_t ptmcmc_sync(ptmcmc_engine *e);
+
+/* ref p0 / lnlike0 / lnprob0 of every chain; any pointer may be NULL */
+int32_t ptmcmc_get_state(ptmcmc_engine *e, double *x, double *lnl, double *lnprior, double *lnprob);
+
+/* ref _chain/_lnlike/_lnprob (:208-212, :331-335).  Rows are numbered iter/thin; the device keeps
+ * a window [row_base, row_base+record_rows).  chain is [nrows][ntr][W][d], lnl/lnprob [nrows][ntr][W],
+ * ntr = record_hot ? T : 1. */
+int64_t ptmcmc_rows(const ptmcmc_engine *e);
+int64_t ptmcmc_row_base(const ptmcmc_engine *e);
+int32_t ptmcmc_get_chain(ptmcmc_engine *e, int64_t row0, int64_t nrows, double *chain, double *lnl,
+                         double *lnprob);
+int32_t ptmcmc_release_rows(ptmcmc_engine *e, int64_t upto_row);
+
+/* ref cov / mu / M2 (:147-148, :769-794) and the per-group factor U, S (:797-803) */
+int32_t ptmcmc_get_adapt(ptmcmc_engine *e, double *cov, double *mu, double *m2, int64_t *nsamp);
+int32_t ptmcmc_get_factor(ptmcmc_engine *e, double *U, double *S);
+int32_t ptmcmc_set_factor(ptmcmc_engine *e, const double *U, const double *S);
+/* ref _AMbuffer [covUpdate][W][d] and _DEbuffer [burn][W][d] (:219-221) */
+int32_t ptmcmc_get_buffers(ptmcmc_engine *e, double *am, double *de);
+
+/* Pooled adaptation across devices (walker sharding).  begin: if a covariance update is due at
+ * the current iteration, compute this device's batch moments into batch_out = {n, mean[d],
+ * M2c[d*d]} and return 1 (0 if none is due).  finish: apply the (all-reduced) batch. */
+int32_t ptmcmc_adapt_begin(ptmcmc_engine *e, double *batch_out);
+int32_t ptmcmc_adapt_finish(ptmcmc_engine *e, const double *batch_in);
+
+/* ref jumpDict[name] = [proposed, accepted] (:602, :622) per chain: prop/acc are [T][W][njumps];
+ * nswap_accepted per chain [T][W] (:691) and swapProposed (:692) */
+int32_t ptmcmc_njumps(const ptmcmc_engine *e);
+int32_t ptmcmc_get_counters(ptmcmc_engine *e, int64_t *prop, int64_t *acc, int64_t *swap_acc,
+                            int64_t *swap_proposed);
+/* test hook: trace bytes [iters][T][W] (jump | accepted<<7) and swap maps [events][W][T] */
+int32_t ptmcmc_get_trace(ptmcmc_engine *e, uint8_t *trace, int64_t iters, int16_t *swapmaps,
+                         int64_t events);
+
+int32_t ptmcmc_get_timing(ptmcmc_engine *e, ptmcmc_timing *out);
+int32_t ptmcmc_reset_timing(ptmcmc_engine *e);
+/* the engine's CUDA stream (cudaStream_t) for callers that time with their own events */
+void *ptmcmc_stream(ptmcmc_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTMCMC_B200_H */

@@ -1,0 +1,334 @@
+"""ctypes binding of the engine's C ABI (include/ptmcmc_b200.h).
+
+There is no CPU implementation behind this module: if the shared library is missing, or no CUDA
+device is visible when an engine is created, the error is raised to the caller.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libptmcmc_b200.so")
+ABI_VERSION = 1
+MAX_CYCLE = 16
+
+JUMP_SCAM, JUMP_AM, JUMP_DE, JUMP_EXT0 = 0, 1, 2, 3
+LOGL_EXTERNAL, LOGL_GAUSSIAN, LOGL_CURVED, LOGL_ROSENBROCK = 0, 1, 2, 3
+LOGP_EXTERNAL, LOGP_UNIFORM, LOGP_FLAT = 0, 1, 2
+ERR_ARG, ERR_DE_SHAPE, ERR_CUDA, ERR_STATE, ERR_CAPACITY = -1, -2, -3, -4, -5
+K_NAMES = ["mh", "swap", "adapt", "de", "init", "propose", "accept", "reserved"]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32), ("ndim", C.c_int32), ("nwalkers", C.c_int32),
+        ("ntemps", C.c_int32), ("walker_offset", C.c_int32), ("temp_offset", C.c_int32), ("reserved0", C.c_int32),
+        ("seed", C.c_uint64),
+        ("ladder", _dp), ("mh_temp", _dp), ("cov", _dp),
+        ("ngroups", C.c_int32), ("reserved1", C.c_int32),
+        ("group_offsets", _ip), ("group_indices", _ip),
+        ("ncycle", C.c_int32), ("de_weight", C.c_int32),
+        ("cycle_jump", C.c_int32 * MAX_CYCLE), ("cycle_weight", C.c_int32 * MAX_CYCLE),
+        ("cov_update", C.c_int64), ("burn", C.c_int64), ("tskip", C.c_int64), ("thin", C.c_int64),
+        ("logl_kind", C.c_int32), ("logp_kind", C.c_int32),
+        ("logl_params", _dp), ("logp_params", _dp),
+        ("record_hot", C.c_int32), ("trace", C.c_int32),
+        ("record_rows", C.c_int64), ("trace_iters", C.c_int64),
+        ("timing", C.c_int32), ("reserved2", C.c_int32),
+    ]
+
+
+class Timing(C.Structure):
+    _fields_ = [("launches", C.c_int64 * 8), ("ms", C.c_double * 8), ("chain_steps", C.c_int64)]
+
+
+SYMBOLS = [
+    "ptmcmc_abi_version", "ptmcmc_device_count", "ptmcmc_create_error", "ptmcmc_last_error", "ptmcmc_create",
+    "ptmcmc_destroy", "ptmcmc_set_state", "ptmcmc_set_state_external", "ptmcmc_run", "ptmcmc_propose",
+    "ptmcmc_accept", "ptmcmc_iteration", "ptmcmc_sync", "ptmcmc_get_state", "ptmcmc_rows", "ptmcmc_row_base",
+    "ptmcmc_get_chain", "ptmcmc_release_rows", "ptmcmc_get_adapt", "ptmcmc_get_factor", "ptmcmc_set_factor",
+    "ptmcmc_get_buffers", "ptmcmc_adapt_begin", "ptmcmc_adapt_finish", "ptmcmc_njumps", "ptmcmc_get_counters",
+    "ptmcmc_get_trace", "ptmcmc_get_timing", "ptmcmc_reset_timing", "ptmcmc_stream",
+]
+
+_lib = None
+
+
+def load():
+    """Load libptmcmc_b200.so; raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s is missing: build the CUDA engine with `python -m ptmcmcsampler_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    h = C.c_void_p
+    L.ptmcmc_abi_version.restype = C.c_int32
+    L.ptmcmc_device_count.restype = C.c_int32
+    L.ptmcmc_create_error.restype = C.c_char_p
+    L.ptmcmc_last_error.restype = C.c_char_p
+    L.ptmcmc_last_error.argtypes = [h]
+    L.ptmcmc_create.restype = h
+    L.ptmcmc_create.argtypes = [C.POINTER(Config)]
+    L.ptmcmc_destroy.restype = None
+    L.ptmcmc_destroy.argtypes = [h]
+    L.ptmcmc_set_state.argtypes = [h, _dp]
+    L.ptmcmc_set_state_external.argtypes = [h, _dp, _dp, _dp]
+    L.ptmcmc_run.argtypes = [h, C.c_int64]
+    L.ptmcmc_propose.argtypes = [h, _dp, _ip]
+    L.ptmcmc_accept.argtypes = [h, _dp, _dp, _dp, _dp]
+    L.ptmcmc_iteration.restype = C.c_int64
+    L.ptmcmc_iteration.argtypes = [h]
+    L.ptmcmc_sync.argtypes = [h]
+    L.ptmcmc_get_state.argtypes = [h, _dp, _dp, _dp, _dp]
+    L.ptmcmc_rows.restype = C.c_int64
+    L.ptmcmc_rows.argtypes = [h]
+    L.ptmcmc_row_base.restype = C.c_int64
+    L.ptmcmc_row_base.argtypes = [h]
+    L.ptmcmc_get_chain.argtypes = [h, C.c_int64, C.c_int64, _dp, _dp, _dp]
+    L.ptmcmc_release_rows.argtypes = [h, C.c_int64]
+    L.ptmcmc_get_adapt.argtypes = [h, _dp, _dp, _dp, _i64p]
+    L.ptmcmc_get_factor.argtypes = [h, _dp, _dp]
+    L.ptmcmc_set_factor.argtypes = [h, _dp, _dp]
+    L.ptmcmc_get_buffers.argtypes = [h, _dp, _dp]
+    L.ptmcmc_adapt_begin.argtypes = [h, _dp]
+    L.ptmcmc_adapt_finish.argtypes = [h, _dp]
+    L.ptmcmc_njumps.argtypes = [h]
+    L.ptmcmc_get_counters.argtypes = [h, _i64p, _i64p, _i64p, _i64p]
+    L.ptmcmc_get_trace.argtypes = [h, C.POINTER(C.c_uint8), C.c_int64, C.POINTER(C.c_int16), C.c_int64]
+    L.ptmcmc_get_timing.argtypes = [h, C.POINTER(Timing)]
+    L.ptmcmc_reset_timing.argtypes = [h]
+    L.ptmcmc_stream.restype = C.c_void_p
+    L.ptmcmc_stream.argtypes = [h]
+    for name in SYMBOLS:
+        getattr(L, name)
+    if L.ptmcmc_abi_version() != ABI_VERSION:
+        raise ImportError("libptmcmc_b200.so ABI %d != binding %d" % (L.ptmcmc_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "ptmcmc engine error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Engine(object):
+    """Thin object wrapper over one ptmcmc_engine handle.  Arrays are [T][W][d] numpy float64."""
+
+    def __init__(self, ndim, nwalkers, ntemps, cov, ladder, mh_temp=None, seed=0, groups=None,
+                 cycle=((JUMP_SCAM, 20), (JUMP_AM, 20)), de_weight=20, cov_update=1000, burn=10000, tskip=100,
+                 thin=10, logl_kind=LOGL_GAUSSIAN, logl_params=None, logp_kind=LOGP_UNIFORM, logp_params=None,
+                 record_hot=False, record_rows=1024, trace_iters=0, timing=False, device=0, walker_offset=0,
+                 temp_offset=0):
+        L = load()
+        self._L = L
+        self.d, self.W, self.T = int(ndim), int(nwalkers), int(ntemps)
+        self.cov_update, self.burn, self.thin = int(cov_update), int(burn), int(thin)
+        cfg = Config()
+        cfg.abi_version, cfg.device = ABI_VERSION, int(device)
+        cfg.ndim, cfg.nwalkers, cfg.ntemps = self.d, self.W, self.T
+        cfg.walker_offset, cfg.temp_offset, cfg.seed = int(walker_offset), int(temp_offset), int(seed) & (2**64 - 1)
+        keep = []
+        ladder = np.ascontiguousarray(ladder, dtype=np.float64)
+        cov = np.ascontiguousarray(cov, dtype=np.float64)
+        assert ladder.shape == (self.T,) and cov.shape == (self.d, self.d)
+        keep += [ladder, cov]
+        cfg.ladder, cfg.cov = _d(ladder), _d(cov)
+        if mh_temp is not None:
+            mh_temp = np.ascontiguousarray(mh_temp, dtype=np.float64)
+            keep.append(mh_temp)
+            cfg.mh_temp = _d(mh_temp)
+        if groups is None:
+            self.groups = [np.arange(self.d, dtype=np.int32)]
+            cfg.ngroups = 0
+        else:
+            self.groups = [np.asarray(g, dtype=np.int32) for g in groups]
+            offs = np.zeros(len(self.groups) + 1, dtype=np.int32)
+            offs[1:] = np.cumsum([len(g) for g in self.groups])
+            idx = np.ascontiguousarray(np.concatenate(self.groups), dtype=np.int32)
+            keep += [offs, idx]
+            cfg.ngroups, cfg.group_offsets, cfg.group_indices = len(self.groups), _i(offs), _i(idx)
+        cycle = [(int(j), int(w)) for j, w in cycle]
+        if len(cycle) >= MAX_CYCLE:
+            raise ValueError("at most %d proposal-cycle segments" % (MAX_CYCLE - 1))
+        cfg.ncycle, cfg.de_weight = len(cycle), int(de_weight)
+        for i, (j, w) in enumerate(cycle):
+            cfg.cycle_jump[i], cfg.cycle_weight[i] = j, w
+        cfg.cov_update, cfg.burn, cfg.tskip, cfg.thin = self.cov_update, self.burn, int(tskip), self.thin
+        cfg.logl_kind, cfg.logp_kind = int(logl_kind), int(logp_kind)
+        if logl_params is not None:
+            lpar = np.ascontiguousarray(logl_params, dtype=np.float64)
+            keep.append(lpar)
+            cfg.logl_params = _d(lpar)
+        if logp_params is not None:
+            ppar = np.ascontiguousarray(logp_params, dtype=np.float64)
+            keep.append(ppar)
+            cfg.logp_params = _d(ppar)
+        cfg.record_hot, cfg.record_rows = int(bool(record_hot)), int(record_rows)
+        cfg.trace, cfg.trace_iters = int(trace_iters > 0), int(trace_iters)
+        cfg.timing = int(bool(timing))
+        self.ntr = self.T if record_hot else 1
+        self.usize = sum(len(g) ** 2 for g in self.groups)
+        self.ssize = sum(len(g) for g in self.groups)
+        self._h = L.ptmcmc_create(C.byref(cfg))
+        if not self._h:
+            msg = L.ptmcmc_create_error().decode()
+            if "No jump proposals" in msg:
+                raise ValueError(msg)
+            raise EngineError(ERR_CUDA, msg)
+        self.njumps = L.ptmcmc_njumps(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ptmcmc_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            msg = self._L.ptmcmc_last_error(self._h).decode()
+            if rc == ERR_DE_SHAPE:
+                raise ValueError(msg)
+            raise EngineError(rc, msg)
+        return rc
+
+    def _full(self, x0):
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(x0, dtype=np.float64), (self.T, self.W, self.d)))
+
+    def set_state(self, x0):
+        self._check(self._L.ptmcmc_set_state(self._h, _d(self._full(x0))))
+
+    def set_state_external(self, x0, lnl, lnprior):
+        lnl = np.ascontiguousarray(np.broadcast_to(lnl, (self.T, self.W)), dtype=np.float64)
+        lnprior = np.ascontiguousarray(np.broadcast_to(lnprior, (self.T, self.W)), dtype=np.float64)
+        self._check(self._L.ptmcmc_set_state_external(self._h, _d(self._full(x0)), _d(lnl), _d(lnprior)))
+
+    def run(self, niter):
+        self._check(self._L.ptmcmc_run(self._h, int(niter)))
+
+    def propose(self):
+        q = np.empty((self.T, self.W, self.d))
+        jump = np.empty((self.T, self.W), dtype=np.int32)
+        self._check(self._L.ptmcmc_propose(self._h, _d(q), _i(jump)))
+        return q, jump
+
+    def accept(self, q, qxy, lnl, lnprior):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        qxy = np.ascontiguousarray(qxy, dtype=np.float64)
+        lnl = np.ascontiguousarray(lnl, dtype=np.float64)
+        lnprior = np.ascontiguousarray(lnprior, dtype=np.float64)
+        self._check(self._L.ptmcmc_accept(self._h, _d(q), _d(qxy), _d(lnl), _d(lnprior)))
+
+    @property
+    def iteration(self):
+        return int(self._L.ptmcmc_iteration(self._h))
+
+    def sync(self):
+        self._check(self._L.ptmcmc_sync(self._h))
+
+    def state(self):
+        x = np.empty((self.T, self.W, self.d))
+        lnl, lp, lnp = (np.empty((self.T, self.W)) for _ in range(3))
+        self._check(self._L.ptmcmc_get_state(self._h, _d(x), _d(lnl), _d(lp), _d(lnp)))
+        return x, lnl, lp, lnp
+
+    @property
+    def rows(self):
+        return int(self._L.ptmcmc_rows(self._h))
+
+    @property
+    def row_base(self):
+        return int(self._L.ptmcmc_row_base(self._h))
+
+    def chain(self, row0=None, nrows=None, out=None):
+        row0 = self.row_base if row0 is None else row0
+        nrows = self.rows - row0 if nrows is None else nrows
+        if out is None:
+            ch = np.empty((nrows, self.ntr, self.W, self.d))
+            lnl, lnp = np.empty((nrows, self.ntr, self.W)), np.empty((nrows, self.ntr, self.W))
+        else:
+            ch, lnl, lnp = out
+        self._check(self._L.ptmcmc_get_chain(self._h, row0, nrows, _d(ch), _d(lnl), _d(lnp)))
+        return ch, lnl, lnp
+
+    def release_rows(self, upto_row):
+        self._check(self._L.ptmcmc_release_rows(self._h, int(upto_row)))
+
+    def adapt(self):
+        cov, mu, m2 = np.empty((self.d, self.d)), np.empty(self.d), np.empty((self.d, self.d))
+        n = C.c_int64()
+        self._check(self._L.ptmcmc_get_adapt(self._h, _d(cov), _d(mu), _d(m2), C.byref(n)))
+        return cov, mu, m2, n.value
+
+    def factor(self):
+        U, S = np.empty(self.usize), np.empty(self.ssize)
+        self._check(self._L.ptmcmc_get_factor(self._h, _d(U), _d(S)))
+        return U, S
+
+    def set_factor(self, U, S):
+        U = np.ascontiguousarray(U, dtype=np.float64).ravel()
+        S = np.ascontiguousarray(S, dtype=np.float64).ravel()
+        assert U.size == self.usize and S.size == self.ssize
+        self._check(self._L.ptmcmc_set_factor(self._h, _d(U), _d(S)))
+
+    def buffers(self):
+        am = np.empty((self.cov_update, self.W, self.d))
+        de = np.empty((self.burn, self.W, self.d))
+        self._check(self._L.ptmcmc_get_buffers(self._h, _d(am), _d(de)))
+        return am, de
+
+    def adapt_begin(self):
+        batch = np.empty(1 + self.d + self.d * self.d)
+        rc = self._check(self._L.ptmcmc_adapt_begin(self._h, _d(batch)))
+        return batch if rc == 1 else None
+
+    def adapt_finish(self, batch):
+        batch = np.ascontiguousarray(batch, dtype=np.float64)
+        self._check(self._L.ptmcmc_adapt_finish(self._h, _d(batch)))
+
+    def counters(self):
+        shp = (self.T, self.W, self.njumps)
+        prop, acc = np.empty(shp, dtype=np.int64), np.empty(shp, dtype=np.int64)
+        sw = np.empty((self.T, self.W), dtype=np.int64)
+        n = C.c_int64()
+        p64 = lambda a: a.ctypes.data_as(_i64p)  # noqa: E731
+        self._check(self._L.ptmcmc_get_counters(self._h, p64(prop), p64(acc), p64(sw), C.byref(n)))
+        return prop, acc, sw, n.value
+
+    def trace(self, iters, events=0):
+        tr = np.empty((iters, self.T, self.W), dtype=np.uint8)
+        sm = np.empty((events, self.W, self.T), dtype=np.int16)
+        self._check(self._L.ptmcmc_get_trace(self._h, tr.ctypes.data_as(C.POINTER(C.c_uint8)), iters,
+                                             sm.ctypes.data_as(C.POINTER(C.c_int16)), events))
+        return tr, sm
+
+    def timing(self):
+        t = Timing()
+        self._check(self._L.ptmcmc_get_timing(self._h, C.byref(t)))
+        return dict(launches={K_NAMES[i]: int(t.launches[i]) for i in range(8)},
+                    ms={K_NAMES[i]: float(t.ms[i]) for i in range(8)}, chain_steps=int(t.chain_steps))
+
+    def reset_timing(self):
+        self._check(self._L.ptmcmc_reset_timing(self._h))
+
+    @property
+    def stream(self):
+        return self._L.ptmcmc_stream(self._h)

@@ -1,0 +1,289 @@
+// Pooled adaptive state: running mean / second moment of the cold walkers' samples, covariance,
+// per-group eigen-factor (stand-in for np.linalg.svd of a symmetric PSD block), DE history.
+//
+// Follows ref PTMCMCSampler.py _updateRecursive :769-803 (Welford over the covUpdate buffered
+// rows; here the batch of covUpdate x W pooled samples is reduced in parallel and merged into the
+// running (n, mu, M2) with Chan's formula, which equals the sequential recursion up to rounding),
+// _updateDEbuffer :806-817 and shift_array :27-37.
+#pragma once
+#include "params.h"
+
+namespace ptm {
+
+constexpr int MOM_THREADS = 256;
+constexpr int MOM_TILE = 64;  // walkers per shared-memory tile
+
+// Pass 1: per-block column sums over the AM ring am[slot][k][w].  part[block][k]
+__global__ void __launch_bounds__(MOM_THREADS) moments_sum_kernel(const double *am, int d, int W, long long nslots,
+                                                                  double *part)
+{
+    __shared__ double red[MOM_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < d; ++k) {
+        double s = 0.0;
+        for (long long slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+            const double *row = am + ((size_t)slot * d + k) * W;
+            for (int w = threadIdx.x; w < W; w += blockDim.x) s += row[w];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[warp] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int i = 0; i < MOM_THREADS / 32; ++i) tot += red[i];
+            part[(size_t)blockIdx.x * d + k] = tot;
+        }
+        __syncthreads();
+    }
+}
+
+// mean[k] = (sum over blocks in fixed order) / n
+__global__ void moments_mean_kernel(const double *part, int nblocks, int d, double n, double *batch)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= d) return;
+    double tot = 0.0;
+    for (int b = 0; b < nblocks; ++b) tot += part[(size_t)b * d + k];
+    batch[0] = n;
+    batch[1 + k] = tot / n;
+}
+
+// Pass 2: per-block centred second moments.  part2[block][i*d+j], upper triangle (j >= i)
+__global__ void __launch_bounds__(MOM_THREADS) moments_m2_kernel(const double *am, int d, int W, long long nslots,
+                                                                 const double *batch, double *part2)
+{
+    extern __shared__ double tile[];  // [d][MOM_TILE+1]
+    const int ld = MOM_TILE + 1;
+    const int npairs = d * (d + 1) / 2;
+    const double *mean = batch + 1;
+    // each thread owns pairs p = threadIdx.x, +blockDim.x, ... (at most 8 per thread kept in regs
+    // per pass over the tiles; larger d loops over pair chunks)
+    for (int p0 = 0; p0 < npairs; p0 += MOM_THREADS * 8) {
+        double acc[8];
+        int pi[8], pj[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            acc[a] = 0.0;
+            int pidx = p0 + a * MOM_THREADS + threadIdx.x;
+            pi[a] = -1; pj[a] = 0;
+            if (pidx < npairs) {
+                // invert the row-major upper-triangular index
+                int i = 0, rem = pidx;
+                while (rem >= d - i) { rem -= d - i; ++i; }
+                pi[a] = i; pj[a] = i + rem;
+            }
+        }
+        const long long ntiles_w = (W + MOM_TILE - 1) / MOM_TILE;
+        for (long long tidx = blockIdx.x; tidx < nslots * ntiles_w; tidx += gridDim.x) {
+            const long long slot = tidx / ntiles_w;
+            const int w0 = (int)(tidx % ntiles_w) * MOM_TILE;
+            const int nw = min(MOM_TILE, W - w0);
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < d * MOM_TILE; idx += blockDim.x) {
+                const int k = idx / MOM_TILE, ww = idx % MOM_TILE;
+                tile[k * ld + ww] = (ww < nw) ? am[((size_t)slot * d + k) * W + w0 + ww] - mean[k] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                if (pi[a] >= 0) {
+                    const double *ri = tile + pi[a] * ld, *rj = tile + pj[a] * ld;
+                    double s = acc[a];
+                    for (int ww = 0; ww < MOM_TILE; ++ww) s = fma(ri[ww], rj[ww], s);
+                    acc[a] = s;
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+            if (pi[a] >= 0) part2[(size_t)blockIdx.x * d * d + pi[a] * d + pj[a]] = acc[a];
+    }
+}
+
+// batch[1+d + i*d+j] = sum over blocks (fixed order), symmetrised
+__global__ void moments_m2_reduce_kernel(const double *part2, int nblocks, int d, double *batch)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= d * d) return;
+    const int i = idx / d, j = idx % d;
+    const int a = i <= j ? i : j, b = i <= j ? j : i;
+    double tot = 0.0;
+    for (int k = 0; k < nblocks; ++k) tot += part2[(size_t)k * d * d + a * d + b];
+    batch[1 + d + idx] = tot;
+}
+
+// Cyclic Jacobi eigen-decomposition of the n x n symmetric matrix a (destroyed); v receives the
+// eigenvectors.  One thread block; rotations are applied by n threads in parallel, in the same
+// (p, q) order and with the same formulas as the CPU oracle's orc_sym_factor.
+__device__ inline void jacobi_block(int n, double *a, double *v, double *scratch)
+{
+    const int r = threadIdx.x;
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) v[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        if (threadIdx.x == 0) {
+            double off = 0.0;
+            for (int p = 0; p < n; ++p)
+                for (int q = p + 1; q < n; ++q) off += fabs(a[p * n + q]);
+            scratch[0] = off;
+        }
+        __syncthreads();
+        if (scratch[0] == 0.0) break;
+        __syncthreads();
+        for (int p = 0; p < n - 1; ++p) {
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = a[p * n + q], app = a[p * n + p], aqq = a[q * n + q];
+                const double g = 100.0 * fabs(apq);
+                __syncthreads();  // everyone has read the pivot entries
+                if (sweep > 3 && fabs(app) + g == fabs(app) && fabs(aqq) + g == fabs(aqq)) {
+                    if (threadIdx.x == 0) { a[p * n + q] = 0.0; a[q * n + p] = 0.0; }
+                    __syncthreads();
+                    continue;
+                }
+                if (apq == 0.0) continue;
+                const double h = aqq - app;
+                double t;
+                if (fabs(h) + g == fabs(h)) {
+                    t = apq / h;
+                } else {
+                    const double theta = 0.5 * h / apq;
+                    t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+                    if (theta < 0.0) t = -t;
+                }
+                const double c = 1.0 / sqrt(1.0 + t * t);
+                const double sn = t * c;
+                const double tau = sn / (1.0 + c);
+                if (r < n) {
+                    if (r != p && r != q) {
+                        const double arp = a[r * n + p], arq = a[r * n + q];
+                        const double nrp = arp - sn * (arq + tau * arp);
+                        const double nrq = arq + sn * (arp - tau * arq);
+                        a[r * n + p] = nrp; a[p * n + r] = nrp;
+                        a[r * n + q] = nrq; a[q * n + r] = nrq;
+                    }
+                    const double vrp = v[r * n + p], vrq = v[r * n + q];
+                    v[r * n + p] = vrp - sn * (vrq + tau * vrp);
+                    v[r * n + q] = vrq + sn * (vrp - tau * vrq);
+                }
+                if (threadIdx.x == 0) {
+                    a[p * n + p] = app - t * apq;
+                    a[q * n + q] = aqq + t * apq;
+                    a[p * n + q] = 0.0;
+                    a[q * n + p] = 0.0;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+}
+
+struct FactorArgs {
+    int d, ngroups;
+    const int *goff, *gidx, *uoff, *soff;
+    double *cov, *mu, *m2;      // running state (updated in place)
+    const double *batch;        // {n_b, mean_b[d], M2c_b[d*d]} or NULL to factor cov as is
+    double n_prev;              // samples already in (mu, m2)
+    int reset;                  // it == 0 in ref :781-783: forget the running state first
+    double *U, *S, *sqrtS;      // outputs, concatenated per group
+    double *work_a, *work_v;    // [dmax*dmax] scratch each
+    int *ord;                   // [dmax] scratch
+};
+
+// One block: merge the batch into the running moments (ref :785-794), then factor every group
+// (ref :797-803): eigenvalues by descending magnitude (ties keep index order), S = |lambda|, each
+// eigenvector's largest-magnitude component made positive.
+__global__ void __launch_bounds__(128) adapt_finalize_kernel(const FactorArgs f)
+{
+    __shared__ double scratch[2];
+    const int d = f.d;
+    if (f.batch) {
+        const double nb = f.batch[0];
+        const double *mb = f.batch + 1, *m2b = f.batch + 1 + d;
+        const double na = f.reset ? 0.0 : f.n_prev;
+        const double ntot = na + nb;
+        for (int idx = threadIdx.x; idx < d * d; idx += blockDim.x) {
+            const int i = idx / d, j = idx % d;
+            const double mai = f.reset ? 0.0 : f.mu[i], maj = f.reset ? 0.0 : f.mu[j];
+            const double di = mb[i] - mai, dj = mb[j] - maj;
+            const double m2a = f.reset ? 0.0 : f.m2[idx];
+            const double m2 = m2a + m2b[idx] + di * dj * (na * nb / ntot);
+            f.m2[idx] = m2;
+            f.cov[idx] = m2 / (ntot - 1.0);
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < d; k += blockDim.x) {
+            const double ma = f.reset ? 0.0 : f.mu[k];
+            f.mu[k] = ma + (mb[k] - ma) * (nb / ntot);
+        }
+        __syncthreads();
+    }
+    for (int g = 0; g < f.ngroups; ++g) {
+        const int g0 = f.goff[g], n = f.goff[g + 1] - g0;
+        const int *gi = f.gidx + g0;
+        double *a = f.work_a, *v = f.work_v;
+        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x)
+            a[idx] = f.cov[gi[idx / n] * d + gi[idx % n]];
+        __syncthreads();
+        jacobi_block(n, a, v, scratch);
+        if (threadIdx.x == 0) {
+            int *ord = f.ord;
+            for (int i = 0; i < n; ++i) ord[i] = i;
+            for (int i = 0; i < n; ++i) {
+                int best = i;
+                for (int j = i + 1; j < n; ++j)
+                    if (fabs(a[ord[j] * n + ord[j]]) > fabs(a[ord[best] * n + ord[best]])) best = j;
+                const int tmp = ord[best];
+                for (int j = best; j > i; --j) ord[j] = ord[j - 1];
+                ord[i] = tmp;
+            }
+        }
+        __syncthreads();
+        double *U = f.U + f.uoff[g], *S = f.S + f.soff[g], *sS = f.sqrtS + f.soff[g];
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const int src = f.ord[k];
+            const double lam = fabs(a[src * n + src]);
+            S[k] = lam;
+            sS[k] = sqrt(lam);
+            int big = 0;
+            for (int r = 1; r < n; ++r)
+                if (fabs(v[r * n + src]) > fabs(v[big * n + src])) big = r;
+            const double sg = (v[big * n + src] < 0.0) ? -1.0 : 1.0;
+            for (int r = 0; r < n; ++r) U[r * n + k] = sg * v[r * n + src];
+        }
+        __syncthreads();
+    }
+}
+
+// sqrtS = sqrt(S) after a host-supplied factor (ptmcmc_set_factor)
+__global__ void sqrt_kernel(const double *S, double *sqrtS, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sqrtS[i] = sqrt(S[i]);
+}
+
+// DE history append (ref :806-817): the reference shifts the buffer left by covUpdate rows and
+// copies the AM buffer into the freed tail; here the history is a ring (head advances by
+// covUpdate slots) and the AM ring am[slot][k][w] is transposed into de[slot'][w][k].
+__global__ void __launch_bounds__(256) de_append_kernel(const double *am, double *de, int d, int W, long long cu,
+                                                        long long burn, long long new_head)
+{
+    __shared__ double tile[32][33];
+    // grid: (ceil(W/32), ceil(d/32), cu)
+    const long long slot = blockIdx.z;
+    const long long dst_slot = (new_head + (burn - cu) + slot) % burn;
+    const int w0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int kk = ty; kk < 32; kk += 8) {
+        const int k = k0 + kk, w = w0 + tx;
+        tile[kk][tx] = (k < d && w < W) ? am[((size_t)slot * d + k) * W + w] : 0.0;
+    }
+    __syncthreads();
+    for (int ww = ty; ww < 32; ww += 8) {
+        const int w = w0 + ww, k = k0 + tx;
+        if (w < W && k < d) de[((size_t)dst_slot * W + w) * d + k] = tile[tx][ww];
+    }
+}
+
+}  // namespace ptm

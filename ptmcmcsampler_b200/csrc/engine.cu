@@ -1,0 +1,903 @@
+// Host side of the B200 PT-MCMC engine and its C ABI (include/ptmcmc_b200.h).
+//
+// Owns the device-resident state of W walkers x T temperatures and sequences the kernels of one
+// reference iteration (ref PTMCMCSampler.py PTMCMCOneStep :530-629): covariance update -> DE
+// history update -> fused MH segment -> swap -> buffers/record.  Everything is enqueued on one
+// CUDA stream; nothing in ptmcmc_run synchronises with the host.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ptmcmc_b200.h"
+#include "adapt_kernels.cuh"
+#include "mh_kernels.cuh"
+#include "params.h"
+#include "swap_kernels.cuh"
+
+using namespace ptm;
+
+static_assert(PTMCMC_MAX_CYCLE == MAX_CYCLE, "cycle capacity mismatch");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Engine {
+    ptmcmc_config cfg{};
+    int d = 0, W = 0, T = 0, ngroups = 0, njumps = 3, ntr = 1;
+    bool identity_group = true, has_state = false, de_in_cycle = false;
+    std::vector<double> ladder, mh_temp;
+    std::vector<int> goff, gidx, uoff, soff;
+    std::vector<int> cyc_jump, cyc_w;
+    long long iter = 0, rows = 0, rec_base = 0, de_head = 0, swap_proposed = 0, swap_events = 0;
+    long long adapt_done_iter = -1;  // boundary iteration whose covariance update already ran
+    long long nsamp = 0;
+    bool pending_propose = false;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    // device memory
+    double *x[2] = {nullptr, nullptr}, *lnl[2] = {nullptr, nullptr}, *lp[2] = {nullptr, nullptr};
+    int cur = 0;
+    double *d_ladder = nullptr, *d_mh_temp = nullptr;
+    double *d_cov = nullptr, *d_mu = nullptr, *d_m2 = nullptr, *d_U = nullptr, *d_S = nullptr, *d_sqrtS = nullptr;
+    int *d_goff = nullptr, *d_gidx = nullptr, *d_uoff = nullptr, *d_soff = nullptr, *d_ord = nullptr;
+    double *d_work_a = nullptr, *d_work_v = nullptr;
+    double *d_am = nullptr, *d_de = nullptr;
+    double *d_gmu = nullptr, *d_gP = nullptr, *d_plo = nullptr, *d_phi = nullptr;
+    double g_offset = 0.0, p_inside = 0.0;
+    int p_inclusive = 1;
+    double *d_rec_x = nullptr, *d_rec_lnl = nullptr, *d_rec_lnp = nullptr;
+    unsigned long long *d_prop = nullptr, *d_acc = nullptr, *d_swap_acc = nullptr;
+    unsigned char *d_trace = nullptr;
+    short *d_swapmaps = nullptr;
+    int *d_map = nullptr;
+    double *d_part = nullptr, *d_part2 = nullptr, *d_batch = nullptr;
+    int mom_blocks = 0;
+    // host-callback path staging
+    double *d_q = nullptr, *d_qxy = nullptr, *d_lnl_new = nullptr, *d_lp_new = nullptr;
+    int *d_jump = nullptr;
+    unsigned *d_wordpos = nullptr;
+    // timing
+    ptmcmc_timing tm{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+};
+
+int fail(Engine *e, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(e, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t _st = (call);                                                                  \
+        if (_st != cudaSuccess)                                                                    \
+            return fail(e, PTMCMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t n)
+{
+    cudaError_t st = cudaMalloc((void **)p, sizeof(T) * (n ? n : 1));
+    if (st == cudaSuccess) st = cudaMemset(*p, 0, sizeof(T) * (n ? n : 1));
+    return st;
+}
+
+DevParams make_params(const Engine *e)
+{
+    DevParams p{};
+    p.d = e->d; p.W = e->W; p.T = e->T;
+    p.walker_offset = e->cfg.walker_offset; p.temp_offset = e->cfg.temp_offset;
+    p.ngroups = e->ngroups; p.identity_group = e->identity_group; p.njumps = e->njumps;
+    p.seed = e->cfg.seed;
+    p.x = e->x[e->cur]; p.lnl = e->lnl[e->cur]; p.lp = e->lp[e->cur];
+    p.mh_temp = e->d_mh_temp; p.ladder = e->d_ladder;
+    p.U = e->d_U; p.sqrtS = e->d_sqrtS;
+    p.goff = e->d_goff; p.gidx = e->d_gidx; p.uoff = e->d_uoff; p.soff = e->d_soff;
+    p.ncycle = (int)e->cyc_jump.size();
+    int cum = 0;
+    for (int i = 0; i < p.ncycle; ++i) {
+        cum += e->cyc_w[i];
+        p.cyc_jump[i] = e->cyc_jump[i];
+        p.cyc_cum[i] = cum;
+    }
+    p.total_weight = cum;
+    p.am = e->d_am; p.de = e->d_de;
+    p.cov_update = e->cfg.cov_update; p.burn = e->cfg.burn; p.de_head = e->de_head;
+    p.logl_kind = e->cfg.logl_kind; p.logp_kind = e->cfg.logp_kind; p.p_inclusive = e->p_inclusive;
+    p.g_mu = e->d_gmu; p.g_P = e->d_gP; p.g_offset = e->g_offset; p.p_inside = e->p_inside;
+    p.p_lo = e->d_plo; p.p_hi = e->d_phi;
+    p.rec_x = e->d_rec_x; p.rec_lnl = e->d_rec_lnl; p.rec_lnp = e->d_rec_lnp;
+    p.rec_base = e->rec_base; p.rec_cap = e->cfg.record_rows; p.thin = e->cfg.thin; p.ntr = e->ntr;
+    p.prop = e->d_prop; p.acc = e->d_acc; p.swap_acc = e->d_swap_acc;
+    p.trace = e->d_trace; p.trace_cap = e->cfg.trace ? e->cfg.trace_iters : 0;
+    return p;
+}
+
+struct LaunchTimer {
+    Engine *e;
+    int cls;
+    LaunchTimer(Engine *e_, int cls_, int nlaunch = 1) : e(e_), cls(cls_)
+    {
+        e->tm.launches[cls] += nlaunch;
+        if (e->cfg.timing) cudaEventRecord(e->ev0, e->stream);
+    }
+    ~LaunchTimer()
+    {
+        if (e->cfg.timing) {
+            cudaEventRecord(e->ev1, e->stream);
+            cudaEventSynchronize(e->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+            e->tm.ms[cls] += ms;
+        }
+    }
+};
+
+int chain_blocks(const Engine *e) { return (int)(((long long)e->T * e->W + MH_THREADS - 1) / MH_THREADS); }
+
+bool fast_reg_path(const Engine *e) { return e->identity_group && e->d <= MAX_REG_DIM; }
+
+template <int DP>
+cudaError_t launch_reg(const Engine *e, const DevParams &p)
+{
+    const size_t smem = sizeof(double) * (2 * DP * DP + 4 * DP);
+    static bool attr_done = false;
+    if (!attr_done && smem > 48 * 1024) {
+        cudaFuncSetAttribute(mh_reg_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
+    mh_reg_kernel<DP><<<chain_blocks(e), MH_THREADS, smem, e->stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mh(Engine *e, long long it0, long long it1, bool tail)
+{
+    DevParams p = make_params(e);
+    p.it0 = it0; p.it1 = it1; p.tail = tail ? 1 : 0;
+    LaunchTimer lt(e, PTMCMC_K_MH);
+    e->tm.chain_steps += (it1 - it0 + 1) * (long long)e->T * e->W;
+    if (fast_reg_path(e)) {
+        const int d = e->d;
+        if (d <= 4) return launch_reg<4>(e, p);
+        if (d <= 8) return launch_reg<8>(e, p);
+        if (d <= 12) return launch_reg<12>(e, p);
+        if (d <= 16) return launch_reg<16>(e, p);
+        if (d <= 20) return launch_reg<20>(e, p);
+        if (d <= 24) return launch_reg<24>(e, p);
+        return launch_reg<32>(e, p);
+    }
+    mh_generic_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ref :631-697 + :627 for the iteration `it` that has just been stepped
+cudaError_t launch_swap(Engine *e, long long it)
+{
+    DevParams p = make_params(e);
+    LaunchTimer lt(e, PTMCMC_K_SWAP, 2);
+    short *tr = nullptr;
+    if (e->d_swapmaps && e->swap_events < e->cfg.trace_iters) tr = e->d_swapmaps + (size_t)e->swap_events * e->W * e->T;
+    swap_decide_kernel<<<(e->W + 127) / 128, 128, 0, e->stream>>>(p, it, e->d_map, tr);
+    const int nxt = e->cur ^ 1;
+    swap_apply_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, it, e->d_map, e->x[nxt], e->lnl[nxt], e->lp[nxt]);
+    e->cur = nxt;
+    e->swap_proposed++;
+    e->swap_events++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_factor(Engine *e, const double *batch, double n_prev, int reset)
+{
+    FactorArgs f{};
+    f.d = e->d; f.ngroups = e->ngroups;
+    f.goff = e->d_goff; f.gidx = e->d_gidx; f.uoff = e->d_uoff; f.soff = e->d_soff;
+    f.cov = e->d_cov; f.mu = e->d_mu; f.m2 = e->d_m2;
+    f.batch = batch; f.n_prev = n_prev; f.reset = reset;
+    f.U = e->d_U; f.S = e->d_S; f.sqrtS = e->d_sqrtS;
+    f.work_a = e->d_work_a; f.work_v = e->d_work_v; f.ord = e->d_ord;
+    adapt_finalize_kernel<<<1, 128, 0, e->stream>>>(f);
+    return cudaGetLastError();
+}
+
+// local batch moments of the AM ring into d_batch = {n, mean, M2c}
+cudaError_t launch_batch_moments(Engine *e)
+{
+    const int d = e->d, W = e->W;
+    const long long cu = e->cfg.cov_update;
+    const double n = (double)cu * (double)W;
+    moments_sum_kernel<<<e->mom_blocks, MOM_THREADS, 0, e->stream>>>(e->d_am, d, W, cu, e->d_part);
+    moments_mean_kernel<<<(d + 127) / 128, 128, 0, e->stream>>>(e->d_part, e->mom_blocks, d, n, e->d_batch);
+    const size_t smem = sizeof(double) * d * (MOM_TILE + 1);
+    moments_m2_kernel<<<e->mom_blocks, MOM_THREADS, smem, e->stream>>>(e->d_am, d, W, cu, e->d_batch, e->d_part2);
+    moments_m2_reduce_kernel<<<(d * d + 127) / 128, 128, 0, e->stream>>>(e->d_part2, e->mom_blocks, d, e->d_batch);
+    return cudaGetLastError();
+}
+
+// ref :545-560 at the start of iteration it0 (boundary = it0-1)
+cudaError_t cov_update(Engine *e, long long boundary)
+{
+    LaunchTimer lt(e, PTMCMC_K_ADAPT, 5);
+    cudaError_t st = launch_batch_moments(e);
+    if (st != cudaSuccess) return st;
+    const long long it = boundary - e->cfg.cov_update;  // ref :778
+    st = launch_factor(e, e->d_batch, (double)it * (double)e->W, it == 0);
+    e->nsamp = boundary * (long long)e->W;
+    e->adapt_done_iter = boundary;
+    return st;
+}
+
+// ref :563-585 at the start of iteration it0
+int de_update(Engine *e)
+{
+    const long long cu = e->cfg.cov_update, burn = e->cfg.burn;
+    if (cu > burn)
+        return fail(e, PTMCMC_ERR_DE_SHAPE,
+                    "could not broadcast AM buffer of %lld rows into a DE buffer of %lld rows (covUpdate > burn)",
+                    cu, burn);
+    {
+        LaunchTimer lt(e, PTMCMC_K_DE);
+        const long long new_head = (e->de_head + cu) % burn;
+        dim3 grid((e->W + 31) / 32, (e->d + 31) / 32, (unsigned)cu);
+        de_append_kernel<<<grid, 256, 0, e->stream>>>(e->d_am, e->d_de, e->d, e->W, cu, burn, new_head);
+        e->de_head = new_head;
+    }
+    if (!e->de_in_cycle && e->cfg.de_weight > 0) {
+        e->cyc_jump.push_back(PTMCMC_JUMP_DE);
+        e->cyc_w.push_back(e->cfg.de_weight);
+        e->de_in_cycle = true;
+    }
+    cudaError_t st = cudaGetLastError();
+    if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "de_append_kernel: %s", cudaGetErrorString(st));
+    return 0;
+}
+
+// maintenance at the start of iteration it0 (ref :545-585)
+int maintenance(Engine *e, long long it0)
+{
+    const long long b = it0 - 1;
+    if (b != 0 && b % e->cfg.cov_update == 0 && e->cfg.temp_offset == 0 && e->adapt_done_iter != b) {
+        cudaError_t st = cov_update(e, b);
+        if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "covariance update: %s", cudaGetErrorString(st));
+    }
+    if (b != 0 && b % e->cfg.burn == 0) {
+        int rc = de_update(e);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+long long next_multiple(long long it, long long m) { return ((it + m - 1) / m) * m; }
+
+int check_rows(Engine *e, long long end_iter)
+{
+    const long long last_row = end_iter / e->cfg.thin;
+    if (last_row - e->rec_base >= e->cfg.record_rows)
+        return fail(e, PTMCMC_ERR_CAPACITY, "record window holds rows [%lld, %lld); iteration %lld needs row %lld",
+                    e->rec_base, e->rec_base + e->cfg.record_rows, end_iter, last_row);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t ptmcmc_abi_version(void) { return PTMCMC_ABI_VERSION; }
+
+int32_t ptmcmc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *ptmcmc_create_error(void) { return g_create_error.c_str(); }
+const char *ptmcmc_last_error(const ptmcmc_engine *h) { return h ? ((const Engine *)h)->err.c_str() : ""; }
+
+static int create_impl(Engine *e, const ptmcmc_config *cfg)
+{
+    e->cfg = *cfg;
+    const int d = e->d = cfg->ndim, W = e->W = cfg->nwalkers, T = e->T = cfg->ntemps;
+    if (cfg->abi_version != PTMCMC_ABI_VERSION) return fail(nullptr, PTMCMC_ERR_ARG, "ABI version mismatch");
+    if (d < 1 || d > MAX_GENERIC_DIM) return fail(nullptr, PTMCMC_ERR_ARG, "ndim must be in [1, %d]", MAX_GENERIC_DIM);
+    if (W < 1 || T < 1) return fail(nullptr, PTMCMC_ERR_ARG, "nwalkers and ntemps must be >= 1");
+    if (T > 32767) return fail(nullptr, PTMCMC_ERR_ARG, "ntemps must be < 32768");
+    if (cfg->cov_update < 1 || cfg->burn < 1 || cfg->tskip < 1 || cfg->thin < 1)
+        return fail(nullptr, PTMCMC_ERR_ARG, "covUpdate, burn, Tskip and thin must be >= 1");
+    if (!cfg->ladder || !cfg->cov) return fail(nullptr, PTMCMC_ERR_ARG, "ladder and cov are required");
+    if (cfg->ncycle < 1 || cfg->ncycle >= PTMCMC_MAX_CYCLE) return fail(nullptr, PTMCMC_ERR_ARG, "No jump proposals specified!");
+    if (cfg->record_rows < 1) return fail(nullptr, PTMCMC_ERR_ARG, "record_rows must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, PTMCMC_ERR_CUDA, "no CUDA device: the PT-MCMC engine has no CPU path");
+    CUDA_TRY(nullptr, cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
+    e->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_TRY(nullptr, cudaEventCreate(&e->ev0));
+    CUDA_TRY(nullptr, cudaEventCreate(&e->ev1));
+    e->ladder.assign(cfg->ladder, cfg->ladder + T);
+    e->mh_temp.assign(cfg->mh_temp ? cfg->mh_temp : cfg->ladder, (cfg->mh_temp ? cfg->mh_temp : cfg->ladder) + T);
+    // groups (ref :129-131)
+    if (cfg->ngroups <= 0 || !cfg->group_offsets) {
+        e->ngroups = 1;
+        e->goff = {0, d};
+        e->gidx.resize(d);
+        for (int i = 0; i < d; ++i) e->gidx[i] = i;
+    } else {
+        e->ngroups = cfg->ngroups;
+        e->goff.assign(cfg->group_offsets, cfg->group_offsets + cfg->ngroups + 1);
+        e->gidx.assign(cfg->group_indices, cfg->group_indices + e->goff[cfg->ngroups]);
+        for (int v : e->gidx)
+            if (v < 0 || v >= d) return fail(nullptr, PTMCMC_ERR_ARG, "group index %d out of range", v);
+    }
+    e->identity_group = (e->ngroups == 1 && e->goff[1] == d);
+    if (e->identity_group)
+        for (int i = 0; i < d; ++i) e->identity_group = e->identity_group && e->gidx[i] == i;
+    e->uoff.assign(e->ngroups + 1, 0);
+    e->soff.assign(e->ngroups + 1, 0);
+    int dmax = 0;
+    for (int g = 0; g < e->ngroups; ++g) {
+        const int dg = e->goff[g + 1] - e->goff[g];
+        if (dg < 1) return fail(nullptr, PTMCMC_ERR_ARG, "empty parameter group");
+        e->uoff[g + 1] = e->uoff[g] + dg * dg;
+        e->soff[g + 1] = e->soff[g] + dg;
+        dmax = dg > dmax ? dg : dmax;
+    }
+    // cycle (ref :1007-1008); zero weights are silently dropped (ref :1001-1004)
+    e->njumps = 3;
+    for (int i = 0; i < cfg->ncycle; ++i) {
+        if (cfg->cycle_weight[i] <= 0) continue;
+        e->cyc_jump.push_back(cfg->cycle_jump[i]);
+        e->cyc_w.push_back(cfg->cycle_weight[i]);
+        if (cfg->cycle_jump[i] + 1 > e->njumps) e->njumps = cfg->cycle_jump[i] + 1;
+        if (cfg->cycle_jump[i] == PTMCMC_JUMP_DE) e->de_in_cycle = true;
+    }
+    if (e->cyc_jump.empty()) return fail(nullptr, PTMCMC_ERR_ARG, "No jump proposals specified!");
+    e->ntr = cfg->record_hot ? T : 1;
+    const size_t C = (size_t)T * W;
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(nullptr, dalloc(&e->x[b], C * d));
+        CUDA_TRY(nullptr, dalloc(&e->lnl[b], C));
+        CUDA_TRY(nullptr, dalloc(&e->lp[b], C));
+    }
+    CUDA_TRY(nullptr, dalloc(&e->d_ladder, T));
+    CUDA_TRY(nullptr, dalloc(&e->d_mh_temp, T));
+    CUDA_TRY(nullptr, cudaMemcpy(e->d_ladder, e->ladder.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+    CUDA_TRY(nullptr, cudaMemcpy(e->d_mh_temp, e->mh_temp.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+    CUDA_TRY(nullptr, dalloc(&e->d_cov, (size_t)d * d));
+    CUDA_TRY(nullptr, dalloc(&e->d_mu, d));
+    CUDA_TRY(nullptr, dalloc(&e->d_m2, (size_t)d * d));
+    CUDA_TRY(nullptr, dalloc(&e->d_U, e->uoff[e->ngroups]));
+    CUDA_TRY(nullptr, dalloc(&e->d_S, e->soff[e->ngroups]));
+    CUDA_TRY(nullptr, dalloc(&e->d_sqrtS, e->soff[e->ngroups]));
+    CUDA_TRY(nullptr, dalloc(&e->d_goff, e->goff.size()));
+    CUDA_TRY(nullptr, dalloc(&e->d_gidx, e->gidx.size()));
+    CUDA_TRY(nullptr, dalloc(&e->d_uoff, e->uoff.size()));
+    CUDA_TRY(nullptr, dalloc(&e->d_soff, e->soff.size()));
+    CUDA_TRY(nullptr, dalloc(&e->d_ord, dmax));
+    CUDA_TRY(nullptr, dalloc(&e->d_work_a, (size_t)dmax * dmax));
+    CUDA_TRY(nullptr, dalloc(&e->d_work_v, (size_t)dmax * dmax));
+    CUDA_TRY(nullptr, cudaMemcpy(e->d_goff, e->goff.data(), sizeof(int) * e->goff.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(nullptr, cudaMemcpy(e->d_gidx, e->gidx.data(), sizeof(int) * e->gidx.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(nullptr, cudaMemcpy(e->d_uoff, e->uoff.data(), sizeof(int) * e->uoff.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(nullptr, cudaMemcpy(e->d_soff, e->soff.data(), sizeof(int) * e->soff.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(nullptr, cudaMemcpy(e->d_cov, cfg->cov, sizeof(double) * d * d, cudaMemcpyHostToDevice));
+    CUDA_TRY(nullptr, dalloc(&e->d_am, (size_t)cfg->cov_update * d * W));  // ref :220
+    CUDA_TRY(nullptr, dalloc(&e->d_de, (size_t)cfg->burn * W * d));        // ref :221
+    // targets
+    if (cfg->logl_kind == PTMCMC_LOGL_GAUSSIAN) {
+        if (!cfg->logl_params) return fail(nullptr, PTMCMC_ERR_ARG, "Gaussian log-likelihood needs parameters");
+        const double *mu = cfg->logl_params, *A = mu + d;
+        e->g_offset = A[(size_t)d * d];
+        // -0.5 * x^T A x folded to the upper triangle: P_ii = -A_ii/2, P_ij = -(A_ij + A_ji)/2 (j > i)
+        std::vector<double> P((size_t)d * d, 0.0);
+        for (int i = 0; i < d; ++i) {
+            P[(size_t)i * d + i] = -0.5 * A[(size_t)i * d + i];
+            for (int j = i + 1; j < d; ++j) P[(size_t)i * d + j] = -0.5 * (A[(size_t)i * d + j] + A[(size_t)j * d + i]);
+        }
+        CUDA_TRY(nullptr, dalloc(&e->d_gmu, d));
+        CUDA_TRY(nullptr, dalloc(&e->d_gP, (size_t)d * d));
+        CUDA_TRY(nullptr, cudaMemcpy(e->d_gmu, mu, sizeof(double) * d, cudaMemcpyHostToDevice));
+        CUDA_TRY(nullptr, cudaMemcpy(e->d_gP, P.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice));
+    } else if (cfg->logl_kind == PTMCMC_LOGL_CURVED) {
+        if (d % 2) return fail(nullptr, PTMCMC_ERR_ARG, "curved log-likelihood needs an even ndim");
+    } else if (cfg->logl_kind != PTMCMC_LOGL_ROSENBROCK && cfg->logl_kind != PTMCMC_LOGL_EXTERNAL) {
+        return fail(nullptr, PTMCMC_ERR_ARG, "unknown logl_kind %d", cfg->logl_kind);
+    }
+    if (cfg->logp_kind == PTMCMC_LOGP_UNIFORM) {
+        if (!cfg->logp_params) return fail(nullptr, PTMCMC_ERR_ARG, "uniform log-prior needs parameters");
+        CUDA_TRY(nullptr, dalloc(&e->d_plo, d));
+        CUDA_TRY(nullptr, dalloc(&e->d_phi, d));
+        CUDA_TRY(nullptr, cudaMemcpy(e->d_plo, cfg->logp_params, sizeof(double) * d, cudaMemcpyHostToDevice));
+        CUDA_TRY(nullptr, cudaMemcpy(e->d_phi, cfg->logp_params + d, sizeof(double) * d, cudaMemcpyHostToDevice));
+        e->p_inside = cfg->logp_params[2 * d];
+        e->p_inclusive = cfg->logp_params[2 * d + 1] != 0.0;
+    } else if (cfg->logp_kind != PTMCMC_LOGP_FLAT && cfg->logp_kind != PTMCMC_LOGP_EXTERNAL) {
+        return fail(nullptr, PTMCMC_ERR_ARG, "unknown logp_kind %d", cfg->logp_kind);
+    }
+    // record window, counters, trace
+    const size_t rrows = (size_t)cfg->record_rows * e->ntr * W;
+    CUDA_TRY(nullptr, dalloc(&e->d_rec_x, rrows * d));
+    CUDA_TRY(nullptr, dalloc(&e->d_rec_lnl, rrows));
+    CUDA_TRY(nullptr, dalloc(&e->d_rec_lnp, rrows));
+    CUDA_TRY(nullptr, dalloc(&e->d_prop, C * e->njumps));
+    CUDA_TRY(nullptr, dalloc(&e->d_acc, C * e->njumps));
+    CUDA_TRY(nullptr, dalloc(&e->d_swap_acc, C));
+    CUDA_TRY(nullptr, dalloc(&e->d_map, C));
+    if (cfg->trace) {
+        CUDA_TRY(nullptr, dalloc(&e->d_trace, (size_t)cfg->trace_iters * C));
+        CUDA_TRY(nullptr, dalloc(&e->d_swapmaps, (size_t)cfg->trace_iters * C));
+    }
+    e->mom_blocks = 2 * e->sm_count;
+    CUDA_TRY(nullptr, dalloc(&e->d_part, (size_t)e->mom_blocks * d));
+    CUDA_TRY(nullptr, dalloc(&e->d_part2, (size_t)e->mom_blocks * d * d));
+    CUDA_TRY(nullptr, dalloc(&e->d_batch, (size_t)1 + d + (size_t)d * d));
+    {
+        const size_t smem = sizeof(double) * d * (MOM_TILE + 1);
+        if (smem > 48 * 1024)
+            CUDA_TRY(nullptr, cudaFuncSetAttribute(moments_m2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const bool external = cfg->logl_kind == PTMCMC_LOGL_EXTERNAL || cfg->logp_kind == PTMCMC_LOGP_EXTERNAL || e->njumps > 3;
+    if (external) {
+        CUDA_TRY(nullptr, dalloc(&e->d_q, C * d));
+        CUDA_TRY(nullptr, dalloc(&e->d_qxy, C));
+        CUDA_TRY(nullptr, dalloc(&e->d_lnl_new, C));
+        CUDA_TRY(nullptr, dalloc(&e->d_lp_new, C));
+        CUDA_TRY(nullptr, dalloc(&e->d_jump, C));
+        CUDA_TRY(nullptr, dalloc(&e->d_wordpos, C));
+    }
+    // initial factor (ref :138-145)
+    cudaError_t st = launch_factor(e, nullptr, 0.0, 0);
+    if (st != cudaSuccess) return fail(nullptr, PTMCMC_ERR_CUDA, "initial factorisation: %s", cudaGetErrorString(st));
+    e->tm.launches[PTMCMC_K_ADAPT] += 1;
+    CUDA_TRY(nullptr, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+ptmcmc_engine *ptmcmc_create(const ptmcmc_config *cfg)
+{
+    g_create_error.clear();
+    if (!cfg) {
+        fail(nullptr, PTMCMC_ERR_ARG, "null config");
+        return nullptr;
+    }
+    Engine *e = new Engine();
+    if (create_impl(e, cfg) != 0) {
+        ptmcmc_destroy((ptmcmc_engine *)e);
+        return nullptr;
+    }
+    return (ptmcmc_engine *)e;
+}
+
+void ptmcmc_destroy(ptmcmc_engine *h)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return;
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    void *ptrs[] = {e->x[0], e->x[1], e->lnl[0], e->lnl[1], e->lp[0], e->lp[1], e->d_ladder, e->d_mh_temp,
+                    e->d_cov, e->d_mu, e->d_m2, e->d_U, e->d_S, e->d_sqrtS, e->d_goff, e->d_gidx, e->d_uoff,
+                    e->d_soff, e->d_ord, e->d_work_a, e->d_work_v, e->d_am, e->d_de, e->d_gmu, e->d_gP,
+                    e->d_plo, e->d_phi, e->d_rec_x, e->d_rec_lnl, e->d_rec_lnp, e->d_prop, e->d_acc,
+                    e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_part, e->d_part2, e->d_batch,
+                    e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+// host [T][W][d] -> device [T][d][W]
+static int upload_state(Engine *e, const double *x0)
+{
+    const int d = e->d, W = e->W, T = e->T;
+    std::vector<double> tmp((size_t)T * W * d);
+    for (int t = 0; t < T; ++t)
+        for (int w = 0; w < W; ++w)
+            for (int k = 0; k < d; ++k) tmp[((size_t)t * d + k) * W + w] = x0[((size_t)t * W + w) * d + k];
+    CUDA_TRY(e, cudaMemcpyAsync(e->x[e->cur], tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+static int finish_set_state(Engine *e)
+{
+    e->iter = 0;
+    e->rows = 1;
+    e->rec_base = 0;
+    e->has_state = true;
+    DevParams p = make_params(e);
+    {
+        LaunchTimer lt(e, PTMCMC_K_INIT);
+        bookkeep_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, 0);  // ref :491
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    return 0;
+}
+
+int32_t ptmcmc_set_state(ptmcmc_engine *h, const double *x0)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !x0) return PTMCMC_ERR_ARG;
+    if (e->cfg.logl_kind == PTMCMC_LOGL_EXTERNAL || e->cfg.logp_kind == PTMCMC_LOGP_EXTERNAL)
+        return fail(e, PTMCMC_ERR_STATE, "external targets: use ptmcmc_set_state_external");
+    int rc = upload_state(e, x0);
+    if (rc) return rc;
+    DevParams p = make_params(e);
+    {
+        LaunchTimer lt(e, PTMCMC_K_INIT);
+        init_eval_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p);
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    return finish_set_state(e);
+}
+
+int32_t ptmcmc_set_state_external(ptmcmc_engine *h, const double *x0, const double *lnl, const double *lnprior)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !x0 || !lnl || !lnprior) return PTMCMC_ERR_ARG;
+    int rc = upload_state(e, x0);
+    if (rc) return rc;
+    const size_t C = (size_t)e->T * e->W;
+    CUDA_TRY(e, cudaMemcpy(e->lnl[e->cur], lnl, sizeof(double) * C, cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpy(e->lp[e->cur], lnprior, sizeof(double) * C, cudaMemcpyHostToDevice));
+    return finish_set_state(e);
+}
+
+int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_run before ptmcmc_set_state");
+    if (e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_run between propose and accept");
+    if (e->cfg.logl_kind == PTMCMC_LOGL_EXTERNAL || e->cfg.logp_kind == PTMCMC_LOGP_EXTERNAL || e->njumps > 3)
+        return fail(e, PTMCMC_ERR_STATE, "external targets or jumps: drive with ptmcmc_propose / ptmcmc_accept");
+    if (niter < 0) return fail(e, PTMCMC_ERR_ARG, "niter < 0");
+    const long long end = e->iter + niter;
+    int rc = check_rows(e, end);
+    if (rc) return rc;
+    const long long cu = e->cfg.cov_update, burn = e->cfg.burn, tskip = e->cfg.tskip;
+    while (e->iter < end) {
+        const long long it0 = e->iter + 1;
+        rc = maintenance(e, it0);
+        if (rc) return rc;
+        long long seg_end = end;
+        seg_end = std::min(seg_end, next_multiple(it0, cu));
+        seg_end = std::min(seg_end, next_multiple(it0, burn));
+        const bool swaps = e->T > 1;
+        if (swaps) seg_end = std::min(seg_end, next_multiple(it0, tskip));
+        const bool swap_now = swaps && (seg_end % tskip == 0);
+        cudaError_t st = launch_mh(e, it0, seg_end, !swap_now);
+        if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "MH kernel: %s", cudaGetErrorString(st));
+        if (swap_now) {
+            st = launch_swap(e, seg_end);
+            if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "swap kernels: %s", cudaGetErrorString(st));
+        }
+        e->iter = seg_end;
+    }
+    e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
+    return 0;
+}
+
+int32_t ptmcmc_propose(ptmcmc_engine *h, double *q, int32_t *jump)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !q || !jump) return PTMCMC_ERR_ARG;
+    if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose before set_state");
+    if (e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose called twice");
+    if (!e->d_q) return fail(e, PTMCMC_ERR_STATE, "engine was created without external targets or jumps");
+    const long long it0 = e->iter + 1;
+    int rc = check_rows(e, it0);
+    if (rc) return rc;
+    rc = maintenance(e, it0);
+    if (rc) return rc;
+    DevParams p = make_params(e);
+    p.it0 = p.it1 = it0;
+    {
+        LaunchTimer lt(e, PTMCMC_K_PROPOSE);
+        propose_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, e->d_q, e->d_jump, e->d_wordpos);
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    const size_t C = (size_t)e->T * e->W;
+    CUDA_TRY(e, cudaMemcpyAsync(q, e->d_q, sizeof(double) * C * e->d, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(jump, e->d_jump, sizeof(int) * C, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->pending_propose = true;
+    return 0;
+}
+
+int32_t ptmcmc_accept(ptmcmc_engine *h, const double *q, const double *qxy, const double *lnl, const double *lnprior)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !q || !qxy || !lnl || !lnprior) return PTMCMC_ERR_ARG;
+    if (!e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_accept without ptmcmc_propose");
+    const size_t C = (size_t)e->T * e->W;
+    const long long it = e->iter + 1;
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_q, q, sizeof(double) * C * e->d, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_qxy, qxy, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_lnl_new, lnl, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_lp_new, lnprior, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
+    DevParams p = make_params(e);
+    p.it0 = p.it1 = it;
+    {
+        LaunchTimer lt(e, PTMCMC_K_ACCEPT);
+        accept_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new,
+                                                                     e->d_jump, e->d_wordpos);
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    e->tm.chain_steps += (long long)C;
+    if (e->T > 1 && it % e->cfg.tskip == 0) {
+        cudaError_t st = launch_swap(e, it);
+        if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "swap kernels: %s", cudaGetErrorString(st));
+    } else {
+        LaunchTimer lt(e, PTMCMC_K_ACCEPT);
+        bookkeep_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, it);
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // the host buffers may be reused by the caller
+    e->iter = it;
+    e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
+    e->pending_propose = false;
+    return 0;
+}
+
+int64_t ptmcmc_iteration(const ptmcmc_engine *h) { return h ? ((const Engine *)h)->iter : -1; }
+
+int32_t ptmcmc_sync(ptmcmc_engine *h)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int32_t ptmcmc_get_state(ptmcmc_engine *h, double *x, double *lnl, double *lnprior, double *lnprob)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    const int d = e->d, W = e->W, T = e->T;
+    const size_t C = (size_t)T * W;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (x) {
+        std::vector<double> tmp(C * d);
+        CUDA_TRY(e, cudaMemcpy(tmp.data(), e->x[e->cur], sizeof(double) * C * d, cudaMemcpyDeviceToHost));
+        for (int t = 0; t < T; ++t)
+            for (int k = 0; k < d; ++k)
+                for (int w = 0; w < W; ++w) x[((size_t)t * W + w) * d + k] = tmp[((size_t)t * d + k) * W + w];
+    }
+    std::vector<double> l, p_;
+    if (lnl || lnprob) {
+        l.resize(C);
+        CUDA_TRY(e, cudaMemcpy(l.data(), e->lnl[e->cur], sizeof(double) * C, cudaMemcpyDeviceToHost));
+        if (lnl) memcpy(lnl, l.data(), sizeof(double) * C);
+    }
+    if (lnprior || lnprob) {
+        p_.resize(C);
+        CUDA_TRY(e, cudaMemcpy(p_.data(), e->lp[e->cur], sizeof(double) * C, cudaMemcpyDeviceToHost));
+        if (lnprior) memcpy(lnprior, p_.data(), sizeof(double) * C);
+    }
+    if (lnprob)
+        for (int t = 0; t < T; ++t)
+            for (int w = 0; w < W; ++w) {
+                const size_t c = (size_t)t * W + w;
+                lnprob[c] = 1.0 / e->mh_temp[t] * l[c] + p_[c];  // ref :487, :612, :695
+            }
+    return 0;
+}
+
+int64_t ptmcmc_rows(const ptmcmc_engine *h) { return h ? ((const Engine *)h)->rows : -1; }
+int64_t ptmcmc_row_base(const ptmcmc_engine *h) { return h ? ((const Engine *)h)->rec_base : -1; }
+
+int32_t ptmcmc_get_chain(ptmcmc_engine *h, int64_t row0, int64_t nrows, double *chain, double *lnl, double *lnprob)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    if (row0 < e->rec_base || row0 + nrows > e->rows || nrows < 0)
+        return fail(e, PTMCMC_ERR_ARG, "rows [%lld, %lld) are not resident (window [%lld, %lld))", (long long)row0,
+                    (long long)(row0 + nrows), e->rec_base, e->rows);
+    const size_t per_row = (size_t)e->ntr * e->W;
+    const size_t off = (size_t)(row0 - e->rec_base) * per_row, n = (size_t)nrows * per_row;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (chain) CUDA_TRY(e, cudaMemcpy(chain, e->d_rec_x + off * e->d, sizeof(double) * n * e->d, cudaMemcpyDeviceToHost));
+    if (lnl) CUDA_TRY(e, cudaMemcpy(lnl, e->d_rec_lnl + off, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (lnprob) CUDA_TRY(e, cudaMemcpy(lnprob, e->d_rec_lnp + off, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t ptmcmc_release_rows(ptmcmc_engine *h, int64_t upto_row)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    if (upto_row < e->rec_base || upto_row > e->rows) return fail(e, PTMCMC_ERR_ARG, "release_rows out of range");
+    const long long keep = e->rows - upto_row;  // rows that stay resident
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (keep > 0) {
+        const size_t per_row = (size_t)e->ntr * e->W;
+        const size_t src = (size_t)(upto_row - e->rec_base) * per_row, n = (size_t)keep * per_row;
+        // windows are small relative to HBM; a staged device copy keeps this simple and overlap-safe
+        double *tmp = nullptr;
+        CUDA_TRY(e, cudaMalloc((void **)&tmp, sizeof(double) * n * e->d));
+        CUDA_TRY(e, cudaMemcpy(tmp, e->d_rec_x + src * e->d, sizeof(double) * n * e->d, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(e, cudaMemcpy(e->d_rec_x, tmp, sizeof(double) * n * e->d, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(e, cudaMemcpy(tmp, e->d_rec_lnl + src, sizeof(double) * n, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(e, cudaMemcpy(e->d_rec_lnl, tmp, sizeof(double) * n, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(e, cudaMemcpy(tmp, e->d_rec_lnp + src, sizeof(double) * n, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(e, cudaMemcpy(e->d_rec_lnp, tmp, sizeof(double) * n, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(e, cudaFree(tmp));
+    }
+    e->rec_base = upto_row;
+    return 0;
+}
+
+int32_t ptmcmc_get_adapt(ptmcmc_engine *h, double *cov, double *mu, double *m2, int64_t *nsamp)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    const int d = e->d;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (cov) CUDA_TRY(e, cudaMemcpy(cov, e->d_cov, sizeof(double) * d * d, cudaMemcpyDeviceToHost));
+    if (mu) CUDA_TRY(e, cudaMemcpy(mu, e->d_mu, sizeof(double) * d, cudaMemcpyDeviceToHost));
+    if (m2) CUDA_TRY(e, cudaMemcpy(m2, e->d_m2, sizeof(double) * d * d, cudaMemcpyDeviceToHost));
+    if (nsamp) *nsamp = e->nsamp;
+    return 0;
+}
+
+int32_t ptmcmc_get_factor(ptmcmc_engine *h, double *U, double *S)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (U) CUDA_TRY(e, cudaMemcpy(U, e->d_U, sizeof(double) * e->uoff[e->ngroups], cudaMemcpyDeviceToHost));
+    if (S) CUDA_TRY(e, cudaMemcpy(S, e->d_S, sizeof(double) * e->soff[e->ngroups], cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t ptmcmc_set_factor(ptmcmc_engine *h, const double *U, const double *S)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !U || !S) return PTMCMC_ERR_ARG;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaMemcpy(e->d_U, U, sizeof(double) * e->uoff[e->ngroups], cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpy(e->d_S, S, sizeof(double) * e->soff[e->ngroups], cudaMemcpyHostToDevice));
+    const int n = e->soff[e->ngroups];
+    sqrt_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(e->d_S, e->d_sqrtS, n);
+    e->tm.launches[PTMCMC_K_ADAPT] += 1;
+    CUDA_TRY(e, cudaGetLastError());
+    return 0;
+}
+
+int32_t ptmcmc_get_buffers(ptmcmc_engine *h, double *am, double *de)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    const int d = e->d, W = e->W;
+    const long long cu = e->cfg.cov_update, burn = e->cfg.burn;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (am) {
+        std::vector<double> tmp((size_t)cu * d * W);
+        CUDA_TRY(e, cudaMemcpy(tmp.data(), e->d_am, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+        for (long long s = 0; s < cu; ++s)
+            for (int k = 0; k < d; ++k)
+                for (int w = 0; w < W; ++w) am[((size_t)s * W + w) * d + k] = tmp[((size_t)s * d + k) * W + w];
+    }
+    if (de) {
+        // un-rotate the ring so that row 0 is the oldest slot, as in the reference's shifted array
+        const size_t row = (size_t)W * d;
+        const long long first = burn - e->de_head;
+        CUDA_TRY(e, cudaMemcpy(de, e->d_de + (size_t)e->de_head * row, sizeof(double) * (size_t)first * row, cudaMemcpyDeviceToHost));
+        if (e->de_head)
+            CUDA_TRY(e, cudaMemcpy(de + (size_t)first * row, e->d_de, sizeof(double) * (size_t)e->de_head * row, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int32_t ptmcmc_adapt_begin(ptmcmc_engine *h, double *batch_out)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !batch_out) return PTMCMC_ERR_ARG;
+    const long long b = e->iter;
+    if (b == 0 || b % e->cfg.cov_update != 0 || e->adapt_done_iter == b) return 0;
+    {
+        LaunchTimer lt(e, PTMCMC_K_ADAPT, 4);
+        cudaError_t st = launch_batch_moments(e);
+        if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "batch moments: %s", cudaGetErrorString(st));
+    }
+    const size_t n = (size_t)1 + e->d + (size_t)e->d * e->d;
+    CUDA_TRY(e, cudaMemcpyAsync(batch_out, e->d_batch, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return 1;
+}
+
+int32_t ptmcmc_adapt_finish(ptmcmc_engine *h, const double *batch_in)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !batch_in) return PTMCMC_ERR_ARG;
+    const long long b = e->iter;
+    if (b == 0 || b % e->cfg.cov_update != 0 || e->adapt_done_iter == b)
+        return fail(e, PTMCMC_ERR_STATE, "no covariance update is due at iteration %lld", b);
+    const size_t n = (size_t)1 + e->d + (size_t)e->d * e->d;
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_batch, batch_in, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    const long long it = b - e->cfg.cov_update;
+    const double n_prev = (it == 0) ? 0.0 : (double)e->nsamp;
+    {
+        LaunchTimer lt(e, PTMCMC_K_ADAPT);
+        cudaError_t st = launch_factor(e, e->d_batch, n_prev, it == 0);
+        if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "factor: %s", cudaGetErrorString(st));
+    }
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->nsamp = (long long)(n_prev + batch_in[0]);
+    e->adapt_done_iter = b;
+    return 0;
+}
+
+int32_t ptmcmc_njumps(const ptmcmc_engine *h) { return h ? ((const Engine *)h)->njumps : -1; }
+
+int32_t ptmcmc_get_counters(ptmcmc_engine *h, int64_t *prop, int64_t *acc, int64_t *swap_acc, int64_t *swap_proposed)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    const size_t C = (size_t)e->T * e->W;
+    const int nj = e->njumps;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    std::vector<unsigned long long> tmp(C * nj);
+    for (int pass = 0; pass < 2; ++pass) {
+        int64_t *dst = pass ? acc : prop;
+        if (!dst) continue;
+        CUDA_TRY(e, cudaMemcpy(tmp.data(), pass ? e->d_acc : e->d_prop, sizeof(unsigned long long) * C * nj, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < nj; ++j)
+            for (size_t c = 0; c < C; ++c) dst[c * nj + j] = (int64_t)tmp[(size_t)j * C + c];
+    }
+    if (swap_acc) CUDA_TRY(e, cudaMemcpy(swap_acc, e->d_swap_acc, sizeof(int64_t) * C, cudaMemcpyDeviceToHost));
+    if (swap_proposed) *swap_proposed = e->swap_proposed;
+    return 0;
+}
+
+int32_t ptmcmc_get_trace(ptmcmc_engine *h, uint8_t *trace, int64_t iters, int16_t *swapmaps, int64_t events)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    if (!e->cfg.trace) return fail(e, PTMCMC_ERR_STATE, "engine created without trace");
+    const size_t C = (size_t)e->T * e->W;
+    if (iters > e->cfg.trace_iters || events > e->cfg.trace_iters) return fail(e, PTMCMC_ERR_ARG, "trace request exceeds capacity");
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (trace) CUDA_TRY(e, cudaMemcpy(trace, e->d_trace, (size_t)iters * C, cudaMemcpyDeviceToHost));
+    if (swapmaps) CUDA_TRY(e, cudaMemcpy(swapmaps, e->d_swapmaps, sizeof(short) * (size_t)events * C, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t ptmcmc_get_timing(ptmcmc_engine *h, ptmcmc_timing *out)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !out) return PTMCMC_ERR_ARG;
+    *out = e->tm;
+    return 0;
+}
+
+int32_t ptmcmc_reset_timing(ptmcmc_engine *h)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    e->tm = ptmcmc_timing{};
+    return 0;
+}
+
+void *ptmcmc_stream(ptmcmc_engine *h) { return h ? (void *)((Engine *)h)->stream : nullptr; }
+
+}  // extern "C"
