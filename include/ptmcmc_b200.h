@@ -171,8 +171,13 @@ int32_t ptmcmc_get_trace(ptmcmc_engine *e, uint8_t *trace, int64_t iters, int16_
 
 int32_t ptmcmc_get_timing(ptmcmc_engine *e, ptmcmc_timing *out);
 int32_t ptmcmc_reset_timing(ptmcmc_engine *e);
+/* switch the per-launch CUDA-event bracketing on or off (same as cfg.timing) */
+int32_t ptmcmc_set_timing(ptmcmc_engine *e, int32_t on);
 /* the engine's CUDA stream (cudaStream_t) for callers that time with their own events */
 void *ptmcmc_stream(ptmcmc_engine *e);
+/* page-locked host memory for the caller-owned buffers (faster DMA); plain malloc memory works too */
+void *ptmcmc_host_alloc(int64_t bytes);
+void ptmcmc_host_free(void *p);
 
 #ifdef __cplusplus
 }

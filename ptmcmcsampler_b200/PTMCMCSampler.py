@@ -1,0 +1,562 @@
+"""Host-side mirror of ``PTMCMCSampler.PTMCMCSampler.PTSampler`` (nanograv/PTMCMCSampler).
+
+Same constructor, ``sample()`` signature, plugin surface (``addProposalToCycle``,
+``addAuxilaryJump``) and public attributes as the reference (ref PTMCMCSampler.py:40-1069); the
+hot path runs in the CUDA engine behind ``include/ptmcmc_b200.h``.  What stays in Python is what
+the reference also does on the host around the step: configuration, the driver loop's chunking,
+chain / jump files and the progress line.
+
+Differences a reference user should know:
+
+* one process drives all temperatures (``ntemps=``) and, new, ``nwalkers`` independent ladders;
+  the reference's one-MPI-rank-per-temperature layout has no counterpart, ``comm`` is accepted
+  for signature parity only;
+* ``logl`` / ``logp`` may be objects from :mod:`ptmcmcsampler_b200.likelihoods` (fully on device)
+  or plain callables (evaluated on the host once per iteration, as are custom Python jumps);
+* random numbers come from a counter-based Philox stream keyed by ``seed`` instead of PCG64, so
+  runs agree with the reference in distribution, not draw by draw;
+* the gradient proposals (NUTS / HMC / MALA, ref nutsjump.py) are not part of this engine.
+"""
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+from . import _cabi
+from . import nompi4py as MPI
+from .likelihoods import DeviceLogLikelihood, DeviceLogPrior
+
+__all__ = ["PTSampler", "shift_array"]
+
+
+def shift_array(arr, num, fill_value=0.0):
+    """Shift rows of ``arr`` by ``num`` places, filling the vacated rows (ref :27-37)."""
+    arr = np.asarray(arr)
+    out = np.full_like(arr, fill_value)
+    if num > 0:
+        out[num:] = arr[:-num]
+    elif num < 0:
+        out[:num] = arr[-num:]
+    else:
+        out[...] = arr
+    return out
+
+
+class _function_wrapper(object):
+    """Binds ``args`` / ``kwargs`` to a user callable (ref :1072-1086)."""
+
+    def __init__(self, f, args, kwargs):
+        self.f, self.args, self.kwargs = f, args, kwargs
+
+    def __call__(self, x):
+        return self.f(x, *self.args, **self.kwargs)
+
+
+class PTSampler(object):
+    """Parallel-tempering MCMC sampler with adaptive (AM / SCAM) and differential-evolution
+    proposals; API of the reference's ``PTSampler`` (ref :40-155).
+
+    Extra keyword arguments (all optional, defaults reproduce a single reference chain):
+
+    :param ntemps: number of temperatures (the reference takes it from ``comm.Get_size()``)
+    :param nwalkers: independent ladders run side by side; the adaptive covariance and the DE
+        history are pooled over the walkers' T=1 chains
+    :param device: CUDA device ordinal
+    :param record_rows: rows of the thinned record kept on the device between flushes
+    :param walker_offset: global id of this process's walker 0 (walker sharding over several GPUs)
+    :param dist_group: ``torch.distributed`` process group over which the proposal covariance is
+        pooled (``True`` = the default group); ``None`` keeps this sampler independent
+    """
+
+    def __init__(self, ndim, logl, logp, cov, groups=None, loglargs=[], loglkwargs={}, logpargs=[],
+                 logpkwargs={}, logl_grad=None, logp_grad=None, comm=MPI.COMM_WORLD, outDir="./chains",
+                 verbose=True, resume=False, seed=None, ntemps=None, nwalkers=1, device=0, record_rows=None,
+                 walker_offset=0, dist_group=None):
+        self.comm = comm
+        self.MPIrank = 0
+        if comm is not None and hasattr(comm, "Get_size") and comm.Get_size() > 1:
+            raise NotImplementedError(
+                "one process drives every temperature on the GPU: pass ntemps=%d instead of launching "
+                "one MPI rank per temperature" % comm.Get_size())
+        self.nchain = int(ntemps) if ntemps else 1
+        self.nwalkers = int(nwalkers)
+        self.device = int(device)
+        self.walker_offset = int(walker_offset)
+        self._record_rows = record_rows
+        self.dist_group = dist_group  # torch.distributed group to pool the covariance over (walker sharding)
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
+        self.seed = int(seed)
+        self.stream = np.random.default_rng(self.seed)  # host-side draws for user plugins only
+
+        self.ndim = int(ndim)
+        self._dev_logl = logl if isinstance(logl, DeviceLogLikelihood) else None
+        self._dev_logp = logp if isinstance(logp, DeviceLogPrior) else None
+        self.logl = logl if self._dev_logl is not None else _function_wrapper(logl, loglargs, loglkwargs)
+        self.logp = logp if self._dev_logp is not None else _function_wrapper(logp, logpargs, logpkwargs)
+        if logl_grad is not None and logp_grad is not None:
+            warnings.warn("gradient proposals (NUTS/HMC/MALA) are outside this engine; logl_grad/logp_grad are ignored")
+        self.logl_grad = None
+        self.logp_grad = None
+
+        self.outDir = outDir
+        self.verbose = verbose
+        self.resume = resume
+        if not os.path.exists(self.outDir):
+            try:
+                os.makedirs(self.outDir)
+            except OSError:
+                pass
+
+        # parameter groups (ref :129-131) and the initial eigen-factor of each block (ref :133-145)
+        self.groups = groups if groups is not None else [np.arange(0, self.ndim)]
+        self.cov = cov
+        cov_arr = np.asarray(cov, dtype=np.float64)
+        if cov_arr.shape != (self.ndim, self.ndim):
+            raise ValueError("cov must be (ndim, ndim)")
+        self.U = [[]] * len(self.groups)
+        self.S = [[]] * len(self.groups)
+        self.M2 = np.zeros((self.ndim, self.ndim))
+        self.mu = np.zeros(self.ndim)
+
+        self.propCycle = []
+        self.jumpDict = {}
+        self.aux = []
+        self._ext_jumps = []  # user callables in registration order -> engine jump ids 3, 4, ...
+        self._engine = None
+
+    # ------------------------------------------------------------------ plugin surface --------
+    def covarianceJumpProposalSCAM(self, x, iter, beta):
+        """Identifies the device-side single-component adaptive jump in ``propCycle`` (ref :820-876)."""
+        raise NotImplementedError("the SCAM proposal is drawn on the device; this handle only names it")
+
+    def covarianceJumpProposalAM(self, x, iter, beta):
+        """Identifies the device-side adaptive-Metropolis jump in ``propCycle`` (ref :879-933)."""
+        raise NotImplementedError("the AM proposal is drawn on the device; this handle only names it")
+
+    def DEJump(self, x, iter, beta):
+        """Identifies the device-side differential-evolution jump in ``propCycle`` (ref :936-985)."""
+        raise NotImplementedError("the DE proposal is drawn on the device; this handle only names it")
+
+    def addProposalToCycle(self, func, weight):
+        """Add ``func(x, iter, beta) -> (q, qxy)`` to the cycle with integer ``weight`` (ref :988-1014)."""
+        if weight == 0:  # silently ignored, as in the reference (:1001-1004)
+            return
+        self.propCycle.extend([func] * int(weight))
+        if func.__name__ not in self.jumpDict:
+            self.jumpDict[func.__name__] = [0, 0]
+            open(os.path.join(self.outDir, func.__name__ + "_jump.txt"), "w").close()
+
+    def addAuxilaryJump(self, func):
+        """Add ``func(x, q, iter, beta) -> (q, qxy_aux)`` applied after every proposal (ref :1017-1028)."""
+        self.aux.append(func)
+
+    def randomizeProposalCycle(self):
+        """Kept for API parity; the reference's shuffled copy is never read (ref :1031-1045)."""
+        index = np.arange(len(self.propCycle))
+        self.stream.shuffle(index)
+        self.randomizedPropCycle = [self.propCycle[i] for i in index]
+
+    def temperatureLadder(self, Tmin, Tmax=None, tstep=None):
+        """Geometric ladder ``Tmin * tstep**i`` (ref :699-720)."""
+        if self.nchain > 1:
+            if tstep is None and Tmax is None:
+                tstep = 1 + np.sqrt(2 / self.ndim)
+            elif tstep is None:
+                tstep = np.exp(np.log(Tmax / Tmin) / (self.nchain - 1))
+            return Tmin * tstep ** np.arange(self.nchain, dtype=np.float64)
+        return np.array([1])
+
+    # ------------------------------------------------------------------ engine plumbing -------
+    def _builtin_ids(self):
+        return {self.covarianceJumpProposalSCAM: _cabi.JUMP_SCAM, self.covarianceJumpProposalAM: _cabi.JUMP_AM,
+                self.DEJump: _cabi.JUMP_DE}
+
+    def _cycle_segments(self):
+        """propCycle (weight-replicated list) -> [(jump id, weight)] in order."""
+        builtin = self._builtin_ids()
+        segs = []
+        for f in self.propCycle:
+            if f in builtin:
+                jid = builtin[f]
+            else:
+                if f not in self._ext_jumps:
+                    self._ext_jumps.append(f)
+                jid = _cabi.JUMP_EXT0 + self._ext_jumps.index(f)
+            if segs and segs[-1][0] == jid:
+                segs[-1][1] += 1
+            else:
+                segs.append([jid, 1])
+        return [(j, w) for j, w in segs]
+
+    @property
+    def _external(self):
+        return self._dev_logl is None or self._dev_logp is None or bool(self._ext_jumps) or bool(self.aux)
+
+    def _make_engine(self, maxIter):
+        d = self.ndim
+        rows_total = int(maxIter / self.thin) + 1
+        rr = self._record_rows or min(rows_total, max(int(self.isave // self.thin) + 2, 64))
+        rr = max(rr, int(self.isave // self.thin) + 2)
+        mh_temp = np.array(self.ladder, dtype=np.float64)
+        if self._hotChain:
+            mh_temp[-1] = 1e80  # ref :281-282
+        self._mh_temp = mh_temp
+        self._engine = _cabi.Engine(
+            d, self.nwalkers, self.nchain, np.asarray(self.cov, dtype=np.float64), np.asarray(self.ladder, np.float64),
+            mh_temp=mh_temp, seed=self.seed, groups=None if self._default_groups() else self.groups,
+            cycle=self._cycle_segments(), de_weight=self.DEweight, cov_update=self.covUpdate, burn=self.burn,
+            tskip=self.Tskip, thin=self.thin,
+            logl_kind=self._dev_logl.kind if self._dev_logl is not None else _cabi.LOGL_EXTERNAL,
+            logl_params=self._dev_logl.params(d) if self._dev_logl is not None else None,
+            logp_kind=self._dev_logp.kind if self._dev_logp is not None else _cabi.LOGP_EXTERNAL,
+            logp_params=self._dev_logp.params(d) if self._dev_logp is not None else None,
+            record_hot=self.writeHotChains, record_rows=rr, device=self.device, walker_offset=self.walker_offset)
+        self._pull_factor()
+
+    def _default_groups(self):
+        return len(self.groups) == 1 and np.array_equal(np.asarray(self.groups[0]), np.arange(self.ndim))
+
+    def _pull_factor(self):
+        U, S = self._engine.factor()
+        uo = so = 0
+        for g, grp in enumerate(self.groups):
+            n = len(grp)
+            self.U[g] = U[uo:uo + n * n].reshape(n, n).copy()
+            self.S[g] = S[so:so + n].copy()
+            uo += n * n
+            so += n
+
+    def _pull_adapt(self):
+        cov, mu, m2, _ = self._engine.adapt()
+        np.asarray(self.cov)[:, :] = cov  # in place, like the reference (:794)
+        self.mu, self.M2 = mu, m2
+        self._pull_factor()
+
+    # ------------------------------------------------------------------ initialize ------------
+    def initialize(self, Niter, ladder=None, Tmin=1, Tmax=None, Tskip=100, isave=1000, covUpdate=1000,
+                   SCAMweight=30, AMweight=20, DEweight=50, NUTSweight=20, HMCweight=20, MALAweight=0,
+                   burn=50000, HMCstepsize=0.1, HMCsteps=300, maxIter=None, thin=10, i0=0, neff=None,
+                   writeHotChains=False, hotChain=False):
+        """Set the run's knobs, register the default proposals, build the device engine (ref :157-319)."""
+        if maxIter is None:
+            maxIter = Niter
+        self.ladder = ladder
+        self.covUpdate, self.burn, self.Tskip, self.thin, self.isave = int(covUpdate), int(burn), int(Tskip), int(thin), int(isave)
+        self.SCAMweight, self.AMweight, self.DEweight = int(SCAMweight), int(AMweight), int(DEweight)
+        self.Niter, self.neff, self.tstart = Niter, neff, 0
+        if neff:
+            raise NotImplementedError("neff needs the optional acor package and is outside this engine")
+
+        N = int(maxIter / thin) + 1
+        W = self.nwalkers
+        # page-locked so that the device record is DMA'd straight into these arrays
+        self._chain_all = _cabi.pinned_empty((N, W, self.ndim))
+        self._lnlike_all = _cabi.pinned_empty((N, W))
+        self._lnprob_all = _cabi.pinned_empty((N, W))
+        self._chain_all[...] = 0.0
+        self._lnlike_all[...] = 0.0
+        self._lnprob_all[...] = 0.0
+        self._chain, self._lnlike, self._lnprob = self._chain_all[:, 0], self._lnlike_all[:, 0], self._lnprob_all[:, 0]
+        self._hot_rows = None
+        self.ind_next_write = 0
+        self._rows_pulled = 0
+        self.naccepted = 0
+        self.swapProposed = 0
+        self.nswap_accepted = 0
+
+        self.addProposalToCycle(self.covarianceJumpProposalSCAM, self.SCAMweight)
+        self.addProposalToCycle(self.covarianceJumpProposalAM, self.AMweight)
+        if len(self.propCycle) == 0:
+            raise ValueError("No jump proposals specified!")
+        self.randomizeProposalCycle()
+
+        if self.ladder is None:
+            self.ladder = self.temperatureLadder(Tmin, Tmax=Tmax)
+        self.ladder = np.asarray(self.ladder)
+        if len(self.ladder) != self.nchain:
+            raise ValueError("ladder has %d entries for %d temperatures" % (len(self.ladder), self.nchain))
+        self.temp = self.ladder[self.MPIrank]
+        self._hotChain = bool(hotChain) and self.nchain > 1
+        self.fname = self.outDir + "/chain_{0}.txt".format(self.temp)
+        self.writeHotChains = bool(writeHotChains)
+        self._hot_fnames = [self.outDir + "/chain_{0}.txt".format(t) for t in self.ladder]
+        if self._hotChain:
+            self._hot_fnames[-1] = self.outDir + "/chain_hot.txt"
+
+        self.resumeLength = 0
+        if self.resume and os.path.isfile(self.fname):
+            raise NotImplementedError("resume=True: replay from chain files is not implemented in this engine yet")
+        open(self.fname, "w").close()
+        if self.writeHotChains:
+            for f in self._hot_fnames[1:]:
+                open(f, "w").close()
+        self._make_engine(maxIter)
+        self._buffers = None
+
+    # ------------------------------------------------------------------ output ----------------
+    def _pull_rows(self):
+        """Copy newly recorded rows from the device window into _chain/_lnlike/_lnprob."""
+        eng = self._engine
+        rows = eng.rows
+        if rows <= self._rows_pulled:
+            return
+        r0 = self._rows_pulled
+        n = min(rows - r0, self._chain_all.shape[0] - r0)
+        if eng.ntr == 1:
+            # T=1 rung only: the device rows land directly in the (pinned) result arrays
+            eng.chain(r0, n, out=(self._chain_all[r0:r0 + n], self._lnlike_all[r0:r0 + n],
+                                  self._lnprob_all[r0:r0 + n]))
+        else:
+            ch, lnl, lnp = eng.chain(r0, n)
+            self._chain_all[r0:r0 + n] = ch[:, 0]
+            self._lnlike_all[r0:r0 + n] = lnl[:, 0]
+            self._lnprob_all[r0:r0 + n] = lnp[:, 0]
+            if self._hot_rows is None:
+                self._hot_rows = []
+            self._hot_rows.append((r0, ch[:, :, 0].copy(), lnl[:, :, 0].copy(), lnp[:, :, 0].copy()))
+        self._rows_pulled = rows
+        eng.release_rows(rows)
+
+    def _pull_counters(self):
+        prop, acc, sw, nsw = self._engine.counters()
+        self._prop, self._acc, self._swap_acc = prop, acc, sw
+        names = {_cabi.JUMP_SCAM: "covarianceJumpProposalSCAM", _cabi.JUMP_AM: "covarianceJumpProposalAM",
+                 _cabi.JUMP_DE: "DEJump"}
+        for k, f in enumerate(self._ext_jumps):
+            names[_cabi.JUMP_EXT0 + k] = f.__name__
+        for jid, name in names.items():
+            if jid < prop.shape[2] and (name in self.jumpDict or prop[0, :, jid].sum() > 0):
+                # T=1 rung, summed over walkers (one walker: the reference's rank-0 jumpDict)
+                self.jumpDict[name] = [int(prop[0, :, jid].sum()), int(acc[0, :, jid].sum())]
+        self.naccepted = acc[0].sum() / float(self.nwalkers)
+        self.naccepted_all = acc.sum(axis=2)           # [T][W]
+        self.swapProposed = nsw
+        self.nswap_accepted = sw[0].sum() / float(self.nwalkers)
+        self.nswap_accepted_all = sw
+
+    def updateChains(self, p0, lnlike0, lnprob0, iter):
+        """The reference's per-iteration buffer/record hook (ref :321-339) is fused into the kernels;
+        kept as a no-op for code that calls it around ``PTMCMCOneStep``."""
+        return None
+
+    def writeOutput(self, iter):
+        """Write chain rows, covariance and jump statistics (ref :341-372)."""
+        self._pull_rows()
+        self._pull_counters()
+        if iter // self.thin >= self.ind_next_write:
+            self._writeToFile(iter)
+            if iter > 0:
+                self._pull_adapt()
+                np.save(self.outDir + "/cov.npy", np.asarray(self.cov))
+            if self.verbose:
+                if iter > 0:
+                    sys.stdout.write("\r")
+                percent = iter / self.Niter * 100
+                acceptance = self.naccepted / iter if iter > 0 else 0
+                sys.stdout.write("Finished %2.2f percent in %f s Acceptance rate = %g"
+                                 % (percent, time.time() - self.tstart, acceptance))
+                sys.stdout.flush()
+
+    def _writeToFile(self, iter):
+        """Chain file: ndim columns ``%22.22f`` then lnprob, lnlike, acceptance rate, PT swap
+        acceptance, rates as of the time of writing (ref :722-766).  Walker 0 is written in the
+        reference's layout; all walkers stay available in ``_chain_all``."""
+        write_end = iter // self.thin + 1
+        rows = range(self.ind_next_write, min(write_end, self._rows_pulled))
+        acc_rate = self.naccepted_all[0, 0] / iter if iter > 0 else 0
+        pt_acc = 1
+        if self.nchain > 1 and self.swapProposed != 0:
+            pt_acc = self.nswap_accepted_all[0, 0] / self.swapProposed
+        with open(self.fname, "a+") as fh:
+            for ind in rows:
+                fh.write("\t".join(["%22.22f" % v for v in self._chain[ind]]))
+                fh.write("\t%f\t%f\t%f\t%f\n" % (self._lnprob[ind], self._lnlike[ind], acc_rate, pt_acc))
+        if self.writeHotChains and self._hot_rows:
+            for t in range(1, self.nchain):
+                a_t = self.naccepted_all[t, 0] / iter if iter > 0 else 0
+                p_t = 1
+                if t < self.nchain - 1 and self.swapProposed != 0:
+                    p_t = self.nswap_accepted_all[t, 0] / self.swapProposed
+                with open(self._hot_fnames[t], "a+") as fh:
+                    for r0, ch, lnl, lnp in self._hot_rows:
+                        for i in range(ch.shape[0]):
+                            fh.write("\t".join(["%22.22f" % v for v in ch[i, t]]))
+                            fh.write("\t%f\t%f\t%f\t%f\n" % (lnp[i, t], lnl[i, t], a_t, p_t))
+            self._hot_rows = []
+        self.ind_next_write = write_end
+        # jump statistics, T=1 chain only (ref :751-766)
+        njumps = len(self.propCycle)
+        with open(self.outDir + "/jumps.txt", "w") as fout:
+            seen = []
+            for jump in self.propCycle:
+                if jump not in seen:
+                    seen.append(jump)
+                    fout.write("%s %4.2g\n" % (jump.__name__, self.propCycle.count(jump) / njumps))
+        for name in self.jumpDict:
+            with open(self.outDir + "/" + name + "_jump.txt", "a+") as fout:
+                fout.write("%g\n" % (self.jumpDict[name][1] / max(1, self.jumpDict[name][0])))
+
+    # ------------------------------------------------------------------ sampling --------------
+    def _full_p0(self, p0):
+        p0 = np.asarray(p0, dtype=np.float64)
+        T, W, d = self.nchain, self.nwalkers, self.ndim
+        if p0.shape == (d,):
+            return np.broadcast_to(p0, (T, W, d)).copy()
+        if p0.shape == (W, d):
+            return np.broadcast_to(p0[None], (T, W, d)).copy()
+        if p0.shape == (T, W, d):
+            return np.ascontiguousarray(p0)
+        raise ValueError("p0 must have shape (ndim,), (nwalkers, ndim) or (ntemps, nwalkers, ndim)")
+
+    def _host_eval(self, x):
+        """logp / logl of every chain on the host (plain Python callables), ref :478-487, :605-612."""
+        T, W = x.shape[:2]
+        lp = np.zeros((T, W))
+        lnl = np.zeros((T, W))
+        for t in range(T):
+            for w in range(W):
+                if self._dev_logp is None:
+                    lp[t, w] = self.logp(x[t, w])
+                if self._dev_logl is None and (self._dev_logp is not None or lp[t, w] != -np.inf):
+                    lnl[t, w] = self.logl(x[t, w])
+        return lnl, lp
+
+    def _maybe_add_de(self, iter):
+        """DE joins the cycle at iteration burn+1 (ref :563-585)."""
+        if (iter - 1) == self.burn and self.DEJump not in self.propCycle and self.DEweight > 0:
+            if self.verbose:
+                print("Adding DE jump with weight {0}".format(self.DEweight))
+            self.addProposalToCycle(self.DEJump, self.DEweight)
+            self.randomizeProposalCycle()
+
+    def _step_external(self, iter):
+        """One iteration with Python callables in the loop (ref :601-612, _jump :1048-1067)."""
+        eng = self._engine
+        x = eng.state()[0]
+        q, jump = eng.propose()
+        T, W = jump.shape
+        qxy = np.zeros((T, W))
+        lnl = np.zeros((T, W))
+        lp = np.zeros((T, W))
+        for t in range(T):
+            beta = 1 / self._mh_temp[t]
+            for w in range(W):
+                jid = jump[t, w]
+                if jid >= _cabi.JUMP_EXT0:
+                    qq, lq = self._ext_jumps[jid - _cabi.JUMP_EXT0](x[t, w].copy(), iter, beta)
+                    q[t, w], qxy[t, w] = qq, lq
+                for aux in self.aux:
+                    qq, lq = aux(x[t, w].copy(), q[t, w].copy(), iter, beta)
+                    q[t, w] = qq
+                    qxy[t, w] += lq
+                if self._dev_logp is None:
+                    lp[t, w] = self.logp(q[t, w])
+                if self._dev_logl is None and (self._dev_logp is not None or lp[t, w] != -np.inf):
+                    lnl[t, w] = self.logl(q[t, w])
+        eng.accept(q, qxy, lnl, lp)
+
+    def _advance(self, n, iter0):
+        """Run ``n`` iterations starting after ``iter0``."""
+        if not self._external:
+            if self.dist_group is not None:
+                from . import distributed
+
+                distributed.run(self._engine, n, None if self.dist_group is True else self.dist_group)
+            else:
+                self._engine.run(n)
+            self._maybe_add_de_bulk(iter0, n)
+            return
+        for it in range(iter0 + 1, iter0 + n + 1):
+            self._maybe_add_de(it)
+            self._step_external(it)
+
+    def _maybe_add_de_bulk(self, iter0, n):
+        if iter0 < self.burn + 1 <= iter0 + n:
+            self._maybe_add_de(self.burn + 1)
+
+    def sample(self, p0, Niter, ladder=None, Tmin=1, Tmax=None, Tskip=100, isave=1000, covUpdate=1000,
+               SCAMweight=20, AMweight=20, DEweight=20, NUTSweight=20, MALAweight=20, HMCweight=20, burn=10000,
+               HMCstepsize=0.1, HMCsteps=300, maxIter=None, thin=10, i0=0, neff=None, writeHotChains=False,
+               hotChain=False):
+        """Run ``Niter`` iterations from ``p0`` (ref :374-528).  ``p0`` may be one point (used for
+        every chain), one per walker, or ``(ntemps, nwalkers, ndim)``."""
+        if maxIter is None:
+            maxIter = Niter
+        if isave % thin != 0:
+            raise ValueError("isave = %d is not a multiple of thin =  %d" % (isave, thin))
+        if Niter % thin != 0:
+            print("Niter = %d is not a multiple of thin = %d.  The last %d samples will be lost"
+                  % (Niter, thin, Niter % thin))
+        if i0 == 0:
+            self.initialize(Niter, ladder=ladder, Tmin=Tmin, Tmax=Tmax, Tskip=Tskip, isave=isave,
+                            covUpdate=covUpdate, SCAMweight=SCAMweight, AMweight=AMweight, DEweight=DEweight,
+                            NUTSweight=NUTSweight, MALAweight=MALAweight, HMCweight=HMCweight, burn=burn,
+                            HMCstepsize=HMCstepsize, HMCsteps=HMCsteps, maxIter=maxIter, thin=thin, i0=i0,
+                            neff=neff, writeHotChains=writeHotChains, hotChain=hotChain)
+            x0 = self._full_p0(p0)
+            if self._dev_logl is not None and self._dev_logp is not None:
+                self._engine.set_state(x0)
+            else:
+                lnl, lp = self._host_eval(x0)
+                if self._dev_logp is not None or self._dev_logl is not None:
+                    raise NotImplementedError("mixing a device target with a Python target is not supported; "
+                                              "pass both as device objects or both as callables")
+                self._engine.set_state_external(x0, lnl, lp)
+        elif self._engine is None:
+            raise ValueError("i0 != 0 requires a sampler that has already been initialised")
+        self.tstart = time.time()
+        self.writeOutput(i0)  # row 0 (ref :491 -> updateChains -> writeOutput at iter 0)
+
+        iter = i0
+        while iter < self.Niter:
+            # advance to the next multiple of isave, the reference's write cadence (ref :338-339)
+            nxt = min(self.Niter, (iter // self.isave + 1) * self.isave)
+            self._advance(nxt - iter, iter)
+            iter = nxt
+            if iter % self.isave == 0 or iter >= self.Niter:
+                self.writeOutput(iter)
+        self._finish()
+        if self.verbose:
+            print("\nRun Complete")
+
+    def _finish(self):
+        self._pull_rows()
+        self._pull_counters()
+        self._pull_adapt()
+        self._buffers = None
+
+    def _fetch_buffers(self):
+        if self._buffers is None:
+            am, de = self._engine.buffers()
+            self._buffers = (am[:, 0], de[:, 0]) if self.nwalkers == 1 else (am, de)
+        return self._buffers
+
+    @property
+    def _AMbuffer(self):
+        """ref _AMbuffer (:220): the last covUpdate T=1 samples, fetched from the device on access."""
+        return self._fetch_buffers()[0]
+
+    @property
+    def _DEbuffer(self):
+        """ref _DEbuffer (:221): the DE history, fetched from the device on access."""
+        return self._fetch_buffers()[1]
+
+    def PTMCMCOneStep(self, p0, lnlike0, lnprob0, iter):
+        """One iteration of every chain on the engine (ref :530-629); returns walker 0's T=1 state."""
+        if self._engine is None:
+            raise ValueError("call initialize() / sample() first")
+        self._advance(1, self._engine.iteration)
+        x, lnl, lp, lnp = self._engine.state()
+        return x[0, 0], lnl[0, 0], lnp[0, 0]
+
+    # convenience accessors beyond the reference ------------------------------------------------
+    @property
+    def engine(self):
+        return self._engine
+
+    def get_state(self):
+        """Current ``(x[T][W][d], lnlike[T][W], lnprior[T][W], lnprob[T][W])`` of every chain."""
+        return self._engine.state()

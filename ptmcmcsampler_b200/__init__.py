@@ -5,13 +5,7 @@ path (MH step, adaptive covariance, DE history, temperature swap) runs in hand-w
 CUDA reached through the C ABI in ``include/ptmcmc_b200.h``.
 """
 from . import _cabi  # noqa: F401
+from . import PTMCMCSampler  # noqa: F401
+from .PTMCMCSampler import PTSampler  # noqa: F401
 
 __version__ = "0.1.0"
-
-
-def __getattr__(name):
-    if name in ("PTSampler", "PTMCMCSampler"):
-        from . import PTMCMCSampler as _m
-
-        return _m if name == "PTMCMCSampler" else _m.PTSampler
-    raise AttributeError(name)

@@ -53,7 +53,8 @@ SYMBOLS = [
     "ptmcmc_accept", "ptmcmc_iteration", "ptmcmc_sync", "ptmcmc_get_state", "ptmcmc_rows", "ptmcmc_row_base",
     "ptmcmc_get_chain", "ptmcmc_release_rows", "ptmcmc_get_adapt", "ptmcmc_get_factor", "ptmcmc_set_factor",
     "ptmcmc_get_buffers", "ptmcmc_adapt_begin", "ptmcmc_adapt_finish", "ptmcmc_njumps", "ptmcmc_get_counters",
-    "ptmcmc_get_trace", "ptmcmc_get_timing", "ptmcmc_reset_timing", "ptmcmc_stream",
+    "ptmcmc_get_trace", "ptmcmc_get_timing", "ptmcmc_reset_timing", "ptmcmc_stream", "ptmcmc_set_timing",
+    "ptmcmc_host_alloc", "ptmcmc_host_free",
 ]
 
 _lib = None
@@ -107,6 +108,11 @@ def load():
     L.ptmcmc_reset_timing.argtypes = [h]
     L.ptmcmc_stream.restype = C.c_void_p
     L.ptmcmc_stream.argtypes = [h]
+    L.ptmcmc_set_timing.argtypes = [h, C.c_int32]
+    L.ptmcmc_host_alloc.restype = C.c_void_p
+    L.ptmcmc_host_alloc.argtypes = [C.c_int64]
+    L.ptmcmc_host_free.restype = None
+    L.ptmcmc_host_free.argtypes = [C.c_void_p]
     for name in SYMBOLS:
         getattr(L, name)
     if L.ptmcmc_abi_version() != ABI_VERSION:
@@ -121,6 +127,37 @@ def _d(a):
 
 def _i(a):
     return a.ctypes.data_as(_ip)
+
+
+class _PinnedBlock(object):
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        if self.ptr and _lib is not None:
+            _lib.ptmcmc_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked memory from the engine library (falls back to pageable
+    memory when no CUDA device is present, e.g. for host-only construction)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = load().ptmcmc_host_alloc(max(n, 1))
+    if not ptr:
+        return np.empty(shape, dtype=dtype)
+    block = _PinnedBlock(ptr)
+    buf = (C.c_char * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _pinned_keepalive[id(buf)] = block  # freed when the array's buffer goes away
+    import weakref
+
+    weakref.finalize(buf, _pinned_keepalive.pop, id(buf), None)
+    return arr
+
+
+_pinned_keepalive = {}
 
 
 class EngineError(RuntimeError):
@@ -266,6 +303,8 @@ class Engine(object):
             lnl, lnp = np.empty((nrows, self.ntr, self.W)), np.empty((nrows, self.ntr, self.W))
         else:
             ch, lnl, lnp = out
+            for a in out:
+                assert a.flags["C_CONTIGUOUS"] and a.dtype == np.float64
         self._check(self._L.ptmcmc_get_chain(self._h, row0, nrows, _d(ch), _d(lnl), _d(lnp)))
         return ch, lnl, lnp
 
@@ -328,6 +367,9 @@ class Engine(object):
 
     def reset_timing(self):
         self._check(self._L.ptmcmc_reset_timing(self._h))
+
+    def set_timing(self, on):
+        self._check(self._L.ptmcmc_set_timing(self._h, int(bool(on))))
 
     @property
     def stream(self):

@@ -28,6 +28,26 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// host layout [T][W][d] <-> device layout [T][d][W]; one block per (walker tile, rung)
+__global__ void __launch_bounds__(256) to_device_layout_kernel(const double *src, double *dst, int d, int W)
+{
+    const int t = blockIdx.y;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long long)W * d;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(idx / d), k = (int)(idx % d);
+        dst[((size_t)t * d + k) * W + w] = src[((size_t)t * W + w) * d + k];
+    }
+}
+__global__ void __launch_bounds__(256) to_host_layout_kernel(const double *src, double *dst, int d, int W)
+{
+    const int t = blockIdx.y;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long long)W * d;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(idx / d), k = (int)(idx % d);
+        dst[((size_t)t * W + w) * d + k] = src[((size_t)t * d + k) * W + w];
+    }
+}
+
 struct Engine {
     ptmcmc_config cfg{};
     int d = 0, W = 0, T = 0, ngroups = 0, njumps = 3, ntr = 1;
@@ -58,6 +78,7 @@ struct Engine {
     short *d_swapmaps = nullptr;
     int *d_map = nullptr;
     double *d_part = nullptr, *d_part2 = nullptr, *d_batch = nullptr;
+    double *d_stage = nullptr;  // [T][W][d] staging in the host layout
     int mom_blocks = 0;
     // host-callback path staging
     double *d_q = nullptr, *d_qxy = nullptr, *d_lnl_new = nullptr, *d_lp_new = nullptr;
@@ -376,6 +397,7 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         CUDA_TRY(nullptr, dalloc(&e->lnl[b], C));
         CUDA_TRY(nullptr, dalloc(&e->lp[b], C));
     }
+    CUDA_TRY(nullptr, dalloc(&e->d_stage, C * d));
     CUDA_TRY(nullptr, dalloc(&e->d_ladder, T));
     CUDA_TRY(nullptr, dalloc(&e->d_mh_temp, T));
     CUDA_TRY(nullptr, cudaMemcpy(e->d_ladder, e->ladder.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
@@ -453,15 +475,6 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         if (smem > 48 * 1024)
             CUDA_TRY(nullptr, cudaFuncSetAttribute(moments_m2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const bool external = cfg->logl_kind == PTMCMC_LOGL_EXTERNAL || cfg->logp_kind == PTMCMC_LOGP_EXTERNAL || e->njumps > 3;
-    if (external) {
-        CUDA_TRY(nullptr, dalloc(&e->d_q, C * d));
-        CUDA_TRY(nullptr, dalloc(&e->d_qxy, C));
-        CUDA_TRY(nullptr, dalloc(&e->d_lnl_new, C));
-        CUDA_TRY(nullptr, dalloc(&e->d_lp_new, C));
-        CUDA_TRY(nullptr, dalloc(&e->d_jump, C));
-        CUDA_TRY(nullptr, dalloc(&e->d_wordpos, C));
-    }
     // initial factor (ref :138-145)
     cudaError_t st = launch_factor(e, nullptr, 0.0, 0);
     if (st != cudaSuccess) return fail(nullptr, PTMCMC_ERR_CUDA, "initial factorisation: %s", cudaGetErrorString(st));
@@ -495,7 +508,7 @@ void ptmcmc_destroy(ptmcmc_engine *h)
                     e->d_soff, e->d_ord, e->d_work_a, e->d_work_v, e->d_am, e->d_de, e->d_gmu, e->d_gP,
                     e->d_plo, e->d_phi, e->d_rec_x, e->d_rec_lnl, e->d_rec_lnp, e->d_prop, e->d_acc,
                     e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_part, e->d_part2, e->d_batch,
-                    e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos};
+                    e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos, e->d_stage};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -504,16 +517,17 @@ void ptmcmc_destroy(ptmcmc_engine *h)
     delete e;
 }
 
-// host [T][W][d] -> device [T][d][W]
+// host [T][W][d] -> device [T][d][W]: one DMA into the staging buffer, transposed on the device
 static int upload_state(Engine *e, const double *x0)
 {
     const int d = e->d, W = e->W, T = e->T;
-    std::vector<double> tmp((size_t)T * W * d);
-    for (int t = 0; t < T; ++t)
-        for (int w = 0; w < W; ++w)
-            for (int k = 0; k < d; ++k) tmp[((size_t)t * d + k) * W + w] = x0[((size_t)t * W + w) * d + k];
-    CUDA_TRY(e, cudaMemcpyAsync(e->x[e->cur], tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    const size_t n = (size_t)T * W * d;
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_stage, x0, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    dim3 grid((unsigned)std::min<long long>(((long long)W * d + 255) / 256, 4096), (unsigned)T);
+    to_device_layout_kernel<<<grid, 256, 0, e->stream>>>(e->d_stage, e->x[e->cur], d, W);
+    e->tm.launches[PTMCMC_K_INIT] += 1;
+    CUDA_TRY(e, cudaGetLastError());
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // x0 may be reused by the caller
     return 0;
 }
 
@@ -602,7 +616,15 @@ int32_t ptmcmc_propose(ptmcmc_engine *h, double *q, int32_t *jump)
     if (!e || !q || !jump) return PTMCMC_ERR_ARG;
     if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose before set_state");
     if (e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose called twice");
-    if (!e->d_q) return fail(e, PTMCMC_ERR_STATE, "engine was created without external targets or jumps");
+    if (!e->d_q) {  // staging for the host round trip, allocated on first use
+        const size_t C0 = (size_t)e->T * e->W;
+        CUDA_TRY(e, dalloc(&e->d_q, C0 * e->d));
+        CUDA_TRY(e, dalloc(&e->d_qxy, C0));
+        CUDA_TRY(e, dalloc(&e->d_lnl_new, C0));
+        CUDA_TRY(e, dalloc(&e->d_lp_new, C0));
+        CUDA_TRY(e, dalloc(&e->d_jump, C0));
+        CUDA_TRY(e, dalloc(&e->d_wordpos, C0));
+    }
     const long long it0 = e->iter + 1;
     int rc = check_rows(e, it0);
     if (rc) return rc;
@@ -676,11 +698,12 @@ int32_t ptmcmc_get_state(ptmcmc_engine *h, double *x, double *lnl, double *lnpri
     const size_t C = (size_t)T * W;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     if (x) {
-        std::vector<double> tmp(C * d);
-        CUDA_TRY(e, cudaMemcpy(tmp.data(), e->x[e->cur], sizeof(double) * C * d, cudaMemcpyDeviceToHost));
-        for (int t = 0; t < T; ++t)
-            for (int k = 0; k < d; ++k)
-                for (int w = 0; w < W; ++w) x[((size_t)t * W + w) * d + k] = tmp[((size_t)t * d + k) * W + w];
+        dim3 grid((unsigned)std::min<long long>(((long long)W * d + 255) / 256, 4096), (unsigned)T);
+        to_host_layout_kernel<<<grid, 256, 0, e->stream>>>(e->x[e->cur], e->d_stage, d, W);
+        e->tm.launches[PTMCMC_K_INIT] += 1;
+        CUDA_TRY(e, cudaGetLastError());
+        CUDA_TRY(e, cudaMemcpyAsync(x, e->d_stage, sizeof(double) * C * d, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     }
     std::vector<double> l, p_;
     if (lnl || lnprob) {
@@ -899,5 +922,26 @@ int32_t ptmcmc_reset_timing(ptmcmc_engine *h)
 }
 
 void *ptmcmc_stream(ptmcmc_engine *h) { return h ? (void *)((Engine *)h)->stream : nullptr; }
+
+int32_t ptmcmc_set_timing(ptmcmc_engine *h, int32_t on)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->cfg.timing = on ? 1 : 0;
+    return 0;
+}
+
+void *ptmcmc_host_alloc(int64_t bytes)
+{
+    void *p = nullptr;
+    if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void ptmcmc_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
 
 }  // extern "C"

@@ -453,8 +453,15 @@ __global__ void __launch_bounds__(MH_THREADS) accept_kernel(const DevParams p, c
               (uint32_t)(p.temp_offset + t));
     st.seek(word_pos[c]);
     const int jump = jump_in[c];
-    const double lpn = lp_new[c];
-    const double lnpn = (lpn == neg_inf()) ? neg_inf() : beta * lnl_new[c] + lpn;  // ref :607-612
+    // built-in targets are evaluated here; external ones come from the host (ref :605-612)
+    double qv[MAX_GENERIC_DIM];
+    for (int k = 0; k < d; ++k) qv[k] = q_in[c * d + k];
+    const double lpn = (p.logp_kind != LOGP_EXTERNAL) ? eval_logp_generic(p, qv) : lp_new[c];
+    double lnln = 0.0, lnpn = neg_inf();
+    if (lpn != neg_inf()) {
+        lnln = (p.logl_kind != LOGL_EXTERNAL) ? eval_logl_generic(p, qv) : lnl_new[c];
+        lnpn = beta * lnln + lpn;
+    }
     const double lnp0 = beta * p.lnl[c] + p.lp[c];
     const double diff = lnpn - lnp0 + qxy[c];
     const double u = word_to_unit(st.next());
@@ -462,8 +469,8 @@ __global__ void __launch_bounds__(MH_THREADS) accept_kernel(const DevParams p, c
     const size_t TW = (size_t)T * W;
     if (accept) {
         double *xg = p.x + (size_t)t * d * W + w;
-        for (int k = 0; k < d; ++k) xg[(size_t)k * W] = q_in[c * d + k];
-        p.lnl[c] = lnl_new[c];
+        for (int k = 0; k < d; ++k) xg[(size_t)k * W] = qv[k];
+        p.lnl[c] = lnln;
         p.lp[c] = lpn;
         p.acc[jump * TW + c] += 1;
     }

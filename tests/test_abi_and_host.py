@@ -1,0 +1,118 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares (no compute
+calls without a GPU), and the host-side mirror of the reference API behaves like the reference
+where no device is involved."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ptmcmcsampler_b200 import PTMCMCSampler, _cabi, nompi4py
+from ptmcmcsampler_b200.likelihoods import CurvedLikelihood, GaussianLikelihood, UniformPrior
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ptmcmc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ptmcmc_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.load()
+    names = declared_symbols()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(lib, name), name
+    assert sorted(_cabi.SYMBOLS) == names
+    assert lib.ptmcmc_abi_version() == _cabi.ABI_VERSION
+
+
+def test_config_struct_layout_matches_header():
+    # the header's struct, compiled by gcc, must have the size ctypes computes
+    import subprocess
+    import tempfile
+
+    src = '#include <stdio.h>\n#include "ptmcmc_b200.h"\nint main(){printf("%zu %zu\\n", sizeof(ptmcmc_config), sizeof(ptmcmc_timing));return 0;}\n'
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "sz.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "sz")
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        a, b = subprocess.check_output([exe]).split()
+    assert int(a) == ctypes.sizeof(_cabi.Config)
+    assert int(b) == ctypes.sizeof(_cabi.Timing)
+
+
+def test_engine_fails_loudly_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_cabi.EngineError) as ei:
+        _cabi.Engine(3, 2, 2, np.eye(3), np.array([1.0, 2.0]), logl_params=np.zeros(13), logp_params=np.zeros(8))
+    assert "no CUDA device" in str(ei.value)
+
+
+def test_sampler_host_surface(tmp_path):
+    out = str(tmp_path / "chains")
+    lk, pr = GaussianLikelihood(np.zeros(4), cov=np.eye(4)), UniformPrior(-5, 5)
+    s = PTMCMCSampler.PTSampler(4, lk, pr, np.eye(4), outDir=out, verbose=False, seed=3, ntemps=5)
+    assert os.path.isdir(out) and s.nchain == 5 and s.MPIrank == 0
+    # ladder formula, ref :709-718
+    assert np.allclose(s.temperatureLadder(1), (1 + np.sqrt(2 / 4.0)) ** np.arange(5))
+    assert np.allclose(s.temperatureLadder(2.0, Tmax=32.0), 2.0 * 2.0 ** np.arange(5))
+    # plugin registry, ref :988-1014
+    def myjump(x, it, beta):
+        return x, 0.0
+    s.addProposalToCycle(myjump, 0)
+    assert s.propCycle == [] and "myjump" not in s.jumpDict
+    s.addProposalToCycle(myjump, 3)
+    s.addProposalToCycle(s.covarianceJumpProposalSCAM, 2)
+    assert len(s.propCycle) == 5 and s.jumpDict["myjump"] == [0, 0]
+    assert os.path.isfile(os.path.join(out, "myjump_jump.txt"))
+    assert s._cycle_segments() == [(_cabi.JUMP_EXT0, 3), (_cabi.JUMP_SCAM, 2)]
+    s.addAuxilaryJump(lambda x, q, it, beta: (q, 0.0))
+    assert len(s.aux) == 1 and s._external
+    one = PTMCMCSampler.PTSampler(4, lk, pr, np.eye(4), outDir=out, verbose=False)
+    assert np.array_equal(one.temperatureLadder(1), np.array([1]))
+
+
+def test_sampler_rejects_bad_arguments_before_touching_the_device(tmp_path):
+    out = str(tmp_path / "chains")
+    lk, pr = GaussianLikelihood(np.zeros(3), cov=np.eye(3)), UniformPrior(-5, 5)
+    s = PTMCMCSampler.PTSampler(3, lk, pr, np.eye(3), outDir=out, verbose=False)
+    with pytest.raises(ValueError):
+        s.sample(np.zeros(3), 100, isave=15, thin=10)
+    with pytest.raises(ValueError):
+        PTMCMCSampler.PTSampler(3, lk, pr, np.eye(4), outDir=out)
+
+    class FakeWorld(nompi4py.MPIDummy):
+        def Get_size(self):
+            return 4
+
+    with pytest.raises(NotImplementedError):
+        PTMCMCSampler.PTSampler(3, lk, pr, np.eye(3), outDir=out, comm=FakeWorld())
+
+
+def test_target_descriptors():
+    lk = GaussianLikelihood(np.arange(3.0), cov=2 * np.eye(3), offset=1.5)
+    p = lk.params(3)
+    assert p.shape == (13,) and np.allclose(p[3:12].reshape(3, 3), 0.5 * np.eye(3)) and p[-1] == 1.5
+    with pytest.raises(ValueError):
+        lk.params(4)
+    with pytest.raises(ValueError):
+        GaussianLikelihood(np.zeros(2))
+    pr = UniformPrior(-1.0, [1.0, 2.0], inclusive=False, value=-3.0)
+    assert np.array_equal(pr.params(2), [-1, -1, 1, 2, -3, 0])
+    assert CurvedLikelihood().kind == _cabi.LOGL_CURVED and CurvedLikelihood().params(4) is None
+
+
+def test_shift_array_semantics():
+    a = np.arange(12.0).reshape(6, 2)
+    assert np.array_equal(PTMCMCSampler.shift_array(a, -2)[:4], a[2:])
+    assert np.all(PTMCMCSampler.shift_array(a, -2)[4:] == 0)
+    assert np.array_equal(PTMCMCSampler.shift_array(a, 2)[2:], a[:4])
+    assert np.array_equal(PTMCMCSampler.shift_array(a, 0), a)

@@ -1,0 +1,152 @@
+"""The reference-facing API on the GPU: tests written like the reference's own
+(tests/test_simple.py) plus statistical parity against the reference's golden bands."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from ptmcmcsampler_b200 import PTMCMCSampler, nompi4py as MPIDUMMY
+from ptmcmcsampler_b200.likelihoods import GaussianLikelihood, UniformPrior
+
+from _helpers import load
+
+pytestmark = pytest.mark.gpu
+
+
+class GaussianLikelihoodPy(object):
+    """The reference's test fixture (ref tests/test_simple.py:14-41), plain Python callables."""
+
+    def __init__(self, ndim=2, pmin=-10, pmax=10):
+        self.a = np.ones(ndim) * pmin
+        self.b = np.ones(ndim) * pmax
+        self.mu = np.random.uniform(pmin, pmax, ndim)
+        cov = 0.5 - np.random.rand(ndim**2).reshape((ndim, ndim))
+        cov = np.triu(cov)
+        cov += cov.T - np.diag(cov.diagonal())
+        self.cov = np.dot(cov, cov)
+        self.icov = np.linalg.inv(self.cov)
+
+    def lnlikefn(self, x):
+        diff = x - self.mu
+        return -np.dot(diff, np.dot(self.icov, diff)) / 2.0
+
+    def lnpriorfn(self, x):
+        if np.all(self.a <= x) and np.all(self.b >= x):
+            return 0.0
+        return -np.inf
+
+
+class UniformJump(object):
+    def __init__(self, pmin, pmax):
+        self.pmin, self.pmax = pmin, pmax
+
+    def jump(self, x, it, beta):
+        return np.random.uniform(self.pmin, self.pmax, len(x)), 0
+
+
+@pytest.fixture
+def outdir(tmp_path):
+    d = str(tmp_path / "chains")
+    yield d
+    shutil.rmtree(d, ignore_errors=True)
+
+
+def test_simple_python_callables_and_custom_jump(outdir):
+    """ref tests/test_simple.py::test_simple, shortened: Python logl/logp + UniformJump plugin."""
+    np.random.seed(0)
+    ndim, pmin, pmax = 20, 0.0, 10.0
+    glo = GaussianLikelihoodPy(ndim=ndim, pmin=pmin, pmax=pmax)
+    p0 = np.random.uniform(pmin, pmax, ndim)
+    cov = np.eye(ndim) * 0.1**2
+    sampler = PTMCMCSampler.PTSampler(ndim, glo.lnlikefn, glo.lnpriorfn, np.copy(cov), outDir=outdir,
+                                      comm=MPIDUMMY.COMM_WORLD, verbose=False, seed=1)
+    ujump = UniformJump(pmin, pmax)
+    sampler.addProposalToCycle(ujump.jump, 5)
+    sampler.sample(p0, 1500, burn=500, thin=1, covUpdate=500, SCAMweight=20, AMweight=20, DEweight=20)
+    assert os.path.isfile(os.path.join(outdir, "chain_1.txt"))
+    data = np.loadtxt(os.path.join(outdir, "chain_1.txt"))
+    assert data.shape == (1501, ndim + 4)
+    assert np.allclose(data[:, :ndim], sampler._chain, atol=0)
+    for name in ("covarianceJumpProposalSCAM", "covarianceJumpProposalAM", "DEJump", "jump"):
+        assert os.path.isfile(os.path.join(outdir, name + "_jump.txt"))
+        assert sampler.jumpDict[name][0] > 0
+    assert sum(v[0] for v in sampler.jumpDict.values()) == 1500
+    assert os.path.isfile(os.path.join(outdir, "cov.npy")) and os.path.isfile(os.path.join(outdir, "jumps.txt"))
+    # lnlike column is the user's function of the recorded point
+    assert np.allclose(data[-1, ndim + 1], glo.lnlikefn(data[-1, :ndim]), rtol=1e-6, atol=1e-5)
+    assert sampler._AMbuffer.shape == (500, ndim) and sampler._DEbuffer.shape == (500, ndim)
+
+
+def test_error_conventions(outdir):
+    lk = GaussianLikelihood(np.zeros(3), cov=np.eye(3))
+    pr = UniformPrior(-5, 5)
+    s = PTMCMCSampler.PTSampler(3, lk, pr, np.eye(3), outDir=outdir, verbose=False, seed=2)
+    with pytest.raises(ValueError):  # ref :434-435
+        s.sample(np.zeros(3), 100, isave=15, thin=10)
+    s = PTMCMCSampler.PTSampler(3, lk, pr, np.eye(3), outDir=outdir, verbose=False, seed=2)
+    with pytest.raises(ValueError):  # ref :267-268
+        s.sample(np.zeros(3), 100, SCAMweight=0, AMweight=0)
+    s = PTMCMCSampler.PTSampler(3, lk, pr, np.eye(3), outDir=outdir, verbose=False, seed=2)
+    with pytest.raises(ValueError):  # covUpdate > burn: ref :817 broadcast error at the first DE update
+        s.sample(np.zeros(3), 100, covUpdate=50, burn=20, thin=1, isave=10)
+
+
+def _run_device(g, W, T, N, outdir, seed, thin=1):
+    d = int(g["d"])
+    lk = GaussianLikelihood(g["pb_mu"], icov=g["pb_icov"])
+    pr = UniformPrior(g["pb_lo"], g["pb_hi"])
+    s = PTMCMCSampler.PTSampler(d, lk, pr, np.eye(d) * 0.01, outDir=outdir, verbose=False, seed=seed, ntemps=T,
+                                nwalkers=W)
+    lo = max(float(g["pb_lo"][0]), 0.0)
+    hi = min(float(g["pb_hi"][0]), 10.0)
+    p0 = np.random.default_rng(seed).uniform(lo, hi, (T, W, d))
+    s.sample(p0, N, burn=int(g["kw_burn"]), thin=thin, covUpdate=int(g["kw_covUpdate"]), SCAMweight=20, AMweight=20,
+             DEweight=20, isave=N, Tskip=int(g["kw_Tskip"]), writeHotChains=T > 1)
+    return s
+
+
+def _band(ref_values, engine_value, nsig=3.0, floor=0.0):
+    """engine value inside mean +- nsig * (standard error of the reference's repeats + floor)."""
+    m = ref_values.mean(axis=0)
+    se = ref_values.std(axis=0, ddof=1) / np.sqrt(ref_values.shape[0])
+    return np.abs(engine_value - m) <= nsig * np.sqrt(se**2 + floor**2)
+
+
+@pytest.mark.parametrize("name", ["stats_t1_d8", "stats_t1_d8_box"])
+def test_posterior_matches_reference_band(name, outdir):
+    """Posterior mean / variance / acceptance of the T=1 chain against the reference's own runs
+    (mean over repeats +- 3 standard errors; the engine's error is negligible with 4096 walkers)."""
+    g = load(name)
+    N, W, thin = int(g["N"]), 1024, 10   # same length as the reference runs
+    s = _run_device(g, W, 1, N, outdir, seed=31, thin=thin)
+    x = s._chain_all[int(N * float(g["burn_frac"])) // thin:]  # [n][W][d]
+    mean, var = x.mean(axis=(0, 1)), x.var(axis=(0, 1))
+    assert np.all(_band(g["means"][:, 0], mean, floor=0.01)), (mean, g["means"][:, 0].mean(0))
+    assert np.all(_band(g["vars"][:, 0], var, floor=0.02 * var.max()))
+    acc = s.naccepted / N
+    assert _band(g["acc"][:, 0], acc, floor=0.01)
+    jacc = np.array([s.jumpDict[k][1] / s.jumpDict[k][0] for k in
+                     ("covarianceJumpProposalSCAM", "covarianceJumpProposalAM", "DEJump")])
+    assert np.all(_band(g["jump_acc"][:, 0], jacc, floor=0.02)), (jacc, g["jump_acc"][:, 0].mean(0))
+    if name == "stats_t1_d8":
+        # analytic known answer: untruncated Gaussian target
+        cov = g["pb_cov"]
+        assert np.allclose(mean, g["pb_mu"], atol=0.03)
+        assert np.allclose(var, np.diag(cov), rtol=0.03)
+
+
+def test_tempered_posteriors_match_reference_band(outdir):
+    g = load("stats_t4_d8")
+    T, N, W = 4, int(g["N"]), 1024
+    s = _run_device(g, W, T, N, outdir, seed=41, thin=10)
+    x, lnl, lp, lnp = s.get_state()
+    # cov at temperature T is T * Sigma for the untruncated Gaussian (SURVEY.md 8c KAT 1)
+    var_ratio = x.var(axis=1) / np.diag(g["pb_cov"])[None, :]
+    assert np.allclose(var_ratio.mean(axis=1), g["ladder"], rtol=0.06), var_ratio.mean(axis=1)
+    swap = s.nswap_accepted_all.mean(axis=1) / s.swapProposed
+    assert np.all(_band(g["swap"][:, :T - 1], swap[:T - 1], floor=0.02)), (swap, g["swap"].mean(0))
+    acc = s.naccepted_all.mean(axis=1) / N
+    assert np.all(_band(g["acc"], acc, floor=0.015)), (acc, g["acc"].mean(0))
+    for t in range(1, T):
+        assert os.path.isfile(os.path.join(outdir, "chain_{0}.txt".format(s.ladder[t])))
