@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,6 +18,7 @@
 #include "../../include/ptmcmc_b200.h"
 #include "adapt_kernels.cuh"
 #include "mh_kernels.cuh"
+#include "mh_sorted_kernel.cuh"
 #include "params.h"
 #include "swap_kernels.cuh"
 
@@ -88,6 +90,7 @@ struct Engine {
     ptmcmc_timing tm{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
+    int mh_variant = 0;  // 0: sorted shared-memory kernel, 1: thread-per-chain register kernel, 2: generic
 };
 
 int fail(Engine *e, int code, const char *fmt, ...)
@@ -186,13 +189,41 @@ cudaError_t launch_reg(const Engine *e, const DevParams &p)
     return cudaGetLastError();
 }
 
+constexpr int SORT_NC = 256, SORT_MINB = 2;
+
+template <int DP>
+cudaError_t launch_sorted(const Engine *e, const DevParams &p)
+{
+    const size_t smem = sizeof(SortedSmem<DP, SORT_NC>);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t st = cudaFuncSetAttribute(mh_sorted_kernel<DP, SORT_NC, SORT_MINB>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (st != cudaSuccess) return st;
+        attr_done = true;
+    }
+    const int blocks = (int)(((long long)e->T * e->W + SORT_NC - 1) / SORT_NC);
+    mh_sorted_kernel<DP, SORT_NC, SORT_MINB><<<blocks, SORT_NC, smem, e->stream>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mh(Engine *e, long long it0, long long it1, bool tail)
 {
     DevParams p = make_params(e);
     p.it0 = it0; p.it1 = it1; p.tail = tail ? 1 : 0;
     LaunchTimer lt(e, PTMCMC_K_MH);
     e->tm.chain_steps += (it1 - it0 + 1) * (long long)e->T * e->W;
-    if (fast_reg_path(e)) {
+    if (fast_reg_path(e) && e->mh_variant == 0) {
+        const int d = e->d;
+        if (d <= 4) return launch_sorted<4>(e, p);
+        if (d <= 8) return launch_sorted<8>(e, p);
+        if (d <= 12) return launch_sorted<12>(e, p);
+        if (d <= 16) return launch_sorted<16>(e, p);
+        if (d <= 20) return launch_sorted<20>(e, p);
+        if (d <= 24) return launch_sorted<24>(e, p);
+        return launch_sorted<32>(e, p);
+    }
+    if (fast_reg_path(e) && e->mh_variant == 1) {
         const int d = e->d;
         if (d <= 4) return launch_reg<4>(e, p);
         if (d <= 8) return launch_reg<8>(e, p);
@@ -391,6 +422,7 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     }
     if (e->cyc_jump.empty()) return fail(nullptr, PTMCMC_ERR_ARG, "No jump proposals specified!");
     e->ntr = cfg->record_hot ? T : 1;
+    if (const char *v = getenv("PTMCMC_MH_VARIANT")) e->mh_variant = atoi(v);
     const size_t C = (size_t)T * W;
     for (int b = 0; b < 2; ++b) {
         CUDA_TRY(nullptr, dalloc(&e->x[b], C * d));
