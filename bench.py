@@ -230,7 +230,7 @@ def run_engine(args, rank, world, local_rank):
     steps_per_launch = W * T * ITERS * args.steps / max(1, mh_launches)
     achieved = bpcs * steps_per_launch / (mh_ms / max(1, mh_launches) * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "mh_reg_kernel<20>", "peak_source": peak_src,
+                "traffic": None, "kernel": "mh_sorted_kernel<20,256,2>", "peak_source": peak_src,
                 "algorithmic_bytes_per_chain_step": bpcs, "launches": mh_launches,
                 "avg_launch_ms": mh_ms / max(1, mh_launches),
                 "kernel_share_of_step": mh_ms / sum(tm["ms"].values()) if sum(tm["ms"].values()) > 0 else None,
@@ -238,7 +238,7 @@ def run_engine(args, rank, world, local_rank):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("mh_reg_kernel_dram_bytes_per_launch")
+            roofline["traffic"] = json.load(open(prof)).get("mh_kernel_dram_bytes_per_launch")
         except Exception:
             pass
     gpu_launches = int(sum(tm["launches"].values()))
