@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PTMCMC_ABI_VERSION 1
+#define PTMCMC_ABI_VERSION 2
 
 /* jump ids: the reference's built-in proposals; ids >= PTMCMC_JUMP_EXT0 are
  * host-side (Python) proposals registered with addProposalToCycle (ref :988-1014) */
@@ -59,7 +59,7 @@ typedef struct ptmcmc_config {
     int32_t ntemps;             /* T: ref nchain = comm.Get_size() (:97) */
     int32_t walker_offset;      /* global id of local walker 0 (keys the RNG; walker sharding) */
     int32_t temp_offset;        /* global index of local rung 0 (keys the RNG; ladder sharding) */
-    int32_t reserved0;
+    int32_t ntemps_global;      /* rungs of the whole ladder when it is sharded over engines (0 = ntemps) */
     uint64_t seed;              /* ref seed (:92); Philox key */
     const double *ladder;       /* [T] swap temperatures, ref self.ladder (:274-275, :658) */
     const double *mh_temp;      /* [T] MH temperatures, ref self.temp (:278-282; 1e80 for hotChain); NULL = ladder */
@@ -86,6 +86,8 @@ typedef struct ptmcmc_config {
     int64_t trace_iters;        /* capacity of the trace, in iterations (0 if trace == 0) */
     int32_t timing;             /* 1: bracket every launch with CUDA events (ptmcmc_get_timing) */
     int32_t reserved2;
+    double ladder_above;        /* ladder sharding: temperature of rung temp_offset+ntemps (hotter neighbour) */
+    double ladder_below;        /* ladder sharding: temperature of rung temp_offset-1 (colder neighbour) */
 } ptmcmc_config;
 
 typedef struct ptmcmc_engine ptmcmc_engine;
@@ -159,6 +161,30 @@ int32_t ptmcmc_get_buffers(ptmcmc_engine *e, double *am, double *de);
  * M2c[d*d]} and return 1 (0 if none is due).  finish: apply the (all-reduced) batch. */
 int32_t ptmcmc_adapt_begin(ptmcmc_engine *e, double *batch_out);
 int32_t ptmcmc_adapt_finish(ptmcmc_engine *e, const double *batch_in);
+
+/* Ladder sharding (ntemps_global > ntemps): the swap sweep (ref PTswap :631-697) cut at the shard
+ * boundaries; replaces the reference's gather / scatter to rank 0 (ref :660-661, :689-691) by a
+ * nearest-neighbour exchange of one rung.  ptmcmc_run stops at every swap iteration (it refuses to
+ * cross one) and leaves the swap pending; the caller then moves three messages between neighbours:
+ *   1. ptmcmc_swap_pack_top(msg_up)            -> send to the hotter neighbour (no dependency)
+ *   2. ptmcmc_swap_sweep(carry_in, carry_out)  carry_in: received from the hotter neighbour (NULL on
+ *      the hottest shard); carry_out: to send to the colder neighbour (NULL on the coldest shard)
+ *   3. ptmcmc_swap_finish(below_top)           below_top: the colder neighbour's msg_up (NULL on the
+ *      coldest shard).  Applies the permutation and the iteration's buffer/record writes (ref :627).
+ * Both sides of a boundary evaluate the same acceptance from the counter-based stream.  A message is
+ * ptmcmc_swap_msg_doubles() doubles in DEVICE memory: x[ndim][W], lnl[W], lnprior[W], origin rung[W].
+ * carry_in must stay valid until ptmcmc_swap_finish returns. */
+int64_t ptmcmc_swap_msg_doubles(const ptmcmc_engine *e);
+int32_t ptmcmc_swap_pending(const ptmcmc_engine *e);
+int32_t ptmcmc_swap_pack_top(ptmcmc_engine *e, double *dev_msg);
+int32_t ptmcmc_swap_sweep(ptmcmc_engine *e, const double *dev_carry_in, double *dev_carry_out);
+int32_t ptmcmc_swap_finish(ptmcmc_engine *e, const double *dev_below_top);
+/* device address and length of the AM ring: the cold shard broadcasts it before a DE update, the
+ * multi-device form of rank 0's send(_DEbuffer) (ref :563-571) */
+int32_t ptmcmc_am_ring(ptmcmc_engine *e, void **dev_ptr, int64_t *ndoubles);
+/* run now the covariance / DE maintenance due at the start of the next iteration (ref :545-585);
+ * ptmcmc_run will not repeat it.  Lets the caller place collectives around it. */
+int32_t ptmcmc_maintain(ptmcmc_engine *e);
 
 /* ref jumpDict[name] = [proposed, accepted] (:602, :622) per chain: prop/acc are [T][W][njumps];
  * nswap_accepted per chain [T][W] (:691) and swapProposed (:692) */

@@ -39,6 +39,7 @@ class _Config(C.Structure):
         ("logp_kind", C.c_int32), ("logp_params", C.POINTER(C.c_double)),
         ("record_hot", C.c_int32), ("max_rows", C.c_int64), ("nthreads", C.c_int32),
         ("ext_logl", LOGFN), ("ext_logp", LOGFN), ("ext_jump", JUMPFN), ("user", C.c_void_p),
+        ("ntemps_global", C.c_int32), ("ladder_above", C.c_double), ("ladder_below", C.c_double),
     ]
 
 
@@ -80,6 +81,15 @@ def lib():
         L.orc_get_buffers.argtypes = [C.c_void_p, dp, dp]
         L.orc_get_counters.argtypes = [C.c_void_p, i64p, i64p, i64p, i64p]
         L.orc_set_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_int64, C.POINTER(C.c_int16), C.c_int64]
+        L.orc_swap_msg_doubles.restype = C.c_int64
+        L.orc_swap_msg_doubles.argtypes = [C.c_void_p]
+        L.orc_swap_pending.argtypes = [C.c_void_p]
+        L.orc_swap_pack_top.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_swap_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_swap_finish.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_maintain.argtypes = [C.c_void_p]
+        L.orc_am_ring.restype = C.c_void_p
+        L.orc_am_ring.argtypes = [C.c_void_p]
         L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.orc_draw_word.restype = C.c_uint64
         L.orc_draw_word.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -159,7 +169,8 @@ class Oracle(object):
                  cycle=((JUMP_SCAM, 20), (JUMP_AM, 20)), de_weight=20, cov_update=1000, burn=10000,
                  tskip=100, thin=10, logl_kind=LOGL_GAUSSIAN, logl_params=None,
                  logp_kind=LOGP_UNIFORM, logp_params=None, record_hot=False, max_rows=1,
-                 nthreads=1, walker_offset=0, temp_offset=0, ext_logl=None, ext_logp=None, ext_jump=None):
+                 nthreads=1, walker_offset=0, temp_offset=0, ext_logl=None, ext_logp=None, ext_jump=None,
+                 ntemps_global=0, ladder_above=0.0, ladder_below=0.0):
         L = lib()
         self.d, self.W, self.T = ndim, nwalkers, ntemps
         self.cov_update, self.burn = cov_update, burn
@@ -215,6 +226,8 @@ class Oracle(object):
             f = JUMPFN(_j)
             self._keep.append(f)
             cfg.ext_jump = f
+        cfg.ntemps_global, cfg.ladder_above, cfg.ladder_below = int(ntemps_global), float(ladder_above), float(ladder_below)
+        self.temp_offset, self.ntemps_global = int(temp_offset), int(ntemps_global) or int(ntemps)
         self.ntr = ntemps if record_hot else 1
         self.usize = sum(len(g) ** 2 for g in self.groups)
         self.ssize = sum(len(g) for g in self.groups)
@@ -288,6 +301,37 @@ class Oracle(object):
         i64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))  # noqa: E731
         lib().orc_get_counters(self._h, i64(prop), i64(acc), i64(sw), C.byref(n))
         return prop, acc, sw, n.value
+
+    # ---- ladder sharding (same surface as ptmcmcsampler_b200._cabi.Engine; pointers are host addresses)
+    @property
+    def swap_msg_doubles(self):
+        return int(lib().orc_swap_msg_doubles(self._h))
+
+    @property
+    def swap_pending(self):
+        return bool(lib().orc_swap_pending(self._h))
+
+    def swap_pack_top(self, msg_ptr):
+        lib().orc_swap_pack_top(self._h, msg_ptr)
+
+    def swap_sweep(self, carry_in_ptr, carry_out_ptr):
+        rc = lib().orc_swap_sweep(self._h, carry_in_ptr or None, carry_out_ptr or None)
+        if rc:
+            raise ValueError("oracle swap_sweep failed rc=%d" % rc)
+
+    def swap_finish(self, below_ptr):
+        rc = lib().orc_swap_finish(self._h, below_ptr or None)
+        if rc:
+            raise ValueError("oracle swap_finish failed rc=%d" % rc)
+
+    def maintain(self):
+        rc = lib().orc_maintain(self._h)
+        if rc:
+            raise ValueError("oracle maintain failed rc=%d" % rc)
+
+    def am_ring(self):
+        """(host address, number of doubles) of the AM ring."""
+        return int(lib().orc_am_ring(self._h)), self.cov_update * self.W * self.d
 
     def set_trace(self, niter, nswaps=0):
         self.trace = np.zeros((niter, self.T, self.W), dtype=np.uint8)

@@ -260,6 +260,13 @@ struct orc_sampler {
     /* trace */
     uint8_t *trace; int64_t trace_iters, trace_pos;
     int16_t *swapmaps; int64_t swap_events, swap_pos;
+    int64_t adapt_done, de_done; /* boundaries whose maintenance already ran */
+    /* ladder sharding */
+    int Tg, sharded, pending_swap, swept;
+    int *smap;          /* [T][W] source code of every local position: 0..T-1 local rung, T carry_in */
+    int *carry_code;    /* [W] */
+    double *carry_L;    /* [W] */
+    const double *carry_in;
 };
 
 static int usize(const orc_sampler *s) { return s->uoff[s->ngroups]; }
@@ -356,6 +363,12 @@ orc_sampler *orc_create(const orc_config *cfg)
     s->prop = (int64_t *)calloc(C * s->njumps, sizeof(int64_t));
     s->acc = (int64_t *)calloc(C * s->njumps, sizeof(int64_t));
     s->swap_acc = (int64_t *)calloc(C, sizeof(int64_t));
+    s->adapt_done = s->de_done = -1;
+    s->Tg = cfg->ntemps_global > 0 ? cfg->ntemps_global : T;
+    s->sharded = s->Tg > T;
+    s->smap = (int *)calloc(C, sizeof(int));
+    s->carry_code = (int *)calloc(W, sizeof(int));
+    s->carry_L = (double *)calloc(W, sizeof(double));
     return s;
 }
 
@@ -367,6 +380,7 @@ void orc_destroy(orc_sampler *s)
     free(s->mu); free(s->m2); free(s->U); free(s->S); free(s->am); free(s->de); free(s->rec_x);
     free(s->rec_lnl); free(s->rec_lnp); free(s->prop); free(s->acc); free(s->swap_acc);
     free(s->inj_U); free(s->inj_S);
+    free(s->smap); free(s->carry_code); free(s->carry_L);
     free(s);
 }
 
@@ -673,6 +687,31 @@ static int64_t next_boundary(const orc_sampler *s, int64_t it)
     return b1 < b2 ? b1 : b2;
 }
 
+/* maintenance at the start of iteration it0: ref :545-560 covariance update, :563-585 DE buffer
+ * update + DE joins the cycle.  Idempotent per boundary so that orc_maintain can run it early. */
+static int maintenance(orc_sampler *s, int64_t it0)
+{
+    int64_t b = it0 - 1;
+    if (b % s->c.cov_update == 0 && b != 0 && s->c.temp_offset == 0 && s->adapt_done != b) {
+        update_recursive(s, b, s->c.cov_update);
+        s->adapt_done = b;
+    }
+    if (b % s->c.burn == 0 && b != 0 && s->de_done != b) {
+        int rc = update_de_buffer(s);
+        if (rc) return rc;
+        s->de_done = b;
+        if (!s->de_in_cycle && s->c.de_weight > 0) {
+            s->cyc_jump[s->ncycle] = ORC_JUMP_DE;
+            s->cyc_w[s->ncycle] = s->c.de_weight;
+            s->ncycle++;
+            s->de_in_cycle = 1;
+        }
+    }
+    return 0;
+}
+
+int orc_maintain(orc_sampler *s) { return s->pending_swap ? -4 : maintenance(s, s->iter + 1); }
+
 /* ref :495-528 driver loop and :530-629 PTMCMCOneStep */
 int orc_run(orc_sampler *s, int64_t niter)
 {
@@ -680,23 +719,17 @@ int orc_run(orc_sampler *s, int64_t niter)
     int64_t end = s->iter + niter;
     int nth = s->c.nthreads > 0 ? s->c.nthreads : 1;
     if (s->c.logl_kind == ORC_LOGL_EXTERNAL || s->c.logp_kind == ORC_LOGP_EXTERNAL || s->njumps > 3) nth = 1;
+    if (s->pending_swap) return -4; /* a sharded swap must be completed first */
     while (s->iter < end) {
         int64_t it0 = s->iter + 1;
-        /* ref :545-560 covariance update, :563-585 DE buffer update + DE joins the cycle */
-        if ((it0 - 1) % s->c.cov_update == 0 && (it0 - 1) != 0 && s->c.temp_offset == 0)
-            update_recursive(s, it0 - 1, s->c.cov_update);
-        if ((it0 - 1) % s->c.burn == 0 && (it0 - 1) != 0) {
-            int rc = update_de_buffer(s);
-            if (rc) return rc;
-            if (!s->de_in_cycle && s->c.de_weight > 0) {
-                s->cyc_jump[s->ncycle] = ORC_JUMP_DE;
-                s->cyc_w[s->ncycle] = s->c.de_weight;
-                s->ncycle++;
-                s->de_in_cycle = 1;
-            }
-        }
+        int mrc = maintenance(s, it0);
+        if (mrc) return mrc;
         int64_t seg_end = next_boundary(s, it0);
         if (seg_end > end) seg_end = end;
+        if (s->sharded) { /* stop at the swap iteration: the exchange is driven from outside */
+            int64_t nsw = ((it0 + s->c.tskip - 1) / s->c.tskip) * s->c.tskip;
+            if (nsw < seg_end) seg_end = nsw;
+        }
         int64_t trace_base = s->trace_pos, swap_base = s->swap_pos;
 #pragma omp parallel num_threads(nth)
         {
@@ -710,6 +743,7 @@ int orc_run(orc_sampler *s, int64_t niter)
                 int64_t nsw = 0;
                 for (int64_t it = it0; it <= seg_end; ++it) {
                     for (int t = 0; t < T; ++t) mh_step(s, it, w, t, q, y, trace_base + (it - it0));
+                    if (s->sharded && it % s->c.tskip == 0) continue; /* swap + updateChains: orc_swap_* */
                     if (it % s->c.tskip == 0 && T > 1) { /* ref :624-625 */
                         pt_swap(s, it, w, map, tmpx, tmpl, swap_base + nsw);
                         nsw++;
@@ -720,13 +754,166 @@ int orc_run(orc_sampler *s, int64_t niter)
             free(q); free(y); free(map); free(tmpx); free(tmpl);
         }
         for (int64_t it = it0; it <= seg_end; ++it) {
+            if (s->sharded) continue;
             if (it % s->c.tskip == 0 && T > 1) { s->swap_proposed++; s->swap_pos++; }
             if (it % s->c.thin == 0 && it / s->c.thin + 1 > s->rows) s->rows = it / s->c.thin + 1;
         }
         s->trace_pos += seg_end - it0 + 1;
         s->iter = seg_end;
+        if (s->sharded) {
+            for (int64_t it = it0; it <= seg_end; ++it)
+                if (it % s->c.tskip != 0 && it % s->c.thin == 0 && it / s->c.thin + 1 > s->rows)
+                    s->rows = it / s->c.thin + 1;
+            if (seg_end % s->c.tskip == 0) {
+                s->pending_swap = 1;
+                s->swept = 0;
+                if (seg_end < end) return -4;
+            }
+        }
     }
     if (s->rows > s->c.max_rows) s->rows = s->c.max_rows;
+    return 0;
+}
+
+/* ------------------------------------------------ ladder-sharded swap -- */
+
+int64_t orc_swap_msg_doubles(const orc_sampler *s) { return (int64_t)(s->d + 3) * s->W; }
+int orc_swap_pending(const orc_sampler *s) { return s->pending_swap; }
+double *orc_am_ring(orc_sampler *s) { return s->am; }
+
+static void pack_state(const orc_sampler *s, double *msg, int w, const double *x, double lnl, double lp,
+                       double origin)
+{
+    int d = s->d, W = s->W;
+    for (int k = 0; k < d; ++k) msg[(size_t)k * W + w] = x[k];
+    msg[(size_t)d * W + w] = lnl;
+    msg[(size_t)(d + 1) * W + w] = lp;
+    msg[(size_t)(d + 2) * W + w] = origin;
+}
+
+void orc_swap_pack_top(const orc_sampler *s, double *msg)
+{
+    int d = s->d, W = s->W, T = s->T;
+    for (int w = 0; w < W; ++w) {
+        size_t ch = (size_t)(T - 1) * W + w;
+        pack_state(s, msg, w, s->x + ch * d, s->lnl[ch], s->lp[ch], (double)(s->c.temp_offset + T - 1));
+    }
+}
+
+/* acceptance of the pair (lower rung at Ta with lnL La, upper rung at Tb with lnL Lb), ref :673-679 */
+static int swap_accept(double La, double Lb, double Ta, double Tb, double u)
+{
+    double lar = -La / Ta;
+    lar += -Lb / Tb;
+    lar += Lb / Ta;
+    lar += La / Tb;
+    return u <= exp(lar);
+}
+
+static double swap_uniform(const orc_sampler *s, int64_t iter, int w, int sc_global)
+{
+    /* the sweep draws one uniform per pair, hottest pair first: pair sc uses word Tg-2-sc */
+    return orc_word_to_unit(orc_draw_word(s->c.seed, ORC_PURPOSE_SWAP, (uint64_t)iter,
+                                          (uint32_t)(s->c.walker_offset + w), 0, (uint32_t)(s->Tg - 2 - sc_global)));
+}
+
+int orc_swap_sweep(orc_sampler *s, const double *carry_in, double *carry_out)
+{
+    int d = s->d, W = s->W, T = s->T, off = s->c.temp_offset;
+    if (!s->pending_swap || s->swept) return -4;
+    int hottest = (off + T == s->Tg), coldest = (off == 0);
+    if ((carry_in == NULL) != hottest || (carry_out == NULL) != coldest) return -1;
+    int64_t iter = s->iter;
+    for (int w = 0; w < W; ++w) {
+        int carry = T - 1;
+        double Lcarry = s->lnl[(size_t)(T - 1) * W + w];
+        if (carry_in) { /* boundary pair: our top rung against the carry of the hotter shard */
+            double La = Lcarry, Lb = carry_in[(size_t)d * W + w];
+            if (swap_accept(La, Lb, s->ladder[T - 1], s->c.ladder_above, swap_uniform(s, iter, w, off + T - 1))) {
+                s->swap_acc[(size_t)(T - 1) * W + w] += 1;
+                carry = T; /* the foreign state keeps travelling down */
+                Lcarry = Lb;
+            }
+        }
+        for (int sc = T - 2; sc >= 0; --sc) {
+            double La = s->lnl[(size_t)sc * W + w];
+            if (swap_accept(La, Lcarry, s->ladder[sc], s->ladder[sc + 1], swap_uniform(s, iter, w, off + sc))) {
+                s->smap[(size_t)(sc + 1) * W + w] = sc;
+                s->swap_acc[(size_t)sc * W + w] += 1;
+            } else {
+                s->smap[(size_t)(sc + 1) * W + w] = carry;
+                carry = sc;
+                Lcarry = La;
+            }
+        }
+        s->carry_code[w] = carry;
+        s->carry_L[w] = Lcarry;
+        if (carry_out) {
+            if (carry == T)
+                for (int k = 0; k < d + 3; ++k) carry_out[(size_t)k * W + w] = carry_in[(size_t)k * W + w];
+            else {
+                size_t ch = (size_t)carry * W + w;
+                pack_state(s, carry_out, w, s->x + ch * d, s->lnl[ch], s->lp[ch], (double)(off + carry));
+            }
+        }
+    }
+    s->carry_in = carry_in;
+    s->swept = 1;
+    return 0;
+}
+
+int orc_swap_finish(orc_sampler *s, const double *below_top)
+{
+    int d = s->d, W = s->W, T = s->T, off = s->c.temp_offset;
+    if (!s->pending_swap || !s->swept) return -4;
+    if ((below_top == NULL) != (off == 0)) return -1;
+    int64_t iter = s->iter;
+    const double *cin = s->carry_in;
+    double *nx = (double *)malloc(sizeof(double) * (size_t)T * d);
+    double *nl = (double *)malloc(sizeof(double) * 2 * T);
+    for (int w = 0; w < W; ++w) {
+        /* position 0: boundary pair with the colder shard's top rung, decided identically there */
+        int code0 = s->carry_code[w];
+        if (below_top) {
+            double La = below_top[(size_t)d * W + w], Lb = s->carry_L[w];
+            if (swap_accept(La, Lb, s->c.ladder_below, s->ladder[0], swap_uniform(s, iter, w, off - 1))) code0 = T + 1;
+        }
+        s->smap[w] = code0;
+        for (int t = 0; t < T; ++t) {
+            int code = s->smap[(size_t)t * W + w];
+            const double *msg = (code == T) ? cin : (code == T + 1) ? below_top : NULL;
+            int origin;
+            if (msg) {
+                for (int k = 0; k < d; ++k) nx[(size_t)t * d + k] = msg[(size_t)k * W + w];
+                nl[t] = msg[(size_t)d * W + w];
+                nl[T + t] = msg[(size_t)(d + 1) * W + w];
+                origin = (int)msg[(size_t)(d + 2) * W + w];
+            } else {
+                size_t ch = (size_t)code * W + w;
+                memcpy(nx + (size_t)t * d, s->x + ch * d, sizeof(double) * d);
+                nl[t] = s->lnl[ch];
+                nl[T + t] = s->lp[ch];
+                origin = off + code;
+            }
+            if (s->swapmaps && s->swap_pos < s->swap_events)
+                s->swapmaps[((size_t)s->swap_pos * W + w) * T + t] = (int16_t)origin;
+        }
+        for (int t = 0; t < T; ++t) {
+            size_t ch = (size_t)t * W + w;
+            memcpy(s->x + ch * d, nx + (size_t)t * d, sizeof(double) * d);
+            s->lnl[ch] = nl[t];
+            s->lp[ch] = nl[T + t];
+        }
+        update_chains(s, iter, w); /* ref :627 */
+    }
+    free(nx); free(nl);
+    if (iter % s->c.thin == 0 && iter / s->c.thin + 1 > s->rows) s->rows = iter / s->c.thin + 1;
+    if (s->rows > s->c.max_rows) s->rows = s->c.max_rows;
+    s->swap_proposed++;
+    s->swap_pos++;
+    s->pending_swap = 0;
+    s->swept = 0;
+    s->carry_in = NULL;
     return 0;
 }
 

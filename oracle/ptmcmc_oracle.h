@@ -59,6 +59,11 @@ typedef struct orc_config {
     int64_t max_rows;         /* record capacity (rows incl. row 0)            */
     int32_t nthreads;         /* OpenMP threads over walkers (1 = scalar port) */
     orc_logfn ext_logl; orc_logfn ext_logp; orc_jumpfn ext_jump; void *user;
+    /* ladder sharding (one shard = ntemps contiguous rungs starting at temp_offset of a ladder of
+     * ntemps_global rungs; 0 or ntemps = not sharded).  ladder_above / ladder_below are the
+     * temperatures of the neighbouring shards' adjacent rungs. */
+    int32_t ntemps_global;
+    double ladder_above, ladder_below;
 } orc_config;
 
 typedef struct orc_sampler orc_sampler;
@@ -89,6 +94,21 @@ int32_t orc_njumps(const orc_sampler *s);
  * swap maps int16 [event][W][T] */
 void orc_set_trace(orc_sampler *s, uint8_t *trace, int64_t trace_iters, int16_t *swapmaps,
                    int64_t swap_events);
+
+/* --- ladder sharding: the swap sweep (ref :631-697) cut at shard boundaries.  A message is
+ *     (ndim+3)*nwalkers doubles: x[ndim][W], lnl[W], lnprior[W], origin rung[W].
+ *     Per swap iteration (orc_run stops there): pack_top -> hotter neighbour; sweep(carry from the
+ *     hotter neighbour or NULL, carry for the colder neighbour or NULL); finish(top rung of the colder
+ *     neighbour or NULL) applies the permutation and the iteration's updateChains. --- */
+int64_t orc_swap_msg_doubles(const orc_sampler *s);
+int orc_swap_pending(const orc_sampler *s);
+void orc_swap_pack_top(const orc_sampler *s, double *msg);
+int orc_swap_sweep(orc_sampler *s, const double *carry_in, double *carry_out);
+int orc_swap_finish(orc_sampler *s, const double *below_top);
+/* AM ring [cov_update][W][d] in place (ladder sharding: broadcast from the cold shard) */
+double *orc_am_ring(orc_sampler *s);
+/* run the covariance / DE maintenance due at the start of the next iteration now (idempotent) */
+int orc_maintain(orc_sampler *s);
 
 /* --- RNG primitives, exported so that the golden harness can feed the very
  *     same draws to the unmodified reference --- */

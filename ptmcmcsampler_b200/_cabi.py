@@ -10,7 +10,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libptmcmc_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_CYCLE = 16
 
 JUMP_SCAM, JUMP_AM, JUMP_DE, JUMP_EXT0 = 0, 1, 2, 3
@@ -27,7 +27,7 @@ _i64p = C.POINTER(C.c_int64)
 class Config(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("device", C.c_int32), ("ndim", C.c_int32), ("nwalkers", C.c_int32),
-        ("ntemps", C.c_int32), ("walker_offset", C.c_int32), ("temp_offset", C.c_int32), ("reserved0", C.c_int32),
+        ("ntemps", C.c_int32), ("walker_offset", C.c_int32), ("temp_offset", C.c_int32), ("ntemps_global", C.c_int32),
         ("seed", C.c_uint64),
         ("ladder", _dp), ("mh_temp", _dp), ("cov", _dp),
         ("ngroups", C.c_int32), ("reserved1", C.c_int32),
@@ -40,6 +40,7 @@ class Config(C.Structure):
         ("record_hot", C.c_int32), ("trace", C.c_int32),
         ("record_rows", C.c_int64), ("trace_iters", C.c_int64),
         ("timing", C.c_int32), ("reserved2", C.c_int32),
+        ("ladder_above", C.c_double), ("ladder_below", C.c_double),
     ]
 
 
@@ -54,7 +55,8 @@ SYMBOLS = [
     "ptmcmc_get_chain", "ptmcmc_release_rows", "ptmcmc_get_adapt", "ptmcmc_get_factor", "ptmcmc_set_factor",
     "ptmcmc_get_buffers", "ptmcmc_adapt_begin", "ptmcmc_adapt_finish", "ptmcmc_njumps", "ptmcmc_get_counters",
     "ptmcmc_get_trace", "ptmcmc_get_timing", "ptmcmc_reset_timing", "ptmcmc_stream", "ptmcmc_set_timing",
-    "ptmcmc_host_alloc", "ptmcmc_host_free",
+    "ptmcmc_host_alloc", "ptmcmc_host_free", "ptmcmc_swap_msg_doubles", "ptmcmc_swap_pending",
+    "ptmcmc_swap_pack_top", "ptmcmc_swap_sweep", "ptmcmc_swap_finish", "ptmcmc_am_ring", "ptmcmc_maintain",
 ]
 
 _lib = None
@@ -113,6 +115,14 @@ def load():
     L.ptmcmc_host_alloc.argtypes = [C.c_int64]
     L.ptmcmc_host_free.restype = None
     L.ptmcmc_host_free.argtypes = [C.c_void_p]
+    L.ptmcmc_swap_msg_doubles.restype = C.c_int64
+    L.ptmcmc_swap_msg_doubles.argtypes = [h]
+    L.ptmcmc_swap_pending.argtypes = [h]
+    L.ptmcmc_swap_pack_top.argtypes = [h, C.c_void_p]
+    L.ptmcmc_swap_sweep.argtypes = [h, C.c_void_p, C.c_void_p]
+    L.ptmcmc_swap_finish.argtypes = [h, C.c_void_p]
+    L.ptmcmc_am_ring.argtypes = [h, C.POINTER(C.c_void_p), _i64p]
+    L.ptmcmc_maintain.argtypes = [h]
     for name in SYMBOLS:
         getattr(L, name)
     if L.ptmcmc_abi_version() != ABI_VERSION:
@@ -173,7 +183,7 @@ class Engine(object):
                  cycle=((JUMP_SCAM, 20), (JUMP_AM, 20)), de_weight=20, cov_update=1000, burn=10000, tskip=100,
                  thin=10, logl_kind=LOGL_GAUSSIAN, logl_params=None, logp_kind=LOGP_UNIFORM, logp_params=None,
                  record_hot=False, record_rows=1024, trace_iters=0, timing=False, device=0, walker_offset=0,
-                 temp_offset=0):
+                 temp_offset=0, ntemps_global=0, ladder_above=0.0, ladder_below=0.0):
         L = load()
         self._L = L
         self.d, self.W, self.T = int(ndim), int(nwalkers), int(ntemps)
@@ -221,6 +231,9 @@ class Engine(object):
         cfg.record_hot, cfg.record_rows = int(bool(record_hot)), int(record_rows)
         cfg.trace, cfg.trace_iters = int(trace_iters > 0), int(trace_iters)
         cfg.timing = int(bool(timing))
+        cfg.ntemps_global, cfg.ladder_above, cfg.ladder_below = int(ntemps_global), float(ladder_above), float(ladder_below)
+        self.temp_offset, self.ntemps_global = int(temp_offset), int(ntemps_global) or self.T
+        self.device = int(device)
         self.ntr = self.T if record_hot else 1
         self.usize = sum(len(g) ** 2 for g in self.groups)
         self.ssize = sum(len(g) for g in self.groups)
@@ -358,6 +371,34 @@ class Engine(object):
         self._check(self._L.ptmcmc_get_trace(self._h, tr.ctypes.data_as(C.POINTER(C.c_uint8)), iters,
                                              sm.ctypes.data_as(C.POINTER(C.c_int16)), events))
         return tr, sm
+
+    # ---- ladder sharding: pointers are DEVICE addresses (e.g. torch tensor .data_ptr()) -------------
+    @property
+    def swap_msg_doubles(self):
+        return int(self._L.ptmcmc_swap_msg_doubles(self._h))
+
+    @property
+    def swap_pending(self):
+        return bool(self._L.ptmcmc_swap_pending(self._h))
+
+    def swap_pack_top(self, msg_ptr):
+        self._check(self._L.ptmcmc_swap_pack_top(self._h, msg_ptr))
+
+    def swap_sweep(self, carry_in_ptr, carry_out_ptr):
+        self._check(self._L.ptmcmc_swap_sweep(self._h, carry_in_ptr or None, carry_out_ptr or None))
+
+    def swap_finish(self, below_ptr):
+        self._check(self._L.ptmcmc_swap_finish(self._h, below_ptr or None))
+
+    def am_ring(self):
+        """(device address, number of doubles) of the AM ring."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        self._check(self._L.ptmcmc_am_ring(self._h, C.byref(ptr), C.byref(n)))
+        return int(ptr.value), int(n.value)
+
+    def maintain(self):
+        """Run the covariance / DE maintenance due at the start of the next iteration now."""
+        self._check(self._L.ptmcmc_maintain(self._h))
 
     def timing(self):
         t = Timing()

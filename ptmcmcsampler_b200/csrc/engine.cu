@@ -59,6 +59,13 @@ struct Engine {
     std::vector<int> cyc_jump, cyc_w;
     long long iter = 0, rows = 0, rec_base = 0, de_head = 0, swap_proposed = 0, swap_events = 0;
     long long adapt_done_iter = -1;  // boundary iteration whose covariance update already ran
+    long long de_done_iter = -1;     // boundary iteration whose DE-history update already ran
+    // ladder sharding
+    int Tg = 0;
+    bool sharded = false, pending_swap = false, swept = false;
+    int *d_carry_code = nullptr;
+    double *d_carry_L = nullptr;
+    const double *carry_in = nullptr;
     long long nsamp = 0;
     bool pending_propose = false;
     std::string err;
@@ -326,9 +333,10 @@ int maintenance(Engine *e, long long it0)
         cudaError_t st = cov_update(e, b);
         if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "covariance update: %s", cudaGetErrorString(st));
     }
-    if (b != 0 && b % e->cfg.burn == 0) {
+    if (b != 0 && b % e->cfg.burn == 0 && e->de_done_iter != b) {
         int rc = de_update(e);
         if (rc) return rc;
+        e->de_done_iter = b;
     }
     return 0;
 }
@@ -422,6 +430,12 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     }
     if (e->cyc_jump.empty()) return fail(nullptr, PTMCMC_ERR_ARG, "No jump proposals specified!");
     e->ntr = cfg->record_hot ? T : 1;
+    e->Tg = cfg->ntemps_global > 0 ? cfg->ntemps_global : T;
+    if (cfg->temp_offset < 0 || cfg->temp_offset + T > e->Tg)
+        return fail(nullptr, PTMCMC_ERR_ARG, "rungs [%d, %d) do not fit a ladder of %d", cfg->temp_offset,
+                    cfg->temp_offset + T, e->Tg);
+    e->sharded = e->Tg > T;
+    if (e->Tg > 32767) return fail(nullptr, PTMCMC_ERR_ARG, "ntemps_global must be < 32768");
     if (const char *v = getenv("PTMCMC_MH_VARIANT")) e->mh_variant = atoi(v);
     const size_t C = (size_t)T * W;
     for (int b = 0; b < 2; ++b) {
@@ -494,6 +508,10 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     CUDA_TRY(nullptr, dalloc(&e->d_acc, C * e->njumps));
     CUDA_TRY(nullptr, dalloc(&e->d_swap_acc, C));
     CUDA_TRY(nullptr, dalloc(&e->d_map, C));
+    if (e->sharded) {
+        CUDA_TRY(nullptr, dalloc(&e->d_carry_code, W));
+        CUDA_TRY(nullptr, dalloc(&e->d_carry_L, W));
+    }
     if (cfg->trace) {
         CUDA_TRY(nullptr, dalloc(&e->d_trace, (size_t)cfg->trace_iters * C));
         CUDA_TRY(nullptr, dalloc(&e->d_swapmaps, (size_t)cfg->trace_iters * C));
@@ -540,7 +558,8 @@ void ptmcmc_destroy(ptmcmc_engine *h)
                     e->d_soff, e->d_ord, e->d_work_a, e->d_work_v, e->d_am, e->d_de, e->d_gmu, e->d_gP,
                     e->d_plo, e->d_phi, e->d_rec_x, e->d_rec_lnl, e->d_rec_lnp, e->d_prop, e->d_acc,
                     e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_part, e->d_part2, e->d_batch,
-                    e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos, e->d_stage};
+                    e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos, e->d_stage,
+                    e->d_carry_code, e->d_carry_L};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -569,6 +588,7 @@ static int finish_set_state(Engine *e)
     e->rows = 1;
     e->rec_base = 0;
     e->has_state = true;
+    e->pending_swap = e->swept = false;
     DevParams p = make_params(e);
     {
         LaunchTimer lt(e, PTMCMC_K_INIT);
@@ -616,10 +636,15 @@ int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
     if (e->cfg.logl_kind == PTMCMC_LOGL_EXTERNAL || e->cfg.logp_kind == PTMCMC_LOGP_EXTERNAL || e->njumps > 3)
         return fail(e, PTMCMC_ERR_STATE, "external targets or jumps: drive with ptmcmc_propose / ptmcmc_accept");
     if (niter < 0) return fail(e, PTMCMC_ERR_ARG, "niter < 0");
+    if (e->pending_swap) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_run with a sharded swap pending (ptmcmc_swap_*)");
     const long long end = e->iter + niter;
+    const long long cu = e->cfg.cov_update, burn = e->cfg.burn, tskip = e->cfg.tskip;
+    if (e->sharded && niter > 0 && end > next_multiple(e->iter + 1, tskip))
+        return fail(e, PTMCMC_ERR_STATE,
+                    "ladder-sharded engine: ptmcmc_run must stop at the swap iteration %lld (asked to reach %lld)",
+                    next_multiple(e->iter + 1, tskip), end);
     int rc = check_rows(e, end);
     if (rc) return rc;
-    const long long cu = e->cfg.cov_update, burn = e->cfg.burn, tskip = e->cfg.tskip;
     while (e->iter < end) {
         const long long it0 = e->iter + 1;
         rc = maintenance(e, it0);
@@ -627,18 +652,22 @@ int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
         long long seg_end = end;
         seg_end = std::min(seg_end, next_multiple(it0, cu));
         seg_end = std::min(seg_end, next_multiple(it0, burn));
-        const bool swaps = e->T > 1;
+        const bool swaps = e->Tg > 1;
         if (swaps) seg_end = std::min(seg_end, next_multiple(it0, tskip));
         const bool swap_now = swaps && (seg_end % tskip == 0);
         cudaError_t st = launch_mh(e, it0, seg_end, !swap_now);
         if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "MH kernel: %s", cudaGetErrorString(st));
-        if (swap_now) {
+        if (swap_now && e->sharded) {
+            e->pending_swap = true;  // the neighbour exchange is driven by the caller
+            e->swept = false;
+        } else if (swap_now) {
             st = launch_swap(e, seg_end);
             if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "swap kernels: %s", cudaGetErrorString(st));
         }
         e->iter = seg_end;
     }
-    e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
+    // a pending sharded swap writes the record of its iteration in ptmcmc_swap_finish
+    e->rows = std::max(e->rows, (long long)((e->iter - (e->pending_swap ? 1 : 0)) / e->cfg.thin + 1));
     return 0;
 }
 
@@ -647,6 +676,7 @@ int32_t ptmcmc_propose(ptmcmc_engine *h, double *q, int32_t *jump)
     Engine *e = (Engine *)h;
     if (!e || !q || !jump) return PTMCMC_ERR_ARG;
     if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose before set_state");
+    if (e->sharded) return fail(e, PTMCMC_ERR_STATE, "host callbacks are not available on a ladder-sharded engine");
     if (e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose called twice");
     if (!e->d_q) {  // staging for the host round trip, allocated on first use
         const size_t C0 = (size_t)e->T * e->W;
@@ -900,6 +930,97 @@ int32_t ptmcmc_adapt_finish(ptmcmc_engine *h, const double *batch_in)
     e->nsamp = (long long)(n_prev + batch_in[0]);
     e->adapt_done_iter = b;
     return 0;
+}
+
+int64_t ptmcmc_swap_msg_doubles(const ptmcmc_engine *h)
+{
+    const Engine *e = (const Engine *)h;
+    return e ? (int64_t)(e->d + 3) * e->W : -1;
+}
+
+int32_t ptmcmc_swap_pending(const ptmcmc_engine *h) { return h && ((const Engine *)h)->pending_swap ? 1 : 0; }
+
+int32_t ptmcmc_swap_pack_top(ptmcmc_engine *h, double *dev_msg)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !dev_msg) return PTMCMC_ERR_ARG;
+    if (!e->sharded || !e->pending_swap) return fail(e, PTMCMC_ERR_STATE, "no sharded swap is pending");
+    DevParams p = make_params(e);
+    {
+        LaunchTimer lt(e, PTMCMC_K_SWAP);
+        const long long n = (long long)(e->d + 3) * e->W;
+        swap_pack_top_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 2048), 256, 0, e->stream>>>(p, dev_msg);
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    return 0;
+}
+
+int32_t ptmcmc_swap_sweep(ptmcmc_engine *h, const double *dev_carry_in, double *dev_carry_out)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    if (!e->sharded || !e->pending_swap || e->swept) return fail(e, PTMCMC_ERR_STATE, "no sharded swap sweep is due");
+    const bool hottest = e->cfg.temp_offset + e->T == e->Tg, coldest = e->cfg.temp_offset == 0;
+    if ((dev_carry_in == nullptr) != hottest || (dev_carry_out == nullptr) != coldest)
+        return fail(e, PTMCMC_ERR_ARG, "carry_in is NULL exactly on the hottest shard, carry_out exactly on the coldest");
+    DevParams p = make_params(e);
+    {
+        LaunchTimer lt(e, PTMCMC_K_SWAP);
+        swap_sweep_kernel<<<(e->W + 127) / 128, 128, 0, e->stream>>>(p, e->iter, e->Tg, e->cfg.ladder_above, dev_carry_in,
+                                                                      dev_carry_out, e->d_map, e->d_carry_code,
+                                                                      e->d_carry_L);
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    e->carry_in = dev_carry_in;
+    e->swept = true;
+    return 0;
+}
+
+int32_t ptmcmc_swap_finish(ptmcmc_engine *h, const double *dev_below_top)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    if (!e->sharded || !e->pending_swap || !e->swept) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_swap_finish before ptmcmc_swap_sweep");
+    if ((dev_below_top == nullptr) != (e->cfg.temp_offset == 0))
+        return fail(e, PTMCMC_ERR_ARG, "below_top is NULL exactly on the coldest shard");
+    DevParams p = make_params(e);
+    short *tr = nullptr;
+    if (e->d_swapmaps && e->swap_events < e->cfg.trace_iters) tr = e->d_swapmaps + (size_t)e->swap_events * e->W * e->T;
+    const int nxt = e->cur ^ 1;
+    {
+        LaunchTimer lt(e, PTMCMC_K_SWAP);
+        swap_finish_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, e->iter, e->Tg, e->cfg.ladder_below, e->d_map,
+                                                                          e->d_carry_code, e->d_carry_L, e->carry_in,
+                                                                          dev_below_top, e->x[nxt], e->lnl[nxt], e->lp[nxt],
+                                                                          tr);
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    e->cur = nxt;
+    e->swap_proposed++;
+    e->swap_events++;
+    e->pending_swap = false;
+    e->swept = false;
+    e->carry_in = nullptr;
+    e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
+    return 0;
+}
+
+int32_t ptmcmc_am_ring(ptmcmc_engine *h, void **dev_ptr, int64_t *ndoubles)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !dev_ptr || !ndoubles) return PTMCMC_ERR_ARG;
+    *dev_ptr = e->d_am;
+    *ndoubles = (int64_t)e->cfg.cov_update * e->d * e->W;
+    return 0;
+}
+
+int32_t ptmcmc_maintain(ptmcmc_engine *h)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return PTMCMC_ERR_ARG;
+    if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_maintain before ptmcmc_set_state");
+    if (e->pending_swap || e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_maintain inside an iteration");
+    return maintenance(e, e->iter + 1);
 }
 
 int32_t ptmcmc_njumps(const ptmcmc_engine *h) { return h ? ((const Engine *)h)->njumps : -1; }

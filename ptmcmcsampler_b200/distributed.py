@@ -1,12 +1,28 @@
-"""Walker sharding across GPUs (one process per GPU, ``torch.distributed``).
+"""Sharding across GPUs (one process per GPU, ``torch.distributed``).
 
-Every rank owns ``nwalkers`` complete ladders (``walker_offset = rank * nwalkers`` keys the RNG, so a
+**Walker sharding** (``run``, ``pooled_adapt``).  Every rank owns ``nwalkers`` complete ladders (``walker_offset = rank * nwalkers`` keys the RNG, so a
 walker's draws do not depend on the sharding).  The MH step and the swap need no communication.  The
 only coupling is the pooled proposal covariance: at every covariance boundary the ranks exchange
 their batch moments {n, mean[d], M2c[d*d]} (d*d+d+1 doubles), merge them with Chan's formula in rank
 order, and each applies the merged batch -- the multi-device form of the reference's rank-0
 ``send(cov)`` broadcast (ref PTMCMCSampler.py:545-560).  The DE history stays shard-local.
+
+**Ladder sharding** (``run_ladder``, ``LadderComm``; BASELINE config 5: 256 rungs as 32 per GPU).  Rank g
+owns the contiguous rungs ``[g*T/G, (g+1)*T/G)`` of every walker.  MH steps need no communication.  The
+swap sweep of the reference runs hottest pair first on rank 0 after a gather of every rung (ref
+:660-697); here it is cut at the shard boundaries and only the boundary rung moves, between nearest
+neighbours: each shard sends its top rung up (no dependency), sweeps its own pairs once the carry of
+the hotter shard has arrived, passes its own carry down, and resolves its lowest position against the
+colder shard's top rung.  Both sides of a boundary evaluate the same acceptance from the counter-based
+stream, so the result is bit-identical to the unsharded sweep.  The adaptive state lives on the shard
+holding T=1: its eigen-factor (d*d+d doubles) is broadcast at every covariance update and its AM ring
+before every DE-history update, the multi-device form of the reference's rank-0 ``send(cov)`` /
+``send(_DEbuffer)`` (ref :545-571).
+
+The drivers are written against the small engine surface both ``_cabi.Engine`` (device pointers, NCCL)
+and the test oracle (host pointers, gloo) expose, so the exchange logic is testable without a GPU.
 """
+import ctypes
 import numpy as np
 
 
@@ -57,4 +73,229 @@ def run(engine, niter, group=None):
         step = min(niter - done, cu - it % cu)
         engine.run(step)
         done += step
+    return done
+
+
+# ------------------------------------------------------------------ ladder sharding ------------
+class _CudaAlias(object):
+    """Exposes a raw device allocation through ``__cuda_array_interface__`` (zero-copy torch view)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def ladder_slice(ntemps_global, world, rank):
+    """Contiguous rungs ``[lo, hi)`` of shard ``rank``; the ladder must divide evenly."""
+    if ntemps_global % world != 0:
+        raise ValueError("%d temperatures do not divide over %d shards" % (ntemps_global, world))
+    n = ntemps_global // world
+    return rank * n, (rank + 1) * n
+
+
+def ladder_shard_kwargs(ladder, world, rank):
+    """Engine keyword arguments (ntemps, ladder, temp_offset, ...) of shard ``rank``."""
+    ladder = np.asarray(ladder, dtype=np.float64)
+    lo, hi = ladder_slice(len(ladder), world, rank)
+    return dict(ntemps=hi - lo, ladder=ladder[lo:hi].copy(), temp_offset=lo, ntemps_global=len(ladder),
+                ladder_above=float(ladder[hi]) if hi < len(ladder) else 0.0,
+                ladder_below=float(ladder[lo - 1]) if lo > 0 else 0.0)
+
+
+class LadderComm(object):
+    """Neighbour exchange and cold-shard broadcasts of one ladder shard over ``torch.distributed``.
+
+    ``device`` is the torch device of the message buffers: a CUDA device for ``_cabi.Engine`` (NCCL) or
+    ``"cpu"`` for a host engine (gloo).  With CUDA, ``stream`` (the engine's stream) is made current so
+    that collectives and engine kernels are ordered on the device without host synchronisation."""
+
+    def __init__(self, engine, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.coldest, self.hottest = self.rank == 0, self.rank == self.world - 1
+        if device is None:
+            device = torch.device("cuda", engine.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        self.device = torch.device(device)
+        self.stream = None
+        if self.device.type == "cuda":
+            self.stream = torch.cuda.ExternalStream(engine.stream, device=self.device)
+        n = engine.swap_msg_doubles
+        with self._on_stream():
+            self.up_out, self.below_in, self.carry_in, self.carry_out = (
+                torch.zeros(n, dtype=torch.float64, device=self.device) for _ in range(4))
+        self.maint_done = -1
+
+    def _on_stream(self):
+        import contextlib
+
+        return self.torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
+    def _peer(self, r):
+        return self.dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def alias(self, ptr, n):
+        """torch view of ``n`` doubles at address ``ptr`` in the engine's memory space."""
+        if self.device.type == "cuda":
+            return self.torch.as_tensor(_CudaAlias(ptr, n), device=self.device)
+        buf = (ctypes.c_double * n).from_address(ptr)
+        return self.torch.from_numpy(np.ctypeslib.as_array(buf))
+
+    def exchange_top(self):
+        """Start: my top rung -> hotter neighbour, colder neighbour's top rung -> me."""
+        ops = []
+        if not self.hottest:
+            ops.append(self.dist.P2POp(self.dist.isend, self.up_out, self._peer(self.rank + 1), self.group))
+        if not self.coldest:
+            ops.append(self.dist.P2POp(self.dist.irecv, self.below_in, self._peer(self.rank - 1), self.group))
+        return self.dist.batch_isend_irecv(ops) if ops else []
+
+    def recv_carry(self):
+        self.dist.recv(self.carry_in, self._peer(self.rank + 1), group=self.group)
+
+    def send_carry(self):
+        self.dist.send(self.carry_out, self._peer(self.rank - 1), group=self.group)
+
+    def bcast(self, tensor):
+        self.dist.broadcast(tensor, self._peer(0), group=self.group)
+
+
+def ladder_swap(engine, comm):
+    """One sharded swap sweep (the engine stopped at a swap iteration)."""
+    with comm._on_stream():
+        if not comm.hottest:
+            engine.swap_pack_top(comm.up_out.data_ptr())
+        reqs = comm.exchange_top()
+        if not comm.hottest:
+            comm.recv_carry()
+        engine.swap_sweep(None if comm.hottest else comm.carry_in.data_ptr(),
+                          None if comm.coldest else comm.carry_out.data_ptr())
+        if not comm.coldest:
+            comm.send_carry()
+        for r in reqs:
+            r.wait()
+        engine.swap_finish(None if comm.coldest else comm.below_in.data_ptr())
+
+
+def ladder_maintenance(engine, comm):
+    """Covariance / DE maintenance due at the start of the next iteration, with the cold shard's
+    AM ring broadcast before a DE update and its eigen-factor after a covariance update."""
+    it = engine.iteration
+    if it == 0 or comm.maint_done == it:
+        return
+    due_cov, due_de = it % engine.cov_update == 0, it % engine.burn == 0
+    if not (due_cov or due_de):
+        return
+    torch = comm.torch
+    with comm._on_stream():
+        if due_de and comm.world > 1:
+            ptr, n = engine.am_ring()
+            comm.bcast(comm.alias(ptr, n))
+        engine.maintain()
+        if due_cov and comm.world > 1:
+            if comm.coldest:
+                U, S = engine.factor()
+                t = torch.from_numpy(np.concatenate([U, S])).to(comm.device)
+            else:
+                t = torch.empty(engine.usize + engine.ssize, dtype=torch.float64, device=comm.device)
+            comm.bcast(t)
+            if not comm.coldest:
+                f = t.cpu().numpy()
+                engine.set_factor(f[:engine.usize], f[engine.usize:])
+    comm.maint_done = it
+
+
+def run_ladder(engine, niter, comm, tskip):
+    """``niter`` iterations of one ladder shard; collective over the shards of ``comm``."""
+    done = 0
+    while done < niter:
+        it = engine.iteration
+        ladder_maintenance(engine, comm)
+        step = min(niter - done, tskip - it % tskip)
+        engine.run(step)
+        done += step
+        if engine.swap_pending:
+            ladder_swap(engine, comm)
+    return done
+
+
+class HostMem(object):
+    """Message memory for host engines (ctypes)."""
+
+    def alloc(self, n):
+        buf = (ctypes.c_double * n)()
+        return ctypes.addressof(buf), buf
+
+    def copy(self, dst, src, n):
+        ctypes.memmove(dst, src, 8 * n)
+
+    def sync(self, engine):
+        pass
+
+
+class CudaMem(object):
+    """Message memory for ``_cabi.Engine`` shards living on one CUDA device (torch allocations)."""
+
+    def __init__(self, device=0):
+        import torch
+
+        self.torch, self.device = torch, torch.device("cuda", device)
+
+    def alloc(self, n):
+        t = self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
+        self.torch.cuda.synchronize(self.device)
+        return t.data_ptr(), t
+
+    def copy(self, dst, src, n):
+        a = self.torch.as_tensor(_CudaAlias(dst, n), device=self.device)
+        a.copy_(self.torch.as_tensor(_CudaAlias(src, n), device=self.device))
+        self.torch.cuda.synchronize(self.device)
+
+    def sync(self, engine):
+        engine.sync()
+
+
+def run_ladder_local(engines, niter, tskip, mem):
+    """All shards of a ladder driven by ONE process (several shards on one device; also the reference
+    implementation of the protocol for the tests): the same steps as ``run_ladder`` with the messages
+    handed over directly.  ``mem`` is a ``HostMem`` / ``CudaMem``."""
+    G = len(engines)
+    n = engines[0].swap_msg_doubles
+    up = [mem.alloc(n) for _ in range(G)]
+    carry = [mem.alloc(n) for _ in range(G)]
+    done = 0
+    while done < niter:
+        it = engines[0].iteration
+        due_cov = it > 0 and it % engines[0].cov_update == 0
+        due_de = it > 0 and it % engines[0].burn == 0
+        if due_de and G > 1:
+            ptr0, na = engines[0].am_ring()
+            mem.sync(engines[0])
+            for e in engines[1:]:
+                mem.sync(e)
+                mem.copy(e.am_ring()[0], ptr0, na)
+        if due_cov or due_de:
+            for e in engines:
+                e.maintain()
+        if due_cov and G > 1:
+            U, S = engines[0].factor()
+            for e in engines[1:]:
+                e.set_factor(U, S)
+        step = min(niter - done, tskip - it % tskip)
+        for e in engines:
+            e.run(step)
+        done += step
+        if engines[0].swap_pending:
+            for g in range(G - 1):
+                engines[g].swap_pack_top(up[g][0])
+                mem.sync(engines[g])
+            for g in reversed(range(G)):
+                engines[g].swap_sweep(carry[g + 1][0] if g < G - 1 else None, carry[g][0] if g > 0 else None)
+                mem.sync(engines[g])
+            for g in range(G):
+                engines[g].swap_finish(up[g - 1][0] if g > 0 else None)
+            for e in engines:
+                mem.sync(e)
     return done
