@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libptmcmc_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["params.h", "rng.cuh", "mh_kernels.cuh", "swap_kernels.cuh", "adapt_kernels.cuh",
-           os.path.join("..", "..", "include", "ptmcmc_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [
+    os.path.join("..", "..", "include", "ptmcmc_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -98,6 +99,7 @@ struct Engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
     int mh_variant = 0;  // 0: sorted shared-memory kernel, 1: thread-per-chain register kernel, 2: generic
+    int sort_nc = 256;   // chains (= threads) per block of the sorted kernel
 };
 
 int fail(Engine *e, int code, const char *fmt, ...)
@@ -209,8 +211,9 @@ cudaError_t launch_sorted(const Engine *e, const DevParams &p)
         if (st != cudaSuccess) return st;
         attr_done = true;
     }
-    const int blocks = (int)(((long long)e->T * e->W + SORT_NC - 1) / SORT_NC);
-    mh_sorted_kernel<DP, SORT_NC, SORT_MINB><<<blocks, SORT_NC, smem, e->stream>>>(p);
+    const int nc = e->sort_nc;
+    const int blocks = (int)(((long long)e->T * e->W + nc - 1) / nc);
+    mh_sorted_kernel<DP, SORT_NC, SORT_MINB><<<blocks, nc, smem, e->stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -437,6 +440,10 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     e->sharded = e->Tg > T;
     if (e->Tg > 32767) return fail(nullptr, PTMCMC_ERR_ARG, "ntemps_global must be < 32768");
     if (const char *v = getenv("PTMCMC_MH_VARIANT")) e->mh_variant = atoi(v);
+    if (const char *v = getenv("PTMCMC_SORT_NC")) {
+        const int nc = atoi(v);
+        if (nc >= 32 && nc <= 256 && nc % 32 == 0) e->sort_nc = nc;
+    }
     const size_t C = (size_t)T * W;
     for (int b = 0; b < 2; ++b) {
         CUDA_TRY(nullptr, dalloc(&e->x[b], C * d));

@@ -57,13 +57,14 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const DevParams p)
     SortedSmem<DP, NC> &S = *reinterpret_cast<SortedSmem<DP, NC> *>(smem_raw);
     const int d = p.d, W = p.W, T = p.T;
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int idx = tid; idx < DP * DP; idx += NC) {
+    const int nc = blockDim.x;  // chains of this block (<= NC, the capacity the arrays are laid out for)
+    for (int idx = tid; idx < DP * DP; idx += nc) {
         const int i = idx / DP, j = idx % DP;
         const bool in = (i < d && j < d);
         S.Us[idx] = in ? p.U[i * d + j] : 0.0;
         S.Ps[idx] = (in && p.logl_kind == LOGL_GAUSSIAN) ? p.g_P[i * d + j] : 0.0;
     }
-    for (int k = tid; k < DP; k += NC) {
+    for (int k = tid; k < DP; k += nc) {
         const bool in = k < d;
         S.sS[k] = in ? p.sqrtS[k] : 0.0;
         S.mus[k] = (in && p.logl_kind == LOGL_GAUSSIAN) ? p.g_mu[k] : 0.0;
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const DevParams p)
         S.his[k] = (in && p.logp_kind == LOGP_UNIFORM) ? p.p_hi[k] : pos_inf();
     }
     const long long TW = (long long)T * W;
-    const long long c0 = (long long)blockIdx.x * NC;       // first chain of this block
+    const long long c0 = (long long)blockIdx.x * nc;       // first chain of this block
     const long long cme = c0 + tid;                        // the chain this thread owns in phase A
     const bool have = cme < TW;
     const int tme = have ? (int)(cme / W) : 0, wme = have ? (int)(cme % W) : 0;
