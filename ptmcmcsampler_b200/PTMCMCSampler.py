@@ -9,8 +9,8 @@ chain / jump files and the progress line.
 Differences a reference user should know:
 
 * one process drives all temperatures (``ntemps=``) and, new, ``nwalkers`` independent ladders;
-  the reference's one-MPI-rank-per-temperature layout has no counterpart, ``comm`` is accepted
-  for signature parity only;
+  ``comm`` is accepted for signature parity only.  The reference's one-MPI-rank-per-temperature layout
+  is covered by ``dist_group=..., shard="ladder"`` (one process per GPU, several rungs each);
 * ``logl`` / ``logp`` may be objects from :mod:`ptmcmcsampler_b200.likelihoods` (fully on device)
   or plain callables (evaluated on the host once per iteration, as are custom Python jumps);
 * random numbers come from a counter-based Philox stream keyed by ``seed`` instead of PCG64, so
@@ -66,14 +66,18 @@ class PTSampler(object):
     :param device: CUDA device ordinal
     :param record_rows: rows of the thinned record kept on the device between flushes
     :param walker_offset: global id of this process's walker 0 (walker sharding over several GPUs)
-    :param dist_group: ``torch.distributed`` process group over which the proposal covariance is
-        pooled (``True`` = the default group); ``None`` keeps this sampler independent
+    :param dist_group: ``torch.distributed`` process group this sampler is sharded over (``True`` =
+        the default group); ``None`` keeps this sampler independent
+    :param shard: with ``dist_group``: ``"walkers"`` (default) -- every rank runs its own ``nwalkers``
+        complete ladders and only the proposal covariance is pooled; ``"ladder"`` -- the ``ntemps`` rungs
+        are split contiguously over the ranks (rank 0 holds T=1, like the reference's MPI layout with
+        several rungs per rank) and the swap exchanges the boundary rung between neighbours
     """
 
     def __init__(self, ndim, logl, logp, cov, groups=None, loglargs=[], loglkwargs={}, logpargs=[],
                  logpkwargs={}, logl_grad=None, logp_grad=None, comm=MPI.COMM_WORLD, outDir="./chains",
                  verbose=True, resume=False, seed=None, ntemps=None, nwalkers=1, device=0, record_rows=None,
-                 walker_offset=0, dist_group=None):
+                 walker_offset=0, dist_group=None, shard="walkers"):
         self.comm = comm
         self.MPIrank = 0
         if comm is not None and hasattr(comm, "Get_size") and comm.Get_size() > 1:
@@ -85,7 +89,19 @@ class PTSampler(object):
         self.device = int(device)
         self.walker_offset = int(walker_offset)
         self._record_rows = record_rows
-        self.dist_group = dist_group  # torch.distributed group to pool the covariance over (walker sharding)
+        self.dist_group = dist_group  # torch.distributed group (walker or ladder sharding)
+        if shard not in ("walkers", "ladder"):
+            raise ValueError("shard must be 'walkers' or 'ladder'")
+        self.shard = shard
+        self._group = None if dist_group is True else dist_group
+        self._shard_rank, self._shard_world = 0, 1
+        if dist_group is not None and shard == "ladder":
+            import torch.distributed as dist
+
+            self._shard_rank, self._shard_world = dist.get_rank(self._group), dist.get_world_size(self._group)
+            self.MPIrank = self._shard_rank  # rank g holds rungs [g*T/G, (g+1)*T/G), ref :94-97, :278
+        self._lo, self._Tloc = 0, self.nchain
+        self._comm = None
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")
         self.seed = int(seed)
@@ -203,10 +219,19 @@ class PTSampler(object):
         mh_temp = np.array(self.ladder, dtype=np.float64)
         if self._hotChain:
             mh_temp[-1] = 1e80  # ref :281-282
+        shard_kw = {}
+        ladder = np.asarray(self.ladder, np.float64)
+        if self._shard_world > 1:
+            from . import distributed
+
+            shard_kw = distributed.ladder_shard_kwargs(ladder, self._shard_world, self._shard_rank)
+            self._Tloc, ladder = shard_kw.pop("ntemps"), shard_kw.pop("ladder")
+            self._lo = shard_kw["temp_offset"]
+            mh_temp = mh_temp[self._lo:self._lo + self._Tloc].copy()
         self._mh_temp = mh_temp
         self._engine = _cabi.Engine(
-            d, self.nwalkers, self.nchain, np.asarray(self.cov, dtype=np.float64), np.asarray(self.ladder, np.float64),
-            mh_temp=mh_temp, seed=self.seed, groups=None if self._default_groups() else self.groups,
+            d, self.nwalkers, self._Tloc, np.asarray(self.cov, dtype=np.float64), ladder,
+            mh_temp=mh_temp, seed=self.seed, **shard_kw, groups=None if self._default_groups() else self.groups,
             cycle=self._cycle_segments(), de_weight=self.DEweight, cov_update=self.covUpdate, burn=self.burn,
             tskip=self.Tskip, thin=self.thin,
             logl_kind=self._dev_logl.kind if self._dev_logl is not None else _cabi.LOGL_EXTERNAL,
@@ -214,6 +239,12 @@ class PTSampler(object):
             logp_kind=self._dev_logp.kind if self._dev_logp is not None else _cabi.LOGP_EXTERNAL,
             logp_params=self._dev_logp.params(d) if self._dev_logp is not None else None,
             record_hot=self.writeHotChains, record_rows=rr, device=self.device, walker_offset=self.walker_offset)
+        if self._shard_world > 1:
+            from . import distributed
+
+            if self._external:
+                raise NotImplementedError("ladder sharding needs device targets and the built-in proposals")
+            self._comm = distributed.LadderComm(self._engine, self._group)
         self._pull_factor()
 
     def _default_groups(self):
@@ -280,16 +311,26 @@ class PTSampler(object):
             raise ValueError("ladder has %d entries for %d temperatures" % (len(self.ladder), self.nchain))
         self.temp = self.ladder[self.MPIrank]
         self._hotChain = bool(hotChain) and self.nchain > 1
-        self.fname = self.outDir + "/chain_{0}.txt".format(self.temp)
         self.writeHotChains = bool(writeHotChains)
         self._hot_fnames = [self.outDir + "/chain_{0}.txt".format(t) for t in self.ladder]
         if self._hotChain:
             self._hot_fnames[-1] = self.outDir + "/chain_hot.txt"
+        if self._shard_world > 1:  # this rank's rungs; its first rung plays the reference's self.temp
+            from . import distributed
+
+            lo, hi = distributed.ladder_slice(self.nchain, self._shard_world, self._shard_rank)
+            self.temp = self.ladder[lo]
+            self._hot_fnames = self._hot_fnames[lo:hi]
+            self.fname = self._hot_fnames[0]
+        else:
+            self.fname = self.outDir + "/chain_{0}.txt".format(self.temp)
+        self._writes_primary = self.MPIrank == 0 or self.writeHotChains  # ref :346
 
         self.resumeLength = 0
         if self.resume and os.path.isfile(self.fname):
             raise NotImplementedError("resume=True: replay from chain files is not implemented in this engine yet")
-        open(self.fname, "w").close()
+        if self._writes_primary:
+            open(self.fname, "w").close()
         if self.writeHotChains:
             for f in self._hot_fnames[1:]:
                 open(f, "w").close()
@@ -348,7 +389,7 @@ class PTSampler(object):
         self._pull_counters()
         if iter // self.thin >= self.ind_next_write:
             self._writeToFile(iter)
-            if iter > 0:
+            if iter > 0 and self.MPIrank == 0:
                 self._pull_adapt()
                 np.save(self.outDir + "/cov.npy", np.asarray(self.cov))
             if self.verbose:
@@ -367,18 +408,19 @@ class PTSampler(object):
         write_end = iter // self.thin + 1
         rows = range(self.ind_next_write, min(write_end, self._rows_pulled))
         acc_rate = self.naccepted_all[0, 0] / iter if iter > 0 else 0
-        pt_acc = 1
-        if self.nchain > 1 and self.swapProposed != 0:
+        pt_acc = 1  # the hottest chain has no hotter partner (ref :737-739)
+        if self._lo < self.nchain - 1 and self.swapProposed != 0:
             pt_acc = self.nswap_accepted_all[0, 0] / self.swapProposed
-        with open(self.fname, "a+") as fh:
-            for ind in rows:
-                fh.write("\t".join(["%22.22f" % v for v in self._chain[ind]]))
-                fh.write("\t%f\t%f\t%f\t%f\n" % (self._lnprob[ind], self._lnlike[ind], acc_rate, pt_acc))
+        if self._writes_primary:
+            with open(self.fname, "a+") as fh:
+                for ind in rows:
+                    fh.write("\t".join(["%22.22f" % v for v in self._chain[ind]]))
+                    fh.write("\t%f\t%f\t%f\t%f\n" % (self._lnprob[ind], self._lnlike[ind], acc_rate, pt_acc))
         if self.writeHotChains and self._hot_rows:
-            for t in range(1, self.nchain):
+            for t in range(1, self._Tloc):
                 a_t = self.naccepted_all[t, 0] / iter if iter > 0 else 0
                 p_t = 1
-                if t < self.nchain - 1 and self.swapProposed != 0:
+                if self._lo + t < self.nchain - 1 and self.swapProposed != 0:
                     p_t = self.nswap_accepted_all[t, 0] / self.swapProposed
                 with open(self._hot_fnames[t], "a+") as fh:
                     for r0, ch, lnl, lnp in self._hot_rows:
@@ -387,6 +429,8 @@ class PTSampler(object):
                             fh.write("\t%f\t%f\t%f\t%f\n" % (lnp[i, t], lnl[i, t], a_t, p_t))
             self._hot_rows = []
         self.ind_next_write = write_end
+        if self.MPIrank != 0:
+            return
         # jump statistics, T=1 chain only (ref :751-766)
         njumps = len(self.propCycle)
         with open(self.outDir + "/jumps.txt", "w") as fout:
@@ -402,7 +446,9 @@ class PTSampler(object):
     # ------------------------------------------------------------------ sampling --------------
     def _full_p0(self, p0):
         p0 = np.asarray(p0, dtype=np.float64)
-        T, W, d = self.nchain, self.nwalkers, self.ndim
+        T, W, d = self._Tloc, self.nwalkers, self.ndim
+        if p0.shape == (self.nchain, W, d) and self._shard_world > 1:
+            return np.ascontiguousarray(p0[self._lo:self._lo + T])
         if p0.shape == (d,):
             return np.broadcast_to(p0, (T, W, d)).copy()
         if p0.shape == (W, d):
@@ -461,7 +507,11 @@ class PTSampler(object):
     def _advance(self, n, iter0):
         """Run ``n`` iterations starting after ``iter0``."""
         if not self._external:
-            if self.dist_group is not None:
+            if self._comm is not None:
+                from . import distributed
+
+                distributed.run_ladder(self._engine, n, self._comm, self.Tskip)
+            elif self.dist_group is not None:
                 from . import distributed
 
                 distributed.run(self._engine, n, None if self.dist_group is True else self.dist_group)
@@ -525,7 +575,10 @@ class PTSampler(object):
     def _finish(self):
         self._pull_rows()
         self._pull_counters()
-        self._pull_adapt()
+        if self.MPIrank == 0:
+            self._pull_adapt()
+        else:
+            self._pull_factor()
         self._buffers = None
 
     def _fetch_buffers(self):
