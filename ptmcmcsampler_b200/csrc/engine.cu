@@ -19,6 +19,7 @@
 #include "../../include/ptmcmc_b200.h"
 #include "adapt_kernels.cuh"
 #include "mh_kernels.cuh"
+#include "mh_mma_kernel.cuh"
 #include "mh_sorted_kernel.cuh"
 #include "params.h"
 #include "swap_kernels.cuh"
@@ -100,6 +101,10 @@ struct Engine {
     int sm_count = 148;
     int mh_variant = 0;  // 0: sorted shared-memory kernel, 1: thread-per-chain register kernel, 2: generic
     int sort_nc = 256;   // chains (= threads) per block of the sorted kernel
+    // tensor-core (DMMA) kernel: fragment-order matrices and launch geometry
+    bool mma_ok = false;
+    int mma_nt = 0, mma_nc = 0, mma_ld = 0, mma_smem = 0;
+    double *d_Uf = nullptr, *d_Pf = nullptr, *d_gPfull = nullptr, *d_Ut = nullptr;
 };
 
 int fail(Engine *e, int code, const char *fmt, ...)
@@ -217,12 +222,88 @@ cudaError_t launch_sorted(const Engine *e, const DevParams &p)
     return cudaGetLastError();
 }
 
+template <int NT>
+cudaError_t launch_mma(const Engine *e, const DevParams &p)
+{
+    constexpr bool USMEM = NT <= 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t st = cudaFuncSetAttribute(mh_mma_kernel<NT, USMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              227 * 1024);
+        if (st != cudaSuccess) return st;
+        attr_done = true;
+    }
+    MmaArgs a{e->d_Uf, e->d_Pf, e->d_Ut, e->mma_nc, e->mma_ld, mma_layout(NT, e->mma_nc, e->mma_ld, USMEM)};
+    const int blocks = (int)(((long long)e->T * e->W + e->mma_nc - 1) / e->mma_nc);
+    mh_mma_kernel<NT, USMEM><<<blocks, MMA_THREADS, e->mma_smem, e->stream>>>(p, a);
+    return cudaGetLastError();
+}
+
+// instantiated n-tile counts (ndim <= 8 NT); the smallest one that covers ndim is used
+int mma_pick_nt(int d)
+{
+    const int need = (d + 7) / 8;
+    for (int nt : {1, 2, 3, 4, 8, 13, 16})
+        if (nt >= need) return nt;
+    return 0;
+}
+
+// chains per block: two blocks per SM when at least 128 chains fit that way, else one block per SM
+void mma_geometry(Engine *e)
+{
+    const int NT = e->mma_nt, KP = 8 * NT;
+    e->mma_ld = (KP % 16 == 8) ? KP : KP + 8;
+    const bool usmem = NT <= 4;
+    auto fits = [&](int nc, int budget) { return mma_layout(NT, nc, e->mma_ld, usmem).total <= budget; };
+    int nc = 0;
+    for (int c : {256, 192, 128})
+        if (!nc && fits(c, 113 * 1024)) nc = c;
+    if (!nc)
+        for (int c = 256; c >= 8 && !nc; c -= 8)
+            if ((c % 64 == 0 || c < 64) && fits(c, 227 * 1024)) nc = c;
+    if (const char *v = getenv("PTMCMC_MMA_NC")) {
+        const int c = atoi(v);
+        if (c >= 8 && c <= 256 && c % 8 == 0 && fits(c, 227 * 1024)) nc = c;
+    }
+    e->mma_nc = nc;
+    e->mma_smem = nc ? mma_layout(NT, nc, e->mma_ld, usmem).total : 0;
+    if (!nc) e->mma_ok = false;
+}
+
+cudaError_t build_u_frags(Engine *e)
+{
+    if (!e->mma_ok) return cudaSuccess;
+    const int n = e->mma_nt * e->mma_nt * 64;
+    frag_build_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_U, e->d, e->mma_nt, 1, e->d_Uf);
+    transpose_kernel<<<(e->d * e->d + 255) / 256, 256, 0, e->stream>>>(e->d_U, e->d, e->d_Ut);
+    e->tm.launches[PTMCMC_K_ADAPT] += 2;
+    return cudaGetLastError();
+}
+
+bool use_mma(const Engine *e)
+{
+    if (!e->mma_ok) return false;
+    if (e->mh_variant == 3) return true;
+    return e->mh_variant == 0 && e->d > MAX_REG_DIM;  // larger ndim: the alternative is the local-memory kernel
+}
+
 cudaError_t launch_mh(Engine *e, long long it0, long long it1, bool tail)
 {
     DevParams p = make_params(e);
     p.it0 = it0; p.it1 = it1; p.tail = tail ? 1 : 0;
     LaunchTimer lt(e, PTMCMC_K_MH);
     e->tm.chain_steps += (it1 - it0 + 1) * (long long)e->T * e->W;
+    if (use_mma(e)) {
+        switch (e->mma_nt) {
+        case 1: return launch_mma<1>(e, p);
+        case 2: return launch_mma<2>(e, p);
+        case 3: return launch_mma<3>(e, p);
+        case 4: return launch_mma<4>(e, p);
+        case 8: return launch_mma<8>(e, p);
+        case 13: return launch_mma<13>(e, p);
+        default: return launch_mma<16>(e, p);
+        }
+    }
     if (fast_reg_path(e) && e->mh_variant == 0) {
         const int d = e->d;
         if (d <= 4) return launch_sorted<4>(e, p);
@@ -273,7 +354,8 @@ cudaError_t launch_factor(Engine *e, const double *batch, double n_prev, int res
     f.U = e->d_U; f.S = e->d_S; f.sqrtS = e->d_sqrtS;
     f.work_a = e->d_work_a; f.work_v = e->d_work_v; f.ord = e->d_ord;
     adapt_finalize_kernel<<<1, 128, 0, e->stream>>>(f);
-    return cudaGetLastError();
+    cudaError_t st = cudaGetLastError();
+    return st != cudaSuccess ? st : build_u_frags(e);
 }
 
 // local batch moments of the AM ring into d_batch = {n, mean, M2c}
@@ -532,6 +614,25 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         if (smem > 48 * 1024)
             CUDA_TRY(nullptr, cudaFuncSetAttribute(moments_m2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    // tensor-core path: dense Gaussian target, one identity group, box or flat prior
+    e->mma_nt = mma_pick_nt(d);
+    e->mma_ok = cfg->logl_kind == PTMCMC_LOGL_GAUSSIAN && e->identity_group && e->mma_nt > 0 &&
+                (cfg->logp_kind == PTMCMC_LOGP_UNIFORM || cfg->logp_kind == PTMCMC_LOGP_FLAT);
+    if (e->mma_ok) mma_geometry(e);
+    if (e->mma_ok) {
+        const size_t nf = (size_t)e->mma_nt * e->mma_nt * 64;
+        CUDA_TRY(nullptr, dalloc(&e->d_Uf, nf));
+        CUDA_TRY(nullptr, dalloc(&e->d_Pf, nf));
+        CUDA_TRY(nullptr, dalloc(&e->d_gPfull, (size_t)d * d));
+        CUDA_TRY(nullptr, dalloc(&e->d_Ut, (size_t)d * d));
+        const double *A = cfg->logl_params + d;
+        std::vector<double> Pn((size_t)d * d);
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) Pn[(size_t)i * d + j] = -0.25 * (A[(size_t)i * d + j] + A[(size_t)j * d + i]);
+        CUDA_TRY(nullptr, cudaMemcpy(e->d_gPfull, Pn.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice));
+        frag_build_kernel<<<((int)nf + 255) / 256, 256, 0, e->stream>>>(e->d_gPfull, d, e->mma_nt, 0, e->d_Pf);
+        CUDA_TRY(nullptr, cudaGetLastError());
+    }
     // initial factor (ref :138-145)
     cudaError_t st = launch_factor(e, nullptr, 0.0, 0);
     if (st != cudaSuccess) return fail(nullptr, PTMCMC_ERR_CUDA, "initial factorisation: %s", cudaGetErrorString(st));
@@ -566,7 +667,7 @@ void ptmcmc_destroy(ptmcmc_engine *h)
                     e->d_plo, e->d_phi, e->d_rec_x, e->d_rec_lnl, e->d_rec_lnp, e->d_prop, e->d_acc,
                     e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_part, e->d_part2, e->d_batch,
                     e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos, e->d_stage,
-                    e->d_carry_code, e->d_carry_L};
+                    e->d_carry_code, e->d_carry_L, e->d_Uf, e->d_Pf, e->d_gPfull, e->d_Ut};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -870,6 +971,7 @@ int32_t ptmcmc_set_factor(ptmcmc_engine *h, const double *U, const double *S)
     CUDA_TRY(e, cudaMemcpy(e->d_S, S, sizeof(double) * e->soff[e->ngroups], cudaMemcpyHostToDevice));
     const int n = e->soff[e->ngroups];
     sqrt_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(e->d_S, e->d_sqrtS, n);
+    CUDA_TRY(e, build_u_frags(e));
     e->tm.launches[PTMCMC_K_ADAPT] += 1;
     CUDA_TRY(e, cudaGetLastError());
     return 0;
