@@ -186,7 +186,7 @@ int32_t ptmcmc_am_ring(ptmcmc_engine *e, void **dev_ptr, int64_t *ndoubles);
  * ptmcmc_run will not repeat it.  Lets the caller place collectives around it. */
 int32_t ptmcmc_maintain(ptmcmc_engine *e);
 
-/* ref jumpDict[name] = [proposed, accepted] (:602, :622) per chain: prop/acc are [T][W][njumps];
+/* ref jumpDict[name] = [proposed, accepted] (:602, :622) per chain: prop/acc are [njumps][T][W];
  * nswap_accepted per chain [T][W] (:691) and swapProposed (:692) */
 int32_t ptmcmc_njumps(const ptmcmc_engine *e);
 int32_t ptmcmc_get_counters(ptmcmc_engine *e, int64_t *prop, int64_t *acc, int64_t *swap_acc,

@@ -54,6 +54,21 @@ class _function_wrapper(object):
         return self.f(x, *self.args, **self.kwargs)
 
 
+class _BuiltinJump(object):
+    """Names one of the device-side proposals in ``propCycle`` / ``jumpDict`` (ref :820-985).  A plain
+    object rather than a bound method, so the sampler is not part of a reference cycle and its
+    page-locked result arrays and device memory are released as soon as it goes out of scope."""
+
+    def __init__(self, name, jid, doc):
+        self.__name__, self.jid, self.__doc__ = name, jid, doc
+
+    def __call__(self, x, iter, beta):
+        raise NotImplementedError("the %s proposal is drawn on the device; this handle only names it" % self.__name__)
+
+    def __repr__(self):
+        return "<device proposal %s>" % self.__name__
+
+
 class PTSampler(object):
     """Parallel-tempering MCMC sampler with adaptive (AM / SCAM) and differential-evolution
     proposals; API of the reference's ``PTSampler`` (ref :40-155).
@@ -142,20 +157,14 @@ class PTSampler(object):
         self.aux = []
         self._ext_jumps = []  # user callables in registration order -> engine jump ids 3, 4, ...
         self._engine = None
+        # handles of the built-in proposals, same names as the reference's methods (ref :820, :879, :936)
+        self.covarianceJumpProposalSCAM = _BuiltinJump(
+            "covarianceJumpProposalSCAM", _cabi.JUMP_SCAM, "single-component adaptive jump (ref :820-876)")
+        self.covarianceJumpProposalAM = _BuiltinJump(
+            "covarianceJumpProposalAM", _cabi.JUMP_AM, "adaptive-Metropolis jump (ref :879-933)")
+        self.DEJump = _BuiltinJump("DEJump", _cabi.JUMP_DE, "differential-evolution jump (ref :936-985)")
 
     # ------------------------------------------------------------------ plugin surface --------
-    def covarianceJumpProposalSCAM(self, x, iter, beta):
-        """Identifies the device-side single-component adaptive jump in ``propCycle`` (ref :820-876)."""
-        raise NotImplementedError("the SCAM proposal is drawn on the device; this handle only names it")
-
-    def covarianceJumpProposalAM(self, x, iter, beta):
-        """Identifies the device-side adaptive-Metropolis jump in ``propCycle`` (ref :879-933)."""
-        raise NotImplementedError("the AM proposal is drawn on the device; this handle only names it")
-
-    def DEJump(self, x, iter, beta):
-        """Identifies the device-side differential-evolution jump in ``propCycle`` (ref :936-985)."""
-        raise NotImplementedError("the DE proposal is drawn on the device; this handle only names it")
-
     def addProposalToCycle(self, func, weight):
         """Add ``func(x, iter, beta) -> (q, qxy)`` to the cycle with integer ``weight`` (ref :988-1014)."""
         if weight == 0:  # silently ignored, as in the reference (:1001-1004)
@@ -186,17 +195,12 @@ class PTSampler(object):
         return np.array([1])
 
     # ------------------------------------------------------------------ engine plumbing -------
-    def _builtin_ids(self):
-        return {self.covarianceJumpProposalSCAM: _cabi.JUMP_SCAM, self.covarianceJumpProposalAM: _cabi.JUMP_AM,
-                self.DEJump: _cabi.JUMP_DE}
-
     def _cycle_segments(self):
         """propCycle (weight-replicated list) -> [(jump id, weight)] in order."""
-        builtin = self._builtin_ids()
         segs = []
         for f in self.propCycle:
-            if f in builtin:
-                jid = builtin[f]
+            if isinstance(f, _BuiltinJump):
+                jid = f.jid
             else:
                 if f not in self._ext_jumps:
                     self._ext_jumps.append(f)
@@ -287,13 +291,12 @@ class PTSampler(object):
         self._chain_all = _cabi.pinned_empty((N, W, self.ndim))
         self._lnlike_all = _cabi.pinned_empty((N, W))
         self._lnprob_all = _cabi.pinned_empty((N, W))
-        self._chain_all[...] = 0.0
-        self._lnlike_all[...] = 0.0
-        self._lnprob_all[...] = 0.0
+        # rows are filled as the device record is pulled; the unwritten tail is zeroed in _finish()
         self._chain, self._lnlike, self._lnprob = self._chain_all[:, 0], self._lnlike_all[:, 0], self._lnprob_all[:, 0]
         self._hot_rows = None
         self.ind_next_write = 0
         self._rows_pulled = 0
+        self._counters_at = None
         self.naccepted = 0
         self.swapProposed = 0
         self.nswap_accepted = 0
@@ -362,7 +365,16 @@ class PTSampler(object):
         eng.release_rows(rows)
 
     def _pull_counters(self):
-        prop, acc, sw, nsw = self._engine.counters()
+        it = self._engine.iteration
+        if getattr(self, "_counters_at", None) == it:
+            return
+        self._counters_at = it
+        if it == 0:  # nothing proposed yet: no device round trip
+            shp = (self._Tloc, self.nwalkers, self._engine.njumps)
+            prop, acc = np.zeros(shp, dtype=np.int64), np.zeros(shp, dtype=np.int64)
+            sw, nsw = np.zeros(shp[:2], dtype=np.int64), 0
+        else:
+            prop, acc, sw, nsw = self._engine.counters()
         self._prop, self._acc, self._swap_acc = prop, acc, sw
         names = {_cabi.JUMP_SCAM: "covarianceJumpProposalSCAM", _cabi.JUMP_AM: "covarianceJumpProposalAM",
                  _cabi.JUMP_DE: "DEJump"}
@@ -575,6 +587,8 @@ class PTSampler(object):
     def _finish(self):
         self._pull_rows()
         self._pull_counters()
+        for a in (self._chain_all, self._lnlike_all, self._lnprob_all):
+            a[self._rows_pulled:] = 0.0  # rows never reached (the reference's arrays start as zeros, :208-212)
         if self.MPIrank == 0:
             self._pull_adapt()
         else:

@@ -127,11 +127,28 @@ int fail(Engine *e, int code, const char *fmt, ...)
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
+// Device memory comes from the stream-ordered allocator with an unbounded release threshold: building
+// and destroying engines repeatedly (one per PTSampler.sample call) then reuses the pooled blocks
+// instead of paying cudaMalloc / cudaFree for gigabytes each time.
+thread_local cudaStream_t g_alloc_stream = nullptr;
+
+void keep_pool_cached(int device)
+{
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[device] = true;
+}
+
 template <typename T>
 cudaError_t dalloc(T **p, size_t n)
 {
-    cudaError_t st = cudaMalloc((void **)p, sizeof(T) * (n ? n : 1));
-    if (st == cudaSuccess) st = cudaMemset(*p, 0, sizeof(T) * (n ? n : 1));
+    cudaError_t st = cudaMallocAsync((void **)p, sizeof(T) * (n ? n : 1), g_alloc_stream);
+    if (st == cudaSuccess) st = cudaMemsetAsync(*p, 0, sizeof(T) * (n ? n : 1), g_alloc_stream);
     return st;
 }
 
@@ -474,6 +491,8 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
     e->sm_count = prop.multiProcessorCount;
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    keep_pool_cached(cfg->device);
+    g_alloc_stream = e->stream;  // allocations, fills and uploads below are ordered on the engine's stream
     CUDA_TRY(nullptr, cudaEventCreate(&e->ev0));
     CUDA_TRY(nullptr, cudaEventCreate(&e->ev1));
     e->ladder.assign(cfg->ladder, cfg->ladder + T);
@@ -535,8 +554,8 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     CUDA_TRY(nullptr, dalloc(&e->d_stage, C * d));
     CUDA_TRY(nullptr, dalloc(&e->d_ladder, T));
     CUDA_TRY(nullptr, dalloc(&e->d_mh_temp, T));
-    CUDA_TRY(nullptr, cudaMemcpy(e->d_ladder, e->ladder.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
-    CUDA_TRY(nullptr, cudaMemcpy(e->d_mh_temp, e->mh_temp.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+    CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_ladder, e->ladder.data(), sizeof(double) * T, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_mh_temp, e->mh_temp.data(), sizeof(double) * T, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(nullptr, dalloc(&e->d_cov, (size_t)d * d));
     CUDA_TRY(nullptr, dalloc(&e->d_mu, d));
     CUDA_TRY(nullptr, dalloc(&e->d_m2, (size_t)d * d));
@@ -550,11 +569,11 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     CUDA_TRY(nullptr, dalloc(&e->d_ord, dmax));
     CUDA_TRY(nullptr, dalloc(&e->d_work_a, (size_t)dmax * dmax));
     CUDA_TRY(nullptr, dalloc(&e->d_work_v, (size_t)dmax * dmax));
-    CUDA_TRY(nullptr, cudaMemcpy(e->d_goff, e->goff.data(), sizeof(int) * e->goff.size(), cudaMemcpyHostToDevice));
-    CUDA_TRY(nullptr, cudaMemcpy(e->d_gidx, e->gidx.data(), sizeof(int) * e->gidx.size(), cudaMemcpyHostToDevice));
-    CUDA_TRY(nullptr, cudaMemcpy(e->d_uoff, e->uoff.data(), sizeof(int) * e->uoff.size(), cudaMemcpyHostToDevice));
-    CUDA_TRY(nullptr, cudaMemcpy(e->d_soff, e->soff.data(), sizeof(int) * e->soff.size(), cudaMemcpyHostToDevice));
-    CUDA_TRY(nullptr, cudaMemcpy(e->d_cov, cfg->cov, sizeof(double) * d * d, cudaMemcpyHostToDevice));
+    CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_goff, e->goff.data(), sizeof(int) * e->goff.size(), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_gidx, e->gidx.data(), sizeof(int) * e->gidx.size(), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_uoff, e->uoff.data(), sizeof(int) * e->uoff.size(), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_soff, e->soff.data(), sizeof(int) * e->soff.size(), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_cov, cfg->cov, sizeof(double) * d * d, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(nullptr, dalloc(&e->d_am, (size_t)cfg->cov_update * d * W));  // ref :220
     CUDA_TRY(nullptr, dalloc(&e->d_de, (size_t)cfg->burn * W * d));        // ref :221
     // targets
@@ -570,8 +589,8 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         }
         CUDA_TRY(nullptr, dalloc(&e->d_gmu, d));
         CUDA_TRY(nullptr, dalloc(&e->d_gP, (size_t)d * d));
-        CUDA_TRY(nullptr, cudaMemcpy(e->d_gmu, mu, sizeof(double) * d, cudaMemcpyHostToDevice));
-        CUDA_TRY(nullptr, cudaMemcpy(e->d_gP, P.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice));
+        CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_gmu, mu, sizeof(double) * d, cudaMemcpyHostToDevice, e->stream));
+        CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_gP, P.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice, e->stream));
     } else if (cfg->logl_kind == PTMCMC_LOGL_CURVED) {
         if (d % 2) return fail(nullptr, PTMCMC_ERR_ARG, "curved log-likelihood needs an even ndim");
     } else if (cfg->logl_kind != PTMCMC_LOGL_ROSENBROCK && cfg->logl_kind != PTMCMC_LOGL_EXTERNAL) {
@@ -581,8 +600,8 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         if (!cfg->logp_params) return fail(nullptr, PTMCMC_ERR_ARG, "uniform log-prior needs parameters");
         CUDA_TRY(nullptr, dalloc(&e->d_plo, d));
         CUDA_TRY(nullptr, dalloc(&e->d_phi, d));
-        CUDA_TRY(nullptr, cudaMemcpy(e->d_plo, cfg->logp_params, sizeof(double) * d, cudaMemcpyHostToDevice));
-        CUDA_TRY(nullptr, cudaMemcpy(e->d_phi, cfg->logp_params + d, sizeof(double) * d, cudaMemcpyHostToDevice));
+        CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_plo, cfg->logp_params, sizeof(double) * d, cudaMemcpyHostToDevice, e->stream));
+        CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_phi, cfg->logp_params + d, sizeof(double) * d, cudaMemcpyHostToDevice, e->stream));
         e->p_inside = cfg->logp_params[2 * d];
         e->p_inclusive = cfg->logp_params[2 * d + 1] != 0.0;
     } else if (cfg->logp_kind != PTMCMC_LOGP_FLAT && cfg->logp_kind != PTMCMC_LOGP_EXTERNAL) {
@@ -629,7 +648,7 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         std::vector<double> Pn((size_t)d * d);
         for (int i = 0; i < d; ++i)
             for (int j = 0; j < d; ++j) Pn[(size_t)i * d + j] = -0.25 * (A[(size_t)i * d + j] + A[(size_t)j * d + i]);
-        CUDA_TRY(nullptr, cudaMemcpy(e->d_gPfull, Pn.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice));
+        CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_gPfull, Pn.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice, e->stream));
         frag_build_kernel<<<((int)nf + 255) / 256, 256, 0, e->stream>>>(e->d_gPfull, d, e->mma_nt, 0, e->d_Pf);
         CUDA_TRY(nullptr, cudaGetLastError());
     }
@@ -669,7 +688,8 @@ void ptmcmc_destroy(ptmcmc_engine *h)
                     e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos, e->d_stage,
                     e->d_carry_code, e->d_carry_L, e->d_Uf, e->d_Pf, e->d_gPfull, e->d_Ut};
     for (void *p : ptrs)
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, e->stream);
+    if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -730,8 +750,9 @@ int32_t ptmcmc_set_state_external(ptmcmc_engine *h, const double *x0, const doub
     int rc = upload_state(e, x0);
     if (rc) return rc;
     const size_t C = (size_t)e->T * e->W;
-    CUDA_TRY(e, cudaMemcpy(e->lnl[e->cur], lnl, sizeof(double) * C, cudaMemcpyHostToDevice));
-    CUDA_TRY(e, cudaMemcpy(e->lp[e->cur], lnprior, sizeof(double) * C, cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpyAsync(e->lnl[e->cur], lnl, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->lp[e->cur], lnprior, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // lnl / lnprior may be reused by the caller
     return finish_set_state(e);
 }
 
@@ -787,6 +808,7 @@ int32_t ptmcmc_propose(ptmcmc_engine *h, double *q, int32_t *jump)
     if (e->sharded) return fail(e, PTMCMC_ERR_STATE, "host callbacks are not available on a ladder-sharded engine");
     if (e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose called twice");
     if (!e->d_q) {  // staging for the host round trip, allocated on first use
+        g_alloc_stream = e->stream;
         const size_t C0 = (size_t)e->T * e->W;
         CUDA_TRY(e, dalloc(&e->d_q, C0 * e->d));
         CUDA_TRY(e, dalloc(&e->d_qxy, C0));
@@ -967,8 +989,8 @@ int32_t ptmcmc_set_factor(ptmcmc_engine *h, const double *U, const double *S)
     Engine *e = (Engine *)h;
     if (!e || !U || !S) return PTMCMC_ERR_ARG;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    CUDA_TRY(e, cudaMemcpy(e->d_U, U, sizeof(double) * e->uoff[e->ngroups], cudaMemcpyHostToDevice));
-    CUDA_TRY(e, cudaMemcpy(e->d_S, S, sizeof(double) * e->soff[e->ngroups], cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_U, U, sizeof(double) * e->uoff[e->ngroups], cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_S, S, sizeof(double) * e->soff[e->ngroups], cudaMemcpyHostToDevice, e->stream));
     const int n = e->soff[e->ngroups];
     sqrt_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(e->d_S, e->d_sqrtS, n);
     CUDA_TRY(e, build_u_frags(e));
@@ -1141,14 +1163,8 @@ int32_t ptmcmc_get_counters(ptmcmc_engine *h, int64_t *prop, int64_t *acc, int64
     const size_t C = (size_t)e->T * e->W;
     const int nj = e->njumps;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    std::vector<unsigned long long> tmp(C * nj);
-    for (int pass = 0; pass < 2; ++pass) {
-        int64_t *dst = pass ? acc : prop;
-        if (!dst) continue;
-        CUDA_TRY(e, cudaMemcpy(tmp.data(), pass ? e->d_acc : e->d_prop, sizeof(unsigned long long) * C * nj, cudaMemcpyDeviceToHost));
-        for (int j = 0; j < nj; ++j)
-            for (size_t c = 0; c < C; ++c) dst[c * nj + j] = (int64_t)tmp[(size_t)j * C + c];
-    }
+    if (prop) CUDA_TRY(e, cudaMemcpy(prop, e->d_prop, sizeof(int64_t) * C * nj, cudaMemcpyDeviceToHost));
+    if (acc) CUDA_TRY(e, cudaMemcpy(acc, e->d_acc, sizeof(int64_t) * C * nj, cudaMemcpyDeviceToHost));
     if (swap_acc) CUDA_TRY(e, cudaMemcpy(swap_acc, e->d_swap_acc, sizeof(int64_t) * C, cudaMemcpyDeviceToHost));
     if (swap_proposed) *swap_proposed = e->swap_proposed;
     return 0;
