@@ -6,6 +6,7 @@
 // running (n, mu, M2) with Chan's formula, which equals the sequential recursion up to rounding),
 // _updateDEbuffer :806-817 and shift_array :27-37.
 #pragma once
+#include "mma_f64.cuh"
 #include "params.h"
 
 namespace ptm {
@@ -111,6 +112,114 @@ __global__ void moments_m2_reduce_kernel(const double *part2, int nblocks, int d
     double tot = 0.0;
     for (int k = 0; k < nblocks; ++k) tot += part2[(size_t)k * d * d + a * d + b];
     batch[1 + d + idx] = tot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass pooled moments on the tensor cores.  The batch of covUpdate x W cold samples is a tall
+// matrix X [N][d]; with a column of ones appended, the Gram matrix G = [X-c, 1]^T [X-c, 1] holds the
+// shifted second moments, the shifted sums (last column) and N (corner) at once.  G is accumulated by
+// DMMA m8n8k4 with the sample index as k: for a k-step of 4 samples the fragment
+//     f[t] = tile[8t + (lane>>2)][s0 + (lane&3)]
+// is at the same time the A operand of row-tile t and the B operand of column-tile t, so each 8x8
+// output tile costs one DMMA and the AM ring is read exactly once (HBM bound: 1.3 GB at C2).
+// c = the running mean before this batch (zeros for the first), for conditioning only.
+constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_TW = 64;        // walkers per staged tile
+constexpr int GRAM_LDT = 68;       // tile row stride (doubles), = 4 mod 16: conflict-free fragment loads
+constexpr int GRAM_MAXT = 20;      // upper 8x8 tiles per warp: covers KP <= 136 (ndim <= 135)
+
+// part[block][KP*KP]: upper tiles (mt <= nt) of this block's partial Gram matrix.
+// MAXT = upper tiles a warp may own (register arrays): 1 covers KP <= 24, 4 covers KP <= 56.
+template <int MAXT>
+__global__ void __launch_bounds__(GRAM_THREADS) moments_gram_kernel(const double *am, int d, int W, long long nslots,
+                                                                    const double *shift, int KP, double *part)
+{
+    extern __shared__ double tile[];  // [KP][GRAM_LDT]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NTg = KP >> 3, nup = NTg * (NTg + 1) / 2;
+    int mtv[MAXT], ntv[MAXT];
+    double acc[MAXT][2];
+    int mine = 0;
+    {
+        int idx = 0;
+        for (int mt = 0; mt < NTg; ++mt)
+            for (int nt = mt; nt < NTg; ++nt, ++idx)
+                if (idx % (GRAM_THREADS / 32) == warp) {
+#pragma unroll
+                    for (int i = 0; i < MAXT; ++i)
+                        if (i == mine) { mtv[i] = mt; ntv[i] = nt; }
+                    ++mine;
+                }
+        (void)nup;
+    }
+#pragma unroll
+    for (int i = 0; i < MAXT; ++i) acc[i][0] = acc[i][1] = 0.0;
+    const long long ntw = (W + GRAM_TW - 1) / GRAM_TW;
+    for (long long item = blockIdx.x; item < nslots * ntw; item += gridDim.x) {
+        const long long slot = item / ntw;
+        const int w0 = (int)(item % ntw) * GRAM_TW;
+        __syncthreads();
+        // stage [KP][64 walkers]; four independent loads in flight per thread
+        for (int idx0 = tid; idx0 < KP * GRAM_TW; idx0 += 4 * GRAM_THREADS) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = idx0 + u * GRAM_THREADS, k = idx / GRAM_TW, ww = idx % GRAM_TW;
+                const bool in = w0 + ww < W && idx < KP * GRAM_TW;
+                v[u] = 0.0;
+                if (in && k < d) v[u] = __ldg(am + ((size_t)slot * d + k) * W + w0 + ww) - __ldg(shift + k);
+                else if (in && k == d) v[u] = 1.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = idx0 + u * GRAM_THREADS;
+                if (idx < KP * GRAM_TW) tile[(idx / GRAM_TW) * GRAM_LDT + idx % GRAM_TW] = v[u];
+            }
+        }
+        __syncthreads();
+        const double *base = tile + (lane >> 2) * GRAM_LDT + (lane & 3);
+#pragma unroll 4
+        for (int s0 = 0; s0 < GRAM_TW; s0 += 4) {
+#pragma unroll
+            for (int i = 0; i < MAXT; ++i) {
+                if (i < mine) {
+                    const double a = base[mtv[i] * 8 * GRAM_LDT + s0], b = base[ntv[i] * 8 * GRAM_LDT + s0];
+                    dmma884(acc[i][0], acc[i][1], a, b);
+                }
+            }
+        }
+    }
+    double *out = part + (size_t)blockIdx.x * KP * KP;
+#pragma unroll
+    for (int i = 0; i < MAXT; ++i) {
+        if (i < mine) {
+            const int row = 8 * mtv[i] + (lane >> 2), col = 8 * ntv[i] + 2 * (lane & 3);
+            out[row * KP + col] = acc[i][0];
+            out[row * KP + col + 1] = acc[i][1];
+        }
+    }
+}
+
+// batch = {n, mean[d], M2c[d*d]} from the blocks' partial Gram matrices (summed in block order):
+// mean = c + S1/n, M2c = S2 - S1 S1^T / n
+__global__ void moments_gram_reduce_kernel(const double *part, int nblocks, int KP, int d, const double *shift,
+                                           double *batch)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= d * d) return;
+    const int i = idx / d, j = idx % d;
+    const int a = i <= j ? i : j, b = i <= j ? j : i;
+    double s2 = 0.0, s1a = 0.0, s1b = 0.0, n = 0.0;
+    for (int k = 0; k < nblocks; ++k) {
+        const double *g = part + (size_t)k * KP * KP;
+        s2 += g[a * KP + b];
+        s1a += g[a * KP + d];
+        s1b += g[b * KP + d];
+        n += g[d * KP + d];
+    }
+    batch[1 + d + idx] = s2 - s1a * s1b / n;
+    if (i == j) batch[1 + i] = shift[i] + s1a / n;
+    if (idx == 0) batch[0] = n;
 }
 
 // Cyclic Jacobi eigen-decomposition of the n x n symmetric matrix a (destroyed); v receives the

@@ -90,7 +90,7 @@ struct Engine {
     int *d_map = nullptr;
     double *d_part = nullptr, *d_part2 = nullptr, *d_batch = nullptr;
     double *d_stage = nullptr;  // [T][W][d] staging in the host layout
-    int mom_blocks = 0;
+    int mom_blocks = 0, gram_kp = 0;
     // host-callback path staging
     double *d_q = nullptr, *d_qxy = nullptr, *d_lnl_new = nullptr, *d_lp_new = nullptr;
     int *d_jump = nullptr;
@@ -239,20 +239,23 @@ cudaError_t launch_sorted(const Engine *e, const DevParams &p)
     return cudaGetLastError();
 }
 
+constexpr int MMA_SMALL_MINB = 4;  // ndim <= 32: four 256-thread blocks per SM (<= 64 registers per thread)
+
 template <int NT>
 cudaError_t launch_mma(const Engine *e, const DevParams &p)
 {
     constexpr bool USMEM = NT <= 4;
+    constexpr int MINB = NT <= 4 ? MMA_SMALL_MINB : 1;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t st = cudaFuncSetAttribute(mh_mma_kernel<NT, USMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t st = cudaFuncSetAttribute(mh_mma_kernel<NT, USMEM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               227 * 1024);
         if (st != cudaSuccess) return st;
         attr_done = true;
     }
     MmaArgs a{e->d_Uf, e->d_Pf, e->d_Ut, e->mma_nc, e->mma_ld, mma_layout(NT, e->mma_nc, e->mma_ld, USMEM)};
     const int blocks = (int)(((long long)e->T * e->W + e->mma_nc - 1) / e->mma_nc);
-    mh_mma_kernel<NT, USMEM><<<blocks, MMA_THREADS, e->mma_smem, e->stream>>>(p, a);
+    mh_mma_kernel<NT, USMEM, MINB><<<blocks, MMA_THREADS, e->mma_smem, e->stream>>>(p, a);
     return cudaGetLastError();
 }
 
@@ -273,6 +276,9 @@ void mma_geometry(Engine *e)
     const bool usmem = NT <= 4;
     auto fits = [&](int nc, int budget) { return mma_layout(NT, nc, e->mma_ld, usmem).total <= budget; };
     int nc = 0;
+    if (NT <= 4)  // MMA_SMALL_MINB blocks per SM
+        for (int c : {128, 96, 64})
+            if (!nc && fits(c, (228 / MMA_SMALL_MINB - 1) * 1024)) nc = c;
     for (int c : {256, 192, 128})
         if (!nc && fits(c, 113 * 1024)) nc = c;
     if (!nc)
@@ -381,18 +387,25 @@ cudaError_t launch_batch_moments(Engine *e)
     const int d = e->d, W = e->W;
     const long long cu = e->cfg.cov_update;
     const double n = (double)cu * (double)W;
-    moments_sum_kernel<<<e->mom_blocks, MOM_THREADS, 0, e->stream>>>(e->d_am, d, W, cu, e->d_part);
-    moments_mean_kernel<<<(d + 127) / 128, 128, 0, e->stream>>>(e->d_part, e->mom_blocks, d, n, e->d_batch);
-    const size_t smem = sizeof(double) * d * (MOM_TILE + 1);
-    moments_m2_kernel<<<e->mom_blocks, MOM_THREADS, smem, e->stream>>>(e->d_am, d, W, cu, e->d_batch, e->d_part2);
-    moments_m2_reduce_kernel<<<(d * d + 127) / 128, 128, 0, e->stream>>>(e->d_part2, e->mom_blocks, d, e->d_batch);
+    (void)n;
+    const int KP = e->gram_kp;
+    const size_t smem = sizeof(double) * KP * GRAM_LDT;
+    if (KP <= 24)
+        moments_gram_kernel<1><<<e->mom_blocks, GRAM_THREADS, smem, e->stream>>>(e->d_am, d, W, cu, e->d_mu, KP, e->d_part2);
+    else if (KP <= 56)
+        moments_gram_kernel<4><<<e->mom_blocks, GRAM_THREADS, smem, e->stream>>>(e->d_am, d, W, cu, e->d_mu, KP, e->d_part2);
+    else
+        moments_gram_kernel<GRAM_MAXT><<<e->mom_blocks, GRAM_THREADS, smem, e->stream>>>(e->d_am, d, W, cu, e->d_mu, KP,
+                                                                                         e->d_part2);
+    moments_gram_reduce_kernel<<<(d * d + 127) / 128, 128, 0, e->stream>>>(e->d_part2, e->mom_blocks, KP, d, e->d_mu,
+                                                                            e->d_batch);
     return cudaGetLastError();
 }
 
 // ref :545-560 at the start of iteration it0 (boundary = it0-1)
 cudaError_t cov_update(Engine *e, long long boundary)
 {
-    LaunchTimer lt(e, PTMCMC_K_ADAPT, 5);
+    LaunchTimer lt(e, PTMCMC_K_ADAPT, 3);
     cudaError_t st = launch_batch_moments(e);
     if (st != cudaSuccess) return st;
     const long long it = boundary - e->cfg.cov_update;  // ref :778
@@ -624,14 +637,15 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         CUDA_TRY(nullptr, dalloc(&e->d_trace, (size_t)cfg->trace_iters * C));
         CUDA_TRY(nullptr, dalloc(&e->d_swapmaps, (size_t)cfg->trace_iters * C));
     }
-    e->mom_blocks = 2 * e->sm_count;
+    e->gram_kp = ((d + 1) + 7) / 8 * 8;  // ndim + the column of ones, padded to the 8x8 tile
+    e->mom_blocks = (e->gram_kp <= 56 ? 8 : 2) * e->sm_count;  // small tiles: many blocks per SM hide the staging latency
     CUDA_TRY(nullptr, dalloc(&e->d_part, (size_t)e->mom_blocks * d));
-    CUDA_TRY(nullptr, dalloc(&e->d_part2, (size_t)e->mom_blocks * d * d));
+    CUDA_TRY(nullptr, dalloc(&e->d_part2, (size_t)e->mom_blocks * e->gram_kp * e->gram_kp));
     CUDA_TRY(nullptr, dalloc(&e->d_batch, (size_t)1 + d + (size_t)d * d));
     {
-        const size_t smem = sizeof(double) * d * (MOM_TILE + 1);
+        const size_t smem = sizeof(double) * e->gram_kp * GRAM_LDT;
         if (smem > 48 * 1024)
-            CUDA_TRY(nullptr, cudaFuncSetAttribute(moments_m2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(nullptr, cudaFuncSetAttribute(moments_gram_kernel<GRAM_MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     // tensor-core path: dense Gaussian target, one identity group, box or flat prior
     e->mma_nt = mma_pick_nt(d);
@@ -1031,7 +1045,7 @@ int32_t ptmcmc_adapt_begin(ptmcmc_engine *h, double *batch_out)
     const long long b = e->iter;
     if (b == 0 || b % e->cfg.cov_update != 0 || e->adapt_done_iter == b) return 0;
     {
-        LaunchTimer lt(e, PTMCMC_K_ADAPT, 4);
+        LaunchTimer lt(e, PTMCMC_K_ADAPT, 2);
         cudaError_t st = launch_batch_moments(e);
         if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "batch moments: %s", cudaGetErrorString(st));
     }

@@ -28,18 +28,12 @@
 #pragma once
 #include "mh_kernels.cuh"
 #include "mh_sorted_kernel.cuh"
+#include "mma_f64.cuh"
 
 namespace ptm {
 
 constexpr int MMA_THREADS = 256;
 constexpr int MMA_WARPS = MMA_THREADS / 32;
-
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
-{
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(c0), "+d"(c1)
-        : "d"(a), "d"(b));
-}
 
 // Fragment-order image of the d x d matrix M used as the B operand of  Y[c][n] = sum_k A[c][k] M(k, n):
 //   out[((kk*NT + nt)*32 + lane)*2 + e] = M(8kk + 2(lane&3) + e, 8nt + (lane>>2)),  zero padded.
@@ -106,8 +100,10 @@ struct MmaArgs {
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
-template <int NT, bool USMEM>
-__global__ void __launch_bounds__(MMA_THREADS) mh_mma_kernel(const __grid_constant__ DevParams p,
+// MINB (blocks per SM the register allocation must allow): small ndim runs many small blocks to hide the
+// fp64 latency of the draw phase; large ndim needs the registers for the fragment arrays.
+template <int NT, bool USMEM, int MINB>
+__global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_constant__ DevParams p,
                                                              const __grid_constant__ MmaArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
