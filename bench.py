@@ -42,6 +42,12 @@ def algorithmic_bytes_per_chain_step(d=D, t=T, thin=THIN, p_de=1.0 / 3.0):
     return 2 * (8 * d + 16 + 16) + p_de * 2 * 8 * d + (8 * d + 16) / thin + 8 * d / t
 
 
+def algorithmic_flops_per_chain_step(d=D, p_am=1.0 / 3.0, p_scam=1.0 / 3.0, p_de=1.0 / 3.0):
+    """dense Gaussian logl 2d^2+3d, box prior 2d, AM mat-vecs 2d^2 (the engine's
+    x + U delta form), SCAM / DE 2d, ~30 for the Hastings test."""
+    return (2 * d * d + 3 * d) + 2 * d + p_am * 2 * d * d + (p_scam + p_de) * 2 * d + 30
+
+
 def problem():
     """C2 target: mu = 5, Sigma = A.A + 0.1 I with A as in examples/simple.py:27-30 from default_rng(20)."""
     rng = np.random.default_rng(20)
@@ -173,16 +179,25 @@ def run_engine(args, rank, world, local_rank):
     icov = np.linalg.inv(cov)
     lpar = np.concatenate([mu, icov.ravel(), [0.0]])
     ppar = np.concatenate([-50 * np.ones(D), 60 * np.ones(D), [0.0, 1.0]])
-    total_iters = ITERS * (args.steps + args.warmup)
-    eng = _cabi.Engine(D, W, T, 0.01 * np.eye(D), ladder, seed=42, cycle=((0, WEIGHTS[0]), (1, WEIGHTS[1])),
-                       de_weight=WEIGHTS[2], cov_update=COV_UPDATE, burn=BURN, tskip=TSKIP, thin=THIN,
-                       logl_params=lpar, logp_params=ppar, record_rows=total_iters // THIN + 2, device=local_rank,
-                       walker_offset=rank * W, timing=False)
+    total_iters = ITERS * (2 * args.steps + args.warmup)
+    ladder_mode = args.shard == "ladder" and world > 1
+    shard_kw, Tg = dict(ntemps=T, ladder=ladder, walker_offset=rank * W), T
+    if ladder_mode:  # BASELINE config 5: T rungs per GPU of one ladder of T * N rungs, same walkers everywhere
+        Tg = T * world
+        ladder = np.minimum((1 + np.sqrt(2.0 / D)) ** np.arange(Tg), 1e30)
+        shard_kw = distributed.ladder_shard_kwargs(ladder, world, rank)
+    eng = _cabi.Engine(D, W, shard_kw.pop("ntemps"), 0.01 * np.eye(D), shard_kw.pop("ladder"), seed=42,
+                       cycle=((0, WEIGHTS[0]), (1, WEIGHTS[1])), de_weight=WEIGHTS[2], cov_update=COV_UPDATE, burn=BURN,
+                       tskip=TSKIP, thin=THIN, logl_params=lpar, logp_params=ppar, record_rows=total_iters // THIN + 2,
+                       device=local_rank, timing=False, **shard_kw)
     x0 = np.random.default_rng(1 + rank).uniform(0, 10, (T, W, D))
     eng.set_state(x0)
+    comm = distributed.LadderComm(eng) if ladder_mode else None
 
     def step():
-        if world > 1:
+        if ladder_mode:
+            distributed.run_ladder(eng, ITERS, comm, TSKIP)
+        elif world > 1:
             distributed.run(eng, ITERS, group)
         else:
             eng.run(ITERS)
@@ -197,9 +212,9 @@ def run_engine(args, rank, world, local_rank):
         dist.barrier()
     torch.cuda.synchronize()
     eng.reset_timing()
-    eng.set_timing(True)   # per-launch CUDA events on the engine's stream (roofline of the MH kernel)
     if rank == 0:
         clocks.start()
+    # timed region: exactly K steps, nothing but the engine's own launches on its stream
     ev0.record(stream)
     for _ in range(args.steps):
         step()
@@ -209,6 +224,15 @@ def run_engine(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
+    gpu_launches = int(sum(eng.timing()["launches"].values()))
+    # same K steps again with every launch bracketed by CUDA events on the engine's stream: the
+    # per-kernel-class durations behind `roofline` (the bracketing serialises host and device, so this
+    # pass is not the one `value` is taken from)
+    eng.reset_timing()
+    eng.set_timing(True)
+    for _ in range(args.steps):
+        step()
+    eng.sync()
     clk = clocks.stop() if rank == 0 else None
     tm = eng.timing()
     eng.set_timing(False)
@@ -229,8 +253,15 @@ def run_engine(args, rank, world, local_rank):
     mh_launches, mh_ms = tm["launches"]["mh"], tm["ms"]["mh"]
     steps_per_launch = W * T * ITERS * args.steps / max(1, mh_launches)
     achieved = bpcs * steps_per_launch / (mh_ms / max(1, mh_launches) * 1e-3) / 1e9
+    fp64_peak = 37.1e12  # measured on this pool's B200: scripts/micro/dmma_rate.cu (DFMA and DMMA alike)
+    flops = algorithmic_flops_per_chain_step()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "mh_sorted_kernel<20,256,2>", "peak_source": peak_src,
+                "fp64": {"algorithmic_flops_per_chain_step": flops, "peak_tflops": fp64_peak / 1e12,
+                         "achieved_tflops": flops * steps_per_launch / (mh_ms / max(1, mh_launches) * 1e-3) / 1e12,
+                         "frac": flops * steps_per_launch / (mh_ms / max(1, mh_launches) * 1e-3) / fp64_peak,
+                         "note": "the launch keeps chain state on chip for Tskip iterations, so fp64 issue, not HBM, "
+                                 "is the binding resource (SURVEY 8d)"},
                 "algorithmic_bytes_per_chain_step": bpcs, "launches": mh_launches,
                 "avg_launch_ms": mh_ms / max(1, mh_launches),
                 "kernel_share_of_step": mh_ms / sum(tm["ms"].values()) if sum(tm["ms"].values()) > 0 else None,
@@ -241,7 +272,6 @@ def run_engine(args, rank, world, local_rank):
             roofline["traffic"] = json.load(open(prof)).get("mh_kernel_dram_bytes_per_launch")
         except Exception:
             pass
-    gpu_launches = int(sum(tm["launches"].values()))
     eng.close()
 
     # end to end through the public API: host p0 in, recorded chain out, every step
@@ -251,11 +281,12 @@ def run_engine(args, rank, world, local_rank):
     outdir = tempfile.mkdtemp(prefix="ptmcmc_bench_")
 
     def e2e_step(seed):
-        s = PTMCMCSampler.PTSampler(D, lk, pr, 0.01 * np.eye(D), outDir=outdir, verbose=False, seed=seed, ntemps=T,
-                                    nwalkers=W, device=local_rank, walker_offset=rank * W,
-                                    dist_group=True if world > 1 else None)
+        s = PTMCMCSampler.PTSampler(D, lk, pr, 0.01 * np.eye(D), outDir=outdir, verbose=False, seed=seed, ntemps=Tg,
+                                    nwalkers=W, device=local_rank, walker_offset=0 if ladder_mode else rank * W,
+                                    dist_group=True if world > 1 else None, shard="ladder" if ladder_mode else "walkers")
         s.sample(p0, ITERS, burn=BURN, covUpdate=COV_UPDATE, Tskip=TSKIP, thin=THIN, isave=ITERS,
-                 SCAMweight=WEIGHTS[0], AMweight=WEIGHTS[1], DEweight=WEIGHTS[2])
+                 SCAMweight=WEIGHTS[0], AMweight=WEIGHTS[1], DEweight=WEIGHTS[2],
+                 ladder=ladder if ladder_mode else None)
         loss = float(s._lnlike_all[-1].mean())   # the step's result read on the host
         d2h = s._chain_all.nbytes + s._lnlike_all.nbytes + s._lnprob_all.nbytes
         s.engine.close()
@@ -297,7 +328,8 @@ def run_engine(args, rank, world, local_rank):
                                    "covUpdate=burn=1000, Tskip=100, thin=10; step = 1000 MH iterations of all chains",
                        "l2": "no flush needed: each step streams the 1.3 GB AM ring and gathers from the 1.3 GB DE "
                              "history (inputs >> 126 MB L2)",
-                       "parallelism": "walker-sharded x%d" % world},
+                       "parallelism": ("ladder-sharded x%d (%d rungs, neighbour exchange of the boundary rung)" % (world, Tg)
+                                       if ladder_mode else "walker-sharded x%d" % world)},
             "ladder_steps_per_s": value / T,
             "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
         }
@@ -312,6 +344,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--shard", default="walkers", choices=["walkers", "ladder"],
+                    help="N > 1: independent walkers per GPU (default, the contract's weak scaling) or one ladder of "
+                         "32 N rungs split over the GPUs (BASELINE config 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
