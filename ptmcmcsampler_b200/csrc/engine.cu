@@ -220,23 +220,31 @@ cudaError_t launch_reg(const Engine *e, const DevParams &p)
     return cudaGetLastError();
 }
 
-constexpr int SORT_NC = 256, SORT_MINB = 2;
+constexpr int SORT_NC = 256;
 
-template <int DP>
-cudaError_t launch_sorted(const Engine *e, const DevParams &p)
+template <int DP, int MINB>
+cudaError_t launch_sorted_minb(const Engine *e, const DevParams &p)
 {
     const size_t smem = sizeof(SortedSmem<DP, SORT_NC>);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t st = cudaFuncSetAttribute(mh_sorted_kernel<DP, SORT_NC, SORT_MINB>,
+        cudaError_t st = cudaFuncSetAttribute(mh_sorted_kernel<DP, SORT_NC, MINB>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (st != cudaSuccess) return st;
         attr_done = true;
     }
     const int nc = e->sort_nc;
     const int blocks = (int)(((long long)e->T * e->W + nc - 1) / nc);
-    mh_sorted_kernel<DP, SORT_NC, SORT_MINB><<<blocks, nc, smem, e->stream>>>(p);
+    mh_sorted_kernel<DP, SORT_NC, MINB><<<blocks, nc, smem, e->stream>>>(p);
     return cudaGetLastError();
+}
+
+// 2 blocks per SM (128 registers).  Bounding the allocation for 3 blocks (<= 85 registers) was measured at
+// 2.7e9 vs 4.4e9 chain-steps/s on C2: the spills cost more than the extra warps hide.
+template <int DP>
+cudaError_t launch_sorted(const Engine *e, const DevParams &p)
+{
+    return launch_sorted_minb<DP, 2>(e, p);
 }
 
 constexpr int MMA_SMALL_MINB = 4;  // ndim <= 32: four 256-thread blocks per SM (<= 64 registers per thread)

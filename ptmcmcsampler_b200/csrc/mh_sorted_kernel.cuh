@@ -162,20 +162,22 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const DevParams p)
             if (kindr == 0) {  // AM (ref :879-933)
                 const double prob = word_to_unit(st.next());
                 const double cd = 2.4 / sqrt(2.0 * d) * cov_jump_scale(prob, temp);
-                double dl[DP];
+                // q = x + U delta accumulated column pair by column pair as the normals are drawn (same
+                // j order per row as a row-wise dot product, so the same bits): no delta array stays live
+                // and the draw of pair j+1 overlaps the 2 d FMAs of pair j
+#pragma unroll
+                for (int i = 0; i < DP; ++i) q[i] = S.xs[i * NC + cl];
 #pragma unroll
                 for (int j = 0; j < DP; j += 2) {
                     double z0 = 0.0, z1 = 0.0;
                     if (j < d) word_to_normals(st.next(), z0, z1);
-                    dl[j] = z0 * cd * S.sS[j];
-                    if (j + 1 < DP) dl[j + 1] = z1 * cd * S.sS[j + 1];
-                }
+                    const double d0 = z0 * cd * S.sS[j];
+                    const double d1 = (j + 1 < DP) ? z1 * cd * S.sS[j + 1] : 0.0;
 #pragma unroll
-                for (int i = 0; i < DP; ++i) {
-                    double a = S.xs[i * NC + cl];
-#pragma unroll
-                    for (int j = 0; j < DP; ++j) a = fma(S.Us[i * DP + j], dl[j], a);
-                    q[i] = a;
+                    for (int i = 0; i < DP; ++i) {
+                        q[i] = fma(S.Us[i * DP + j], d0, q[i]);
+                        if (j + 1 < DP) q[i] = fma(S.Us[i * DP + j + 1], d1, q[i]);
+                    }
                 }
             } else if (kindr == 1) {  // SCAM (ref :820-876)
                 const double prob = word_to_unit(st.next());
