@@ -2,117 +2,14 @@
 // per-group eigen-factor (stand-in for np.linalg.svd of a symmetric PSD block), DE history.
 //
 // Follows ref PTMCMCSampler.py _updateRecursive :769-803 (Welford over the covUpdate buffered
-// rows; here the batch of covUpdate x W pooled samples is reduced in parallel and merged into the
-// running (n, mu, M2) with Chan's formula, which equals the sequential recursion up to rounding),
+// rows; here the batch of covUpdate x W pooled samples is reduced in one tensor-core pass and merged into
+// the running (n, mu, M2) with Chan's formula, which equals the sequential recursion up to rounding),
 // _updateDEbuffer :806-817 and shift_array :27-37.
 #pragma once
 #include "mma_f64.cuh"
 #include "params.h"
 
 namespace ptm {
-
-constexpr int MOM_THREADS = 256;
-constexpr int MOM_TILE = 64;  // walkers per shared-memory tile
-
-// Pass 1: per-block column sums over the AM ring am[slot][k][w].  part[block][k]
-__global__ void __launch_bounds__(MOM_THREADS) moments_sum_kernel(const double *am, int d, int W, long long nslots,
-                                                                  double *part)
-{
-    __shared__ double red[MOM_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = 0; k < d; ++k) {
-        double s = 0.0;
-        for (long long slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
-            const double *row = am + ((size_t)slot * d + k) * W;
-            for (int w = threadIdx.x; w < W; w += blockDim.x) s += row[w];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) red[warp] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double tot = 0.0;
-            for (int i = 0; i < MOM_THREADS / 32; ++i) tot += red[i];
-            part[(size_t)blockIdx.x * d + k] = tot;
-        }
-        __syncthreads();
-    }
-}
-
-// mean[k] = (sum over blocks in fixed order) / n
-__global__ void moments_mean_kernel(const double *part, int nblocks, int d, double n, double *batch)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= d) return;
-    double tot = 0.0;
-    for (int b = 0; b < nblocks; ++b) tot += part[(size_t)b * d + k];
-    batch[0] = n;
-    batch[1 + k] = tot / n;
-}
-
-// Pass 2: per-block centred second moments.  part2[block][i*d+j], upper triangle (j >= i)
-__global__ void __launch_bounds__(MOM_THREADS) moments_m2_kernel(const double *am, int d, int W, long long nslots,
-                                                                 const double *batch, double *part2)
-{
-    extern __shared__ double tile[];  // [d][MOM_TILE+1]
-    const int ld = MOM_TILE + 1;
-    const int npairs = d * (d + 1) / 2;
-    const double *mean = batch + 1;
-    // each thread owns pairs p = threadIdx.x, +blockDim.x, ... (at most 8 per thread kept in regs
-    // per pass over the tiles; larger d loops over pair chunks)
-    for (int p0 = 0; p0 < npairs; p0 += MOM_THREADS * 8) {
-        double acc[8];
-        int pi[8], pj[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            acc[a] = 0.0;
-            int pidx = p0 + a * MOM_THREADS + threadIdx.x;
-            pi[a] = -1; pj[a] = 0;
-            if (pidx < npairs) {
-                // invert the row-major upper-triangular index
-                int i = 0, rem = pidx;
-                while (rem >= d - i) { rem -= d - i; ++i; }
-                pi[a] = i; pj[a] = i + rem;
-            }
-        }
-        const long long ntiles_w = (W + MOM_TILE - 1) / MOM_TILE;
-        for (long long tidx = blockIdx.x; tidx < nslots * ntiles_w; tidx += gridDim.x) {
-            const long long slot = tidx / ntiles_w;
-            const int w0 = (int)(tidx % ntiles_w) * MOM_TILE;
-            const int nw = min(MOM_TILE, W - w0);
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < d * MOM_TILE; idx += blockDim.x) {
-                const int k = idx / MOM_TILE, ww = idx % MOM_TILE;
-                tile[k * ld + ww] = (ww < nw) ? am[((size_t)slot * d + k) * W + w0 + ww] - mean[k] : 0.0;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                if (pi[a] >= 0) {
-                    const double *ri = tile + pi[a] * ld, *rj = tile + pj[a] * ld;
-                    double s = acc[a];
-                    for (int ww = 0; ww < MOM_TILE; ++ww) s = fma(ri[ww], rj[ww], s);
-                    acc[a] = s;
-                }
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-            if (pi[a] >= 0) part2[(size_t)blockIdx.x * d * d + pi[a] * d + pj[a]] = acc[a];
-    }
-}
-
-// batch[1+d + i*d+j] = sum over blocks (fixed order), symmetrised
-__global__ void moments_m2_reduce_kernel(const double *part2, int nblocks, int d, double *batch)
-{
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= d * d) return;
-    const int i = idx / d, j = idx % d;
-    const int a = i <= j ? i : j, b = i <= j ? j : i;
-    double tot = 0.0;
-    for (int k = 0; k < nblocks; ++k) tot += part2[(size_t)k * d * d + a * d + b];
-    batch[1 + d + idx] = tot;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Single-pass pooled moments on the tensor cores.  The batch of covUpdate x W cold samples is a tall

@@ -647,7 +647,6 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     }
     e->gram_kp = ((d + 1) + 7) / 8 * 8;  // ndim + the column of ones, padded to the 8x8 tile
     e->mom_blocks = (e->gram_kp <= 56 ? 8 : 2) * e->sm_count;  // small tiles: many blocks per SM hide the staging latency
-    CUDA_TRY(nullptr, dalloc(&e->d_part, (size_t)e->mom_blocks * d));
     CUDA_TRY(nullptr, dalloc(&e->d_part2, (size_t)e->mom_blocks * e->gram_kp * e->gram_kp));
     CUDA_TRY(nullptr, dalloc(&e->d_batch, (size_t)1 + d + (size_t)d * d));
     {
