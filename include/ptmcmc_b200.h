@@ -186,6 +186,23 @@ int32_t ptmcmc_am_ring(ptmcmc_engine *e, void **dev_ptr, int64_t *ndoubles);
  * ptmcmc_run will not repeat it.  Lets the caller place collectives around it. */
 int32_t ptmcmc_maintain(ptmcmc_engine *e);
 
+/* Checkpoint of the complete sampling state (chain state, adaptive state, AM ring, DE history, counters,
+ * iteration number).  The reference resumes by replaying its chain file (ref :290-319, :591-599) and
+ * cannot continue bit-exactly because generator state is not saved; here the streams are counter-based,
+ * so state + iteration number IS the generator state and a loaded engine continues exactly as the
+ * original would have.  The engine that loads must have been created with the same configuration.  The
+ * record window is not part of the checkpoint: fetch rows before saving. */
+int64_t ptmcmc_state_bytes(const ptmcmc_engine *e);
+int32_t ptmcmc_save_state(ptmcmc_engine *e, void *buf, int64_t nbytes);
+int32_t ptmcmc_load_state(ptmcmc_engine *e, const void *buf, int64_t nbytes);
+/* Reference-style resume (ref :591-599): advance the engine through `nrows * repeat` iterations whose
+ * states are given instead of proposed -- row r is used for `repeat` (= thin) consecutive iterations, the
+ * first call starting at iteration 1 with row index (iteration / repeat).  Buffers, covariance / DE
+ * maintenance and the record run as in ptmcmc_run; no proposal is drawn and no swap is made.
+ * x is [nrows][T][W][d], lnl / lnprior [nrows][T][W]. */
+int32_t ptmcmc_replay(ptmcmc_engine *e, int64_t niter, int64_t repeat, int64_t nrows, const double *x,
+                      const double *lnl, const double *lnprior);
+
 /* ref jumpDict[name] = [proposed, accepted] (:602, :622) per chain: prop/acc are [njumps][T][W];
  * nswap_accepted per chain [T][W] (:691) and swapProposed (:692) */
 int32_t ptmcmc_njumps(const ptmcmc_engine *e);

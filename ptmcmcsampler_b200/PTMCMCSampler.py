@@ -83,6 +83,10 @@ class PTSampler(object):
     :param walker_offset: global id of this process's walker 0 (walker sharding over several GPUs)
     :param dist_group: ``torch.distributed`` process group this sampler is sharded over (``True`` =
         the default group); ``None`` keeps this sampler independent
+    :param checkpoint: write ``<outDir>/engine_state.npy`` (the complete device state) at every
+        ``isave``; with ``resume=True`` such a file is preferred over replaying the chain file and the run
+        continues exactly where it stopped (the draws are counter-based, so state + iteration is all
+        there is to restore)
     :param shard: with ``dist_group``: ``"walkers"`` (default) -- every rank runs its own ``nwalkers``
         complete ladders and only the proposal covariance is pooled; ``"ladder"`` -- the ``ntemps`` rungs
         are split contiguously over the ranks (rank 0 holds T=1, like the reference's MPI layout with
@@ -92,7 +96,7 @@ class PTSampler(object):
     def __init__(self, ndim, logl, logp, cov, groups=None, loglargs=[], loglkwargs={}, logpargs=[],
                  logpkwargs={}, logl_grad=None, logp_grad=None, comm=MPI.COMM_WORLD, outDir="./chains",
                  verbose=True, resume=False, seed=None, ntemps=None, nwalkers=1, device=0, record_rows=None,
-                 walker_offset=0, dist_group=None, shard="walkers"):
+                 walker_offset=0, dist_group=None, shard="walkers", checkpoint=False):
         self.comm = comm
         self.MPIrank = 0
         if comm is not None and hasattr(comm, "Get_size") and comm.Get_size() > 1:
@@ -135,6 +139,7 @@ class PTSampler(object):
         self.outDir = outDir
         self.verbose = verbose
         self.resume = resume
+        self.checkpoint = bool(checkpoint)
         if not os.path.exists(self.outDir):
             try:
                 os.makedirs(self.outDir)
@@ -329,14 +334,36 @@ class PTSampler(object):
             self.fname = self.outDir + "/chain_{0}.txt".format(self.temp)
         self._writes_primary = self.MPIrank == 0 or self.writeHotChains  # ref :346
 
+        # resume (ref :289-319): an engine checkpoint if there is one, else the reference's replay of the chain file
         self.resumeLength = 0
-        if self.resume and os.path.isfile(self.fname):
-            raise NotImplementedError("resume=True: replay from chain files is not implemented in this engine yet")
-        if self._writes_primary:
-            open(self.fname, "w").close()
-        if self.writeHotChains:
-            for f in self._hot_fnames[1:]:
-                open(f, "w").close()
+        self.resumechain = None
+        self._state_file = os.path.join(self.outDir, "engine_state.npy" if self._shard_world == 1
+                                        else "engine_state_%d.npy" % self._shard_rank)
+        self._resume_state = self.resume and os.path.isfile(self._state_file)
+        if self.resume and not self._resume_state and os.path.isfile(self.fname):
+            if self.verbose:
+                print("Resuming run from chain file {0}".format(self.fname))
+            if self.nwalkers != 1 or self._shard_world != 1:
+                raise NotImplementedError("a chain file holds one walker: resuming several walkers or a sharded "
+                                          "run needs the engine checkpoint (checkpoint=True)")
+            try:
+                self.resumechain = np.loadtxt(self.fname, ndmin=2)
+                self.resumeLength = self.resumechain.shape[0]
+            except ValueError as error:
+                print("Reading old chain files failed with error", error)
+                raise Exception("Couldn't read old chain to resume")
+            if self.isave != self.thin and self.resumeLength % (self.isave / self.thin) != 1:
+                raise Exception("Old chain has {0} rows, which is not the initial sample plus a multiple of "
+                                "isave/thin = {1}".format(self.resumeLength, self.isave // self.thin))
+            if self.verbose:
+                print("Resuming with", self.resumeLength, "samples from file representing",
+                      (self.resumeLength - 1) * self.thin + 1, "original samples")
+        elif not self._resume_state:
+            if self._writes_primary:
+                open(self.fname, "w").close()
+            if self.writeHotChains:
+                for f in self._hot_fnames[1:]:
+                    open(f, "w").close()
         self._make_engine(maxIter)
         self._buffers = None
 
@@ -384,7 +411,7 @@ class PTSampler(object):
             if jid < prop.shape[2] and (name in self.jumpDict or prop[0, :, jid].sum() > 0):
                 # T=1 rung, summed over walkers (one walker: the reference's rank-0 jumpDict)
                 self.jumpDict[name] = [int(prop[0, :, jid].sum()), int(acc[0, :, jid].sum())]
-        self.naccepted = acc[0].sum() / float(self.nwalkers)
+        self.naccepted = acc[0].sum() / float(self.nwalkers) + getattr(self, "_acc_offset", 0.0)
         self.naccepted_all = acc.sum(axis=2)           # [T][W]
         self.swapProposed = nsw
         self.nswap_accepted = sw[0].sum() / float(self.nwalkers)
@@ -404,6 +431,10 @@ class PTSampler(object):
             if iter > 0 and self.MPIrank == 0:
                 self._pull_adapt()
                 np.save(self.outDir + "/cov.npy", np.asarray(self.cov))
+            if iter > 0 and self.checkpoint:
+                tmp = self._state_file + ".tmp.npy"
+                np.save(tmp, self._engine.save_state())
+                os.replace(tmp, self._state_file)
             if self.verbose:
                 if iter > 0:
                     sys.stdout.write("\r")
@@ -419,7 +450,7 @@ class PTSampler(object):
         reference's layout; all walkers stay available in ``_chain_all``."""
         write_end = iter // self.thin + 1
         rows = range(self.ind_next_write, min(write_end, self._rows_pulled))
-        acc_rate = self.naccepted_all[0, 0] / iter if iter > 0 else 0
+        acc_rate = (self.naccepted_all[0, 0] + getattr(self, "_acc_offset", 0.0)) / iter if iter > 0 else 0
         pt_acc = 1  # the hottest chain has no hotter partner (ref :737-739)
         if self._lo < self.nchain - 1 and self.swapProposed != 0:
             pt_acc = self.nswap_accepted_all[0, 0] / self.swapProposed
@@ -559,7 +590,11 @@ class PTSampler(object):
                             HMCstepsize=HMCstepsize, HMCsteps=HMCsteps, maxIter=maxIter, thin=thin, i0=i0,
                             neff=neff, writeHotChains=writeHotChains, hotChain=hotChain)
             x0 = self._full_p0(p0)
-            if self._dev_logl is not None and self._dev_logp is not None:
+            if self._resume_state or self.resumeLength > 0:
+                if self._external:
+                    raise NotImplementedError("resume needs device targets and the built-in proposals")
+                i0 = self._resume(x0)
+            elif self._dev_logl is not None and self._dev_logp is not None:
                 self._engine.set_state(x0)
             else:
                 lnl, lp = self._host_eval(x0)
@@ -570,7 +605,8 @@ class PTSampler(object):
         elif self._engine is None:
             raise ValueError("i0 != 0 requires a sampler that has already been initialised")
         self.tstart = time.time()
-        self.writeOutput(i0)  # row 0 (ref :491 -> updateChains -> writeOutput at iter 0)
+        if not (self._resume_state or self.resumeLength > 0):
+            self.writeOutput(i0)  # row 0 (ref :491 -> updateChains -> writeOutput at iter 0)
 
         iter = i0
         while iter < self.Niter:
@@ -583,6 +619,48 @@ class PTSampler(object):
         self._finish()
         if self.verbose:
             print("\nRun Complete")
+
+    def _resume(self, x0):
+        """Bring the engine to the iteration a previous run stopped at; returns that iteration."""
+        eng = self._engine
+        if self._resume_state:
+            # exact continuation: the checkpoint holds every array the step reads, the draws are counter-based
+            eng.set_state(x0)
+            eng.load_state(np.load(self._state_file))
+            it = eng.iteration
+            if self.verbose:
+                print("Resuming from engine checkpoint {0} at iteration {1}".format(self._state_file, it))
+            self._rows_pulled = self.ind_next_write = it // self.thin + 1
+            return it
+        # the reference's replay (ref :474-476, :591-599): row 0 is the initial point, every stored row is
+        # used for `thin` iterations; buffers, covariance and DE history are rebuilt through the normal
+        # update path.  Hot rungs have no file here: they are held at the given p0 during the replay.
+        rc, R, d, T = self.resumechain, self.resumeLength, self.ndim, self._Tloc
+        temp = float(self._mh_temp[0])
+        rows_x = np.repeat(x0[None], R, axis=0)               # [R][T][1][d]
+        rows_x[:, 0, 0, :] = rc[:, :d]
+        rows_lnl = np.zeros((R, T, 1))
+        rows_lp = np.zeros((R, T, 1))
+        eng.set_state(x0)
+        st = eng.state()
+        rows_lnl[:] = st[1][None]
+        rows_lp[:] = st[2][None]
+        rows_lnl[:, 0, 0] = rc[:, -3]
+        rows_lp[:, 0, 0] = rc[:, -4] - rc[:, -3] / temp       # lnprob = lnlike / temp + logp (ref :487)
+        # restart from row 0 exactly as stored
+        eng.set_state_external(rows_x[0], rows_lnl[0], rows_lp[0])
+        total, done = R * self.thin - 1, 0
+        chunk = max(self.thin, (self.isave // self.thin) * self.thin)
+        while done < total:
+            n = min(chunk, total - done)
+            first = (done + 1) // self.thin
+            last = (done + n) // self.thin
+            eng.replay(n, self.thin, rows_x[first:last + 1], rows_lnl[first:last + 1], rows_lp[first:last + 1])
+            done += n
+            self._pull_rows()
+        self.ind_next_write = R                                # these rows are already in the file (ref :476)
+        self._acc_offset = total * float(rc[-1, -2])           # ref :599
+        return total
 
     def _finish(self):
         self._pull_rows()

@@ -57,6 +57,7 @@ SYMBOLS = [
     "ptmcmc_get_trace", "ptmcmc_get_timing", "ptmcmc_reset_timing", "ptmcmc_stream", "ptmcmc_set_timing",
     "ptmcmc_host_alloc", "ptmcmc_host_free", "ptmcmc_swap_msg_doubles", "ptmcmc_swap_pending",
     "ptmcmc_swap_pack_top", "ptmcmc_swap_sweep", "ptmcmc_swap_finish", "ptmcmc_am_ring", "ptmcmc_maintain",
+    "ptmcmc_state_bytes", "ptmcmc_save_state", "ptmcmc_load_state", "ptmcmc_replay",
 ]
 
 _lib = None
@@ -123,6 +124,11 @@ def load():
     L.ptmcmc_swap_finish.argtypes = [h, C.c_void_p]
     L.ptmcmc_am_ring.argtypes = [h, C.POINTER(C.c_void_p), _i64p]
     L.ptmcmc_maintain.argtypes = [h]
+    L.ptmcmc_state_bytes.restype = C.c_int64
+    L.ptmcmc_state_bytes.argtypes = [h]
+    L.ptmcmc_save_state.argtypes = [h, C.c_void_p, C.c_int64]
+    L.ptmcmc_load_state.argtypes = [h, C.c_void_p, C.c_int64]
+    L.ptmcmc_replay.argtypes = [h, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, _dp]
     for name in SYMBOLS:
         getattr(L, name)
     if L.ptmcmc_abi_version() != ABI_VERSION:
@@ -414,6 +420,27 @@ class Engine(object):
     def maintain(self):
         """Run the covariance / DE maintenance due at the start of the next iteration now."""
         self._check(self._L.ptmcmc_maintain(self._h))
+
+    # ---- checkpoint / resume ---------------------------------------------------------------------
+    def save_state(self):
+        """Complete sampling state as a uint8 array (see ptmcmc_save_state)."""
+        n = int(self._L.ptmcmc_state_bytes(self._h))
+        buf = np.empty(n, dtype=np.uint8)
+        self._check(self._L.ptmcmc_save_state(self._h, buf.ctypes.data, n))
+        return buf
+
+    def load_state(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self._check(self._L.ptmcmc_load_state(self._h, buf.ctypes.data, buf.size))
+
+    def replay(self, niter, repeat, x, lnl, lnprior):
+        """Advance ``niter`` iterations taking the states from stored rows (reference-style resume)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        nrows = x.shape[0]
+        assert x.shape == (nrows, self.T, self.W, self.d)
+        lnl = np.ascontiguousarray(np.broadcast_to(lnl, (nrows, self.T, self.W)), dtype=np.float64)
+        lnprior = np.ascontiguousarray(np.broadcast_to(lnprior, (nrows, self.T, self.W)), dtype=np.float64)
+        self._check(self._L.ptmcmc_replay(self._h, int(niter), int(repeat), nrows, _d(x), _d(lnl), _d(lnprior)))
 
     def timing(self):
         t = Timing()

@@ -1175,6 +1175,152 @@ int32_t ptmcmc_maintain(ptmcmc_engine *h)
     return maintenance(e, e->iter + 1);
 }
 
+namespace {
+
+struct StateHeader {
+    uint64_t magic;
+    int32_t version, d, W, T, Tg, temp_offset, njumps, de_in_cycle;
+    int64_t cov_update, burn, iter, de_head, swap_proposed, swap_events, nsamp, adapt_done_iter, de_done_iter;
+    int64_t usize, ssize;
+};
+constexpr uint64_t STATE_MAGIC = 0x3030324250544d43ull;  // "CMTPB200"
+
+struct StateField {
+    void *ptr;
+    size_t bytes;
+};
+
+std::vector<StateField> state_fields(Engine *e)
+{
+    const size_t C = (size_t)e->T * e->W, d = e->d;
+    const size_t us = e->uoff[e->ngroups], ss = e->soff[e->ngroups];
+    return {{e->x[e->cur], C * d * 8},       {e->lnl[e->cur], C * 8},       {e->lp[e->cur], C * 8},
+            {e->d_cov, d * d * 8},           {e->d_mu, d * 8},              {e->d_m2, d * d * 8},
+            {e->d_U, us * 8},                {e->d_S, ss * 8},              {e->d_sqrtS, ss * 8},
+            {e->d_am, (size_t)e->cfg.cov_update * d * e->W * 8},            {e->d_de, (size_t)e->cfg.burn * e->W * d * 8},
+            {e->d_prop, C * e->njumps * 8},  {e->d_acc, C * e->njumps * 8}, {e->d_swap_acc, C * 8}};
+}
+
+}  // namespace
+
+int64_t ptmcmc_state_bytes(const ptmcmc_engine *h)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return -1;
+    size_t n = sizeof(StateHeader);
+    for (const StateField &f : state_fields(e)) n += f.bytes;
+    return (int64_t)n;
+}
+
+int32_t ptmcmc_save_state(ptmcmc_engine *h, void *buf, int64_t nbytes)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !buf) return PTMCMC_ERR_ARG;
+    if (!e->has_state || e->pending_swap || e->pending_propose)
+        return fail(e, PTMCMC_ERR_STATE, "ptmcmc_save_state: no state yet, or inside an iteration");
+    if (nbytes < ptmcmc_state_bytes(h)) return fail(e, PTMCMC_ERR_ARG, "checkpoint buffer too small");
+    StateHeader hd{};
+    hd.magic = STATE_MAGIC; hd.version = PTMCMC_ABI_VERSION;
+    hd.d = e->d; hd.W = e->W; hd.T = e->T; hd.Tg = e->Tg; hd.temp_offset = e->cfg.temp_offset; hd.njumps = e->njumps;
+    hd.de_in_cycle = e->de_in_cycle ? 1 : 0;
+    hd.cov_update = e->cfg.cov_update; hd.burn = e->cfg.burn; hd.iter = e->iter; hd.de_head = e->de_head;
+    hd.swap_proposed = e->swap_proposed; hd.swap_events = e->swap_events; hd.nsamp = e->nsamp;
+    hd.adapt_done_iter = e->adapt_done_iter; hd.de_done_iter = e->de_done_iter;
+    hd.usize = e->uoff[e->ngroups]; hd.ssize = e->soff[e->ngroups];
+    char *out = (char *)buf;
+    memcpy(out, &hd, sizeof hd);
+    out += sizeof hd;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    for (const StateField &f : state_fields(e)) {
+        CUDA_TRY(e, cudaMemcpyAsync(out, f.ptr, f.bytes, cudaMemcpyDeviceToHost, e->stream));
+        out += f.bytes;
+    }
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int32_t ptmcmc_load_state(ptmcmc_engine *h, const void *buf, int64_t nbytes)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !buf) return PTMCMC_ERR_ARG;
+    if (nbytes < (int64_t)sizeof(StateHeader)) return fail(e, PTMCMC_ERR_ARG, "checkpoint truncated");
+    StateHeader hd;
+    memcpy(&hd, buf, sizeof hd);
+    if (hd.magic != STATE_MAGIC || hd.version != PTMCMC_ABI_VERSION) return fail(e, PTMCMC_ERR_ARG, "not a checkpoint of this ABI version");
+    if (hd.d != e->d || hd.W != e->W || hd.T != e->T || hd.Tg != e->Tg || hd.temp_offset != e->cfg.temp_offset ||
+        hd.cov_update != e->cfg.cov_update || hd.burn != e->cfg.burn || hd.usize != e->uoff[e->ngroups] ||
+        hd.ssize != e->soff[e->ngroups])
+        return fail(e, PTMCMC_ERR_ARG, "checkpoint was written by an engine with a different configuration");
+    if (hd.njumps != e->njumps) return fail(e, PTMCMC_ERR_ARG, "checkpoint has %d jump kinds, engine %d", hd.njumps, e->njumps);
+    if (nbytes < ptmcmc_state_bytes(h)) return fail(e, PTMCMC_ERR_ARG, "checkpoint truncated");
+    const char *in = (const char *)buf + sizeof hd;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    for (const StateField &f : state_fields(e)) {
+        CUDA_TRY(e, cudaMemcpyAsync(f.ptr, in, f.bytes, cudaMemcpyHostToDevice, e->stream));
+        in += f.bytes;
+    }
+    e->iter = hd.iter; e->de_head = hd.de_head; e->swap_proposed = hd.swap_proposed; e->swap_events = hd.swap_events;
+    e->nsamp = hd.nsamp; e->adapt_done_iter = hd.adapt_done_iter; e->de_done_iter = hd.de_done_iter;
+    if (hd.de_in_cycle && !e->de_in_cycle && e->cfg.de_weight > 0) {  // DE had joined the cycle (ref :563-585)
+        e->cyc_jump.push_back(PTMCMC_JUMP_DE);
+        e->cyc_w.push_back(e->cfg.de_weight);
+        e->de_in_cycle = true;
+    }
+    e->rows = e->iter / e->cfg.thin + 1;
+    e->rec_base = e->rows;  // the record window restarts empty after the checkpointed iteration
+    e->has_state = true;
+    e->pending_swap = e->swept = e->pending_propose = false;
+    cudaError_t st = build_u_frags(e);
+    if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "fragment rebuild: %s", cudaGetErrorString(st));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int32_t ptmcmc_replay(ptmcmc_engine *h, int64_t niter, int64_t repeat, int64_t nrows, const double *x, const double *lnl,
+                      const double *lnprior)
+{
+    Engine *e = (Engine *)h;
+    if (!e || !x || !lnl || !lnprior || repeat < 1 || nrows < 1 || niter < 0) return PTMCMC_ERR_ARG;
+    if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_replay before ptmcmc_set_state");
+    if (e->sharded || e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_replay on a sharded engine or inside an iteration");
+    const long long end = e->iter + niter;
+    const long long row_base = (e->iter + 1) / repeat;
+    if (end / repeat - row_base >= nrows) return fail(e, PTMCMC_ERR_ARG, "ptmcmc_replay: %lld rows do not cover iterations up to %lld", (long long)nrows, end);
+    int rc = check_rows(e, end);
+    if (rc) return rc;
+    const size_t C = (size_t)e->T * e->W;
+    double *dx = nullptr, *dl = nullptr, *dp = nullptr;
+    g_alloc_stream = e->stream;
+    CUDA_TRY(e, dalloc(&dx, (size_t)nrows * C * e->d));
+    CUDA_TRY(e, dalloc(&dl, (size_t)nrows * C));
+    CUDA_TRY(e, dalloc(&dp, (size_t)nrows * C));
+    CUDA_TRY(e, cudaMemcpyAsync(dx, x, sizeof(double) * nrows * C * e->d, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(dl, lnl, sizeof(double) * nrows * C, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(dp, lnprior, sizeof(double) * nrows * C, cudaMemcpyHostToDevice, e->stream));
+    const long long cu = e->cfg.cov_update, burn = e->cfg.burn;
+    while (e->iter < end) {
+        const long long it0 = e->iter + 1;
+        rc = maintenance(e, it0);
+        if (rc) break;
+        long long seg_end = std::min<long long>(end, std::min(next_multiple(it0, cu), next_multiple(it0, burn)));
+        DevParams p = make_params(e);
+        p.it0 = it0; p.it1 = seg_end; p.tail = 1;
+        {
+            LaunchTimer lt(e, PTMCMC_K_INIT);
+            replay_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, dx, dl, dp, repeat, row_base);
+        }
+        e->iter = seg_end;
+    }
+    cudaFreeAsync(dx, e->stream);
+    cudaFreeAsync(dl, e->stream);
+    cudaFreeAsync(dp, e->stream);
+    if (rc) return rc;
+    CUDA_TRY(e, cudaGetLastError());
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
+    return 0;
+}
+
 int32_t ptmcmc_njumps(const ptmcmc_engine *h) { return h ? ((const Engine *)h)->njumps : -1; }
 
 int32_t ptmcmc_get_counters(ptmcmc_engine *h, int64_t *prop, int64_t *acc, int64_t *swap_acc, int64_t *swap_proposed)

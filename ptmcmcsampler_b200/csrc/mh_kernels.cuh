@@ -418,6 +418,34 @@ __global__ void __launch_bounds__(MH_THREADS) bookkeep_kernel(const DevParams p,
     bookkeep(p, it, t, w, [&](int k) { return xg[(size_t)k * W]; }, p.lnl[c], p.lp[c], 1.0 / p.mh_temp[t]);
 }
 
+// Reference-style resume (ref :591-599): iterations [it0, it1] take their state from stored rows
+// (host layout rows_x[row][T][W][d]); row of iteration it = it / repeat - row_base.  Only the buffer /
+// record side effects of the step happen (ref :627).
+__global__ void __launch_bounds__(MH_THREADS) replay_kernel(const DevParams p, const double *rows_x,
+                                                            const double *rows_lnl, const double *rows_lp,
+                                                            long long repeat, long long row_base)
+{
+    const int d = p.d, W = p.W, T = p.T;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (long long)T * W) return;
+    const int t = (int)(c / W), w = (int)(c % W);
+    const double beta = 1.0 / p.mh_temp[t];
+    const size_t TW = (size_t)T * W;
+    const double *xr = nullptr;
+    double lnl = 0.0, lp = 0.0;
+    for (long long it = p.it0; it <= p.it1; ++it) {
+        const size_t r = (size_t)(it / repeat - row_base);
+        xr = rows_x + (r * TW + c) * d;
+        lnl = rows_lnl[r * TW + c];
+        lp = rows_lp[r * TW + c];
+        bookkeep(p, it, t, w, [&](int k) { return xr[k]; }, lnl, lp, beta);
+    }
+    double *xg = p.x + (size_t)t * d * W + w;
+    for (int k = 0; k < d; ++k) xg[(size_t)k * W] = xr[k];
+    p.lnl[c] = lnl;
+    p.lp[c] = lp;
+}
+
 // ---- host-callback path (Python logl / logp / custom jumps), one iteration per call pair ------
 // q_out [T][W][d] row-major for the host, jump_out [T][W], word_pos [T][W] = stream position
 __global__ void __launch_bounds__(MH_THREADS) propose_kernel(const DevParams p, double *q_out, int *jump_out,
