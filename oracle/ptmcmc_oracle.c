@@ -106,25 +106,60 @@ double orc_word_to_unit(uint64_t word)
     return (double)(word >> 11) * (1.0 / 9007199254740992.0);
 }
 
-/* Box-Muller pair from one word: radius from the high 32 bits, angle from the
- * low 32 bits; quadrant reduction is done on the integer so that the angle is
- * exact (stands in for Generator.standard_normal) */
+/* Box-Muller pair from one word (stands in for Generator.standard_normal): radius from the high 32
+ * bits, angle from the low 32 bits, evaluated in SINGLE precision with individually rounded operations
+ * (fmaf, *, -, sqrtf, integer ops; compiled with -ffp-contract=off) -- the same sequence as
+ * ptmcmcsampler_b200/csrc/rng.cuh, so both sides agree to the bit.  u1 = (2 hi + 1) 2^-33 = m 2^e with a
+ * 24-bit m; the angle keeps 24 of its 30 bits after the exact quadrant reduction. */
 void orc_word_to_normals(uint64_t word, double *z0, double *z1)
 {
     uint32_t hi = (uint32_t)(word >> 32), lo = (uint32_t)word;
-    double u1 = ((double)hi + 0.5) * (1.0 / 4294967296.0);
-    double r = sqrt(-2.0 * log(u1));
-    uint32_t quad = lo >> 30;
-    double f = (double)(lo & 0x3FFFFFFFu) * (1.0 / 2147483648.0); /* in [0, 0.5) */
-    double s0 = sin(M_PI * f), c0 = cos(M_PI * f), s, c;
+    uint64_t n = ((uint64_t)hi << 1) | 1ull;
+    int lz = __builtin_clzll(n);
+    uint32_t mant = (uint32_t)((n << lz) >> 40);
+    int e = 30 - lz;
+    float m = (float)mant * 1.1920929e-07f;
+    if (mant > 11863283u) {
+        m = m * 0.5f;
+        e += 1;
+    }
+    float t = m - 1.0f;
+    float p = 0.0874394551f;
+    p = fmaf(p, t, -0.143773302f);
+    p = fmaf(p, t, 0.149490952f);
+    p = fmaf(p, t, -0.165606961f);
+    p = fmaf(p, t, 0.199569777f);
+    p = fmaf(p, t, -0.250021547f);
+    p = fmaf(p, t, 0.333341837f);
+    p = fmaf(p, t, -0.499999881f);
+    p = fmaf(p, t, 1.0f);
+    float pt = p * t;
+    float lnu = fmaf((float)e, 0.693147182f, pt);
+    float r = sqrtf(-2.0f * lnu);
+    uint32_t quad = lo >> 30, g = (lo >> 6) & 0xFFFFFFu;
+    float f = (float)g * 2.98023224e-08f;
+    int sw = g > 0x800000u;
+    float x = sw ? 0.5f - f : f;
+    float y = x * x;
+    float sp = -0.589076877f;
+    sp = fmaf(sp, y, 2.54976702f);
+    sp = fmaf(sp, y, -5.16770792f);
+    sp = fmaf(sp, y, 3.14159274f);
+    float sx = sp * x;
+    float cx = 0.231329247f;
+    cx = fmaf(cx, y, -1.3350445f);
+    cx = fmaf(cx, y, 4.05870724f);
+    cx = fmaf(cx, y, -4.93480206f);
+    cx = fmaf(cx, y, 1.0f);
+    float s0 = sw ? cx : sx, c0 = sw ? sx : cx, s, c;
     switch (quad) {
     case 0: s = s0; c = c0; break;
     case 1: s = c0; c = -s0; break;
     case 2: s = -s0; c = -c0; break;
     default: s = -c0; c = s0; break;
     }
-    *z0 = r * c;
-    *z1 = r * s;
+    *z0 = (double)(r * c);
+    *z1 = (double)(r * s);
 }
 
 static uint64_t draw_int(orc_stream *st, uint64_t n) { return orc_word_to_int(stream_next(st), n); }

@@ -20,6 +20,7 @@
 #include "adapt_kernels.cuh"
 #include "mh_kernels.cuh"
 #include "mh_mma_kernel.cuh"
+#include "mh_pipe_kernel.cuh"
 #include "mh_sorted_kernel.cuh"
 #include "params.h"
 #include "swap_kernels.cuh"
@@ -101,6 +102,7 @@ struct Engine {
     int sm_count = 148;
     int mh_variant = 0;  // 0: sorted shared-memory kernel, 1: thread-per-chain register kernel, 2: generic
     int sort_nc = 256;   // chains (= threads) per block of the sorted kernel
+    int pipe_npw = 6;    // draw warps of the warp-specialised kernel
     // tensor-core (DMMA) kernel: fragment-order matrices and launch geometry
     bool mma_ok = false;
     int mma_nt = 0, mma_nc = 0, mma_ld = 0, mma_smem = 0;
@@ -247,6 +249,27 @@ cudaError_t launch_sorted(const Engine *e, const DevParams &p)
     return launch_sorted_minb<DP, 2>(e, p);
 }
 
+template <int DP, int NPW>
+cudaError_t launch_pipe(const Engine *e, const DevParams &p)
+{
+    const size_t smem = sizeof(PipeSmem<DP>);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t st = cudaFuncSetAttribute(mh_pipe_kernel<DP, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (st != cudaSuccess) return st;
+        attr_done = true;
+    }
+    const int blocks = (int)(((long long)e->T * e->W + PIPE_NC - 1) / PIPE_NC);
+    mh_pipe_kernel<DP, NPW><<<blocks, PIPE_NC + 32 * NPW, smem, e->stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int DP>
+cudaError_t launch_pipe_npw(const Engine *e, const DevParams &p)
+{
+    return launch_pipe<DP, 6>(e, p);  // 4 / 6 / 8 draw warps measured alike
+}
+
 constexpr int MMA_SMALL_MINB = 4;  // ndim <= 32: four 256-thread blocks per SM (<= 64 registers per thread)
 
 template <int NT>
@@ -335,7 +358,8 @@ cudaError_t launch_mh(Engine *e, long long it0, long long it1, bool tail)
         default: return launch_mma<16>(e, p);
         }
     }
-    if (fast_reg_path(e) && e->mh_variant == 0) {
+    if (fast_reg_path(e) && e->mh_variant == 4 && e->d > 16 && e->d <= 20) return launch_pipe_npw<20>(e, p);
+    if (fast_reg_path(e) && (e->mh_variant == 0 || e->mh_variant == 4)) {
         const int d = e->d;
         if (d <= 4) return launch_sorted<4>(e, p);
         if (d <= 8) return launch_sorted<8>(e, p);
@@ -562,6 +586,7 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     e->sharded = e->Tg > T;
     if (e->Tg > 32767) return fail(nullptr, PTMCMC_ERR_ARG, "ntemps_global must be < 32768");
     if (const char *v = getenv("PTMCMC_MH_VARIANT")) e->mh_variant = atoi(v);
+    if (const char *v = getenv("PTMCMC_PIPE_NPW")) e->pipe_npw = atoi(v);
     if (const char *v = getenv("PTMCMC_SORT_NC")) {
         const int nc = atoi(v);
         if (nc >= 32 && nc <= 256 && nc % 32 == 0) e->sort_nc = nc;

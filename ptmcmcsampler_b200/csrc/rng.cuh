@@ -61,21 +61,57 @@ __device__ __forceinline__ double word_to_unit(uint64_t w)
 {
     return (double)(w >> 11) * (1.0 / 9007199254740992.0);
 }
-// Box-Muller pair: radius from the high 32 bits, angle from the low 32 bits with the quadrant
-// taken from the integer so the reduced angle is exact (stands in for standard_normal)
+// Box-Muller pair (stands in for standard_normal): radius from the high 32 bits, angle from the low 32
+// bits.  Evaluated in SINGLE precision with explicitly rounded operations only (fma, mul, sub, IEEE sqrt,
+// integer ops; no MUFU approximations, no contraction), so the CPU oracle reproduces every bit, at a
+// quarter of the instructions of the double-precision log / sqrt / sincospi -- the normals were a third of
+// all instructions of an MH step.  u1 = (2 hi + 1) 2^-33 is split exactly into m 2^e with a 24-bit m, so the
+// radius is the exact radius of a u1 rounded to 24 significant bits (|z| reaches 6.76); the angle keeps 24
+// of its 30 bits after the exact quadrant reduction.  Polynomials: Chebyshev fits, errors below 1e-8.
 __device__ __forceinline__ void word_to_normals(uint64_t w, double &z0, double &z1)
 {
     const uint32_t hi = (uint32_t)(w >> 32), lo = (uint32_t)w;
-    const double u1 = ((double)hi + 0.5) * (1.0 / 4294967296.0);
-    const double r = sqrt(-2.0 * log(u1));
-    const uint32_t quad = lo >> 30;
-    const double f = (double)(lo & 0x3FFFFFFFu) * (1.0 / 2147483648.0);
-    double s0, c0;
-    sincospi(f, &s0, &c0);
-    const double s = (quad == 0) ? s0 : (quad == 1) ? c0 : (quad == 2) ? -s0 : -c0;
-    const double c = (quad == 0) ? c0 : (quad == 1) ? -s0 : (quad == 2) ? -c0 : s0;
-    z0 = r * c;
-    z1 = r * s;
+    const uint64_t n = ((uint64_t)hi << 1) | 1ull;
+    const int lz = __clzll((long long)n);
+    const uint32_t mant = (uint32_t)((n << lz) >> 40);  // [2^23, 2^24)
+    int e = 30 - lz;
+    float m = __fmul_rn(__uint2float_rn(mant), 1.1920929e-07f);  // mant 2^-23 in [1, 2), exact
+    if (mant > 11863283u) {  // m > sqrt(2)
+        m = __fmul_rn(m, 0.5f);
+        e += 1;
+    }
+    const float t = __fsub_rn(m, 1.0f);  // exact
+    float p = 0.0874394551f;             // ln(1 + t) / t on [sqrt(1/2) - 1, sqrt(2) - 1]
+    p = __fmaf_rn(p, t, -0.143773302f);
+    p = __fmaf_rn(p, t, 0.149490952f);
+    p = __fmaf_rn(p, t, -0.165606961f);
+    p = __fmaf_rn(p, t, 0.199569777f);
+    p = __fmaf_rn(p, t, -0.250021547f);
+    p = __fmaf_rn(p, t, 0.333341837f);
+    p = __fmaf_rn(p, t, -0.499999881f);
+    p = __fmaf_rn(p, t, 1.0f);
+    const float lnu = __fmaf_rn(__int2float_rn(e), 0.693147182f, __fmul_rn(p, t));
+    const float r = __fsqrt_rn(__fmul_rn(-2.0f, lnu));
+    const uint32_t quad = lo >> 30, g = (lo >> 6) & 0xFFFFFFu;
+    const float f = __fmul_rn(__uint2float_rn(g), 2.98023224e-08f);  // g 2^-25 in [0, 1/2), exact
+    const bool sw = g > 0x800000u;                                    // f > 1/4: use the co-function
+    const float x = sw ? __fsub_rn(0.5f, f) : f;
+    const float y = __fmul_rn(x, x);
+    float sp = -0.589076877f;  // sin(pi x) / x in y = x^2, |x| <= 1/4
+    sp = __fmaf_rn(sp, y, 2.54976702f);
+    sp = __fmaf_rn(sp, y, -5.16770792f);
+    sp = __fmaf_rn(sp, y, 3.14159274f);
+    const float sx = __fmul_rn(sp, x);
+    float cx = 0.231329247f;   // cos(pi x) in y
+    cx = __fmaf_rn(cx, y, -1.3350445f);
+    cx = __fmaf_rn(cx, y, 4.05870724f);
+    cx = __fmaf_rn(cx, y, -4.93480206f);
+    cx = __fmaf_rn(cx, y, 1.0f);
+    const float s0 = sw ? cx : sx, c0 = sw ? sx : cx;  // sin(pi f), cos(pi f)
+    const float s = (quad == 0) ? s0 : (quad == 1) ? c0 : (quad == 2) ? -s0 : -c0;
+    const float c = (quad == 0) ? c0 : (quad == 1) ? -s0 : (quad == 2) ? -c0 : s0;
+    z0 = (double)__fmul_rn(r, c);
+    z1 = (double)__fmul_rn(r, s);
 }
 
 }  // namespace ptm

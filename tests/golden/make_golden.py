@@ -3,7 +3,7 @@
 
 Run in the build container only (needs /root/reference):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--traj-only]
 
 Trajectory fixtures (``traj_*.npz``) run the reference with its ``stream`` replaced by the
 oracle's counter-based draws (oracle/ref_harness.py), so every jump choice, accept flag, swap
@@ -103,6 +103,8 @@ def main():
     traj_case("traj_t3_curved_ext_d4", 4, 3, 400, 4242, kw3, curved=True, ext=True)
     kw4 = dict(burn=100, thin=10, covUpdate=100, SCAMweight=20, AMweight=20, DEweight=20, isave=1000, Tskip=100)
     traj_case("traj_t1_d20", 20, 1, 350, 7, kw4, pmin=0.0, pmax=10.0)
+    if "--traj-only" in sys.argv:  # the statistical bands do not depend on the oracle's draw functions
+        return
     # statistical bands (reference's own PCG64 stream)
     kws = dict(burn=1000, thin=1, covUpdate=1000, SCAMweight=20, AMweight=20, DEweight=20, isave=10**9, Tskip=10)
     stats_case("stats_t1_d8", 8, 1, 40000, 12, kws, -50.0, 60.0, 500)

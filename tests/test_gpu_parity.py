@@ -112,6 +112,16 @@ def test_tensor_core_kernel_matches_oracle(d, W, T):
     compare(o, g, x0, niter, tskip, T, chunks=(0.33, 0.7, 1.0), ftol=1e-8 if d > 32 else FTOL)
 
 
+@pytest.mark.parametrize("d,W,T", [(20, 64, 4), (20, 300, 2), (18, 33, 3), (17, 5, 1)])
+def test_warp_specialised_kernel_matches_oracle(d, W, T):
+    """mh_pipe_kernel: draw warps one iteration ahead of the step warps; same draws, same decisions."""
+    niter, tskip = 320, 10
+    cov0 = np.diag(0.01 * (1.0 + np.arange(d)))
+    o, g = make_pair(d, W, T, cov0, seed=11 + d, target=gaussian_target(d, d), niter=niter, tskip=tskip, variant=4)
+    x0 = np.random.default_rng(d).uniform(0, 10, (T, W, d))
+    compare(o, g, x0, niter, tskip, T, chunks=(0.33, 0.7, 1.0))
+
+
 def test_tensor_core_kernel_truncated_box_and_outside_start():
     d, W, T, niter = 6, 40, 3, 250
     tgt = gaussian_target(d, 3, lo=3.0, hi=7.0)
