@@ -97,24 +97,29 @@ __global__ void __launch_bounds__(GRAM_THREADS) moments_gram_kernel(const double
     }
 }
 
-// batch = {n, mean[d], M2c[d*d]} from the blocks' partial Gram matrices (summed in block order):
-// mean = c + S1/n, M2c = S2 - S1 S1^T / n
-__global__ void moments_gram_reduce_kernel(const double *part, int nblocks, int KP, int d, const double *shift,
-                                           double *batch)
+// G[idx] = sum over blocks of part[block][idx], one warp per entry, lanes stride over the blocks and the
+// lane sums are combined in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) moments_gram_sum_kernel(const double *part, int nblocks, int KP, double *G)
+{
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (idx >= KP * KP) return;
+    double s = 0.0;
+    for (int k = lane; k < nblocks; k += 32) s += part[(size_t)k * KP * KP + idx];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) G[idx] = s;
+}
+
+// batch = {n, mean[d], M2c[d*d]} from the Gram matrix G (upper tiles valid): mean = c + S1/n,
+// M2c = S2 - S1 S1^T / n
+__global__ void moments_gram_batch_kernel(const double *G, int KP, int d, const double *shift, double *batch)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= d * d) return;
     const int i = idx / d, j = idx % d;
     const int a = i <= j ? i : j, b = i <= j ? j : i;
-    double s2 = 0.0, s1a = 0.0, s1b = 0.0, n = 0.0;
-    for (int k = 0; k < nblocks; ++k) {
-        const double *g = part + (size_t)k * KP * KP;
-        s2 += g[a * KP + b];
-        s1a += g[a * KP + d];
-        s1b += g[b * KP + d];
-        n += g[d * KP + d];
-    }
-    batch[1 + d + idx] = s2 - s1a * s1b / n;
+    const double n = G[d * KP + d], s1a = G[a * KP + d], s1b = G[b * KP + d];
+    batch[1 + d + idx] = G[a * KP + b] - s1a * s1b / n;
     if (i == j) batch[1 + i] = shift[i] + s1a / n;
     if (idx == 0) batch[0] = n;
 }

@@ -89,7 +89,7 @@ struct Engine {
     unsigned char *d_trace = nullptr;
     short *d_swapmaps = nullptr;
     int *d_map = nullptr;
-    double *d_part = nullptr, *d_part2 = nullptr, *d_batch = nullptr;
+    double *d_part = nullptr, *d_part2 = nullptr, *d_batch = nullptr, *d_gram = nullptr;
     double *d_stage = nullptr;  // [T][W][d] staging in the host layout
     int mom_blocks = 0, gram_kp = 0;
     // host-callback path staging
@@ -429,15 +429,15 @@ cudaError_t launch_batch_moments(Engine *e)
     else
         moments_gram_kernel<GRAM_MAXT><<<e->mom_blocks, GRAM_THREADS, smem, e->stream>>>(e->d_am, d, W, cu, e->d_mu, KP,
                                                                                          e->d_part2);
-    moments_gram_reduce_kernel<<<(d * d + 127) / 128, 128, 0, e->stream>>>(e->d_part2, e->mom_blocks, KP, d, e->d_mu,
-                                                                            e->d_batch);
+    moments_gram_sum_kernel<<<(KP * KP + 7) / 8, 256, 0, e->stream>>>(e->d_part2, e->mom_blocks, KP, e->d_gram);
+    moments_gram_batch_kernel<<<(d * d + 127) / 128, 128, 0, e->stream>>>(e->d_gram, KP, d, e->d_mu, e->d_batch);
     return cudaGetLastError();
 }
 
 // ref :545-560 at the start of iteration it0 (boundary = it0-1)
 cudaError_t cov_update(Engine *e, long long boundary)
 {
-    LaunchTimer lt(e, PTMCMC_K_ADAPT, 3);
+    LaunchTimer lt(e, PTMCMC_K_ADAPT, 4);
     cudaError_t st = launch_batch_moments(e);
     if (st != cudaSuccess) return st;
     const long long it = boundary - e->cfg.cov_update;  // ref :778
@@ -673,6 +673,7 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     e->gram_kp = ((d + 1) + 7) / 8 * 8;  // ndim + the column of ones, padded to the 8x8 tile
     e->mom_blocks = (e->gram_kp <= 56 ? 8 : 2) * e->sm_count;  // small tiles: many blocks per SM hide the staging latency
     CUDA_TRY(nullptr, dalloc(&e->d_part2, (size_t)e->mom_blocks * e->gram_kp * e->gram_kp));
+    CUDA_TRY(nullptr, dalloc(&e->d_gram, (size_t)e->gram_kp * e->gram_kp));
     CUDA_TRY(nullptr, dalloc(&e->d_batch, (size_t)1 + d + (size_t)d * d));
     {
         const size_t smem = sizeof(double) * e->gram_kp * GRAM_LDT;
@@ -730,7 +731,7 @@ void ptmcmc_destroy(ptmcmc_engine *h)
                     e->d_cov, e->d_mu, e->d_m2, e->d_U, e->d_S, e->d_sqrtS, e->d_goff, e->d_gidx, e->d_uoff,
                     e->d_soff, e->d_ord, e->d_work_a, e->d_work_v, e->d_am, e->d_de, e->d_gmu, e->d_gP,
                     e->d_plo, e->d_phi, e->d_rec_x, e->d_rec_lnl, e->d_rec_lnp, e->d_prop, e->d_acc,
-                    e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_part, e->d_part2, e->d_batch,
+                    e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_part, e->d_part2, e->d_batch, e->d_gram,
                     e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos, e->d_stage,
                     e->d_carry_code, e->d_carry_L, e->d_Uf, e->d_Pf, e->d_gPfull, e->d_Ut};
     for (void *p : ptrs)
@@ -1077,7 +1078,7 @@ int32_t ptmcmc_adapt_begin(ptmcmc_engine *h, double *batch_out)
     const long long b = e->iter;
     if (b == 0 || b % e->cfg.cov_update != 0 || e->adapt_done_iter == b) return 0;
     {
-        LaunchTimer lt(e, PTMCMC_K_ADAPT, 2);
+        LaunchTimer lt(e, PTMCMC_K_ADAPT, 3);
         cudaError_t st = launch_batch_moments(e);
         if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "batch moments: %s", cudaGetErrorString(st));
     }
