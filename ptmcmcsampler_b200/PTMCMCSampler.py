@@ -411,8 +411,9 @@ class PTSampler(object):
             if jid < prop.shape[2] and (name in self.jumpDict or prop[0, :, jid].sum() > 0):
                 # T=1 rung, summed over walkers (one walker: the reference's rank-0 jumpDict)
                 self.jumpDict[name] = [int(prop[0, :, jid].sum()), int(acc[0, :, jid].sum())]
-        self.naccepted = acc[0].sum() / float(self.nwalkers) + getattr(self, "_acc_offset", 0.0)
-        self.naccepted_all = acc.sum(axis=2)           # [T][W]
+        # acc is a [T][W][njumps] view of the engine's [njumps][T][W] array: reduce along the contiguous layout
+        self.naccepted_all = np.add.reduce(acc.transpose(2, 0, 1), axis=0)  # [T][W]
+        self.naccepted = self.naccepted_all[0].sum() / float(self.nwalkers) + getattr(self, "_acc_offset", 0.0)
         self.swapProposed = nsw
         self.nswap_accepted = sw[0].sum() / float(self.nwalkers)
         self.nswap_accepted_all = sw
@@ -696,6 +697,23 @@ class PTSampler(object):
         self._advance(1, self._engine.iteration)
         x, lnl, lp, lnp = self._engine.state()
         return x[0, 0], lnl[0, 0], lnp[0, 0]
+
+    def write_walker_chain(self, walker, fname=None):
+        """Write the recorded T=1 chain of ``walker`` in the reference's chain-file format
+        (ref :736-745; ``sample`` itself writes walker 0 only).  Acceptance columns are the walker's final
+        rates, as in a file written in one block."""
+        if fname is None:
+            fname = os.path.join(self.outDir, "chain_1_walker%d.txt" % walker)
+        it = self._engine.iteration
+        acc = (self.naccepted_all[0, walker] / it) if it > 0 else 0
+        pt_acc = 1
+        if self._lo < self.nchain - 1 and self.swapProposed != 0:
+            pt_acc = self.nswap_accepted_all[0, walker] / self.swapProposed
+        with open(fname, "w") as fh:
+            for ind in range(self._rows_pulled):
+                fh.write("\t".join(["%22.22f" % v for v in self._chain_all[ind, walker]]))
+                fh.write("\t%f\t%f\t%f\t%f\n" % (self._lnprob_all[ind, walker], self._lnlike_all[ind, walker], acc, pt_acc))
+        return fname
 
     # convenience accessors beyond the reference ------------------------------------------------
     @property

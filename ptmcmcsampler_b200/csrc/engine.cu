@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <limits>
 #include <string>
 #include <vector>
@@ -517,6 +518,9 @@ const char *ptmcmc_last_error(const ptmcmc_engine *h) { return h ? ((const Engin
 
 static int create_impl(Engine *e, const ptmcmc_config *cfg)
 {
+    const bool tlog = getenv("PTMCMC_CREATE_TIMING") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = now();
     e->cfg = *cfg;
     const int d = e->d = cfg->ndim, W = e->W = cfg->nwalkers, T = e->T = cfg->ntemps;
     if (cfg->abi_version != PTMCMC_ABI_VERSION) return fail(nullptr, PTMCMC_ERR_ARG, "ABI version mismatch");
@@ -532,9 +536,8 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, PTMCMC_ERR_CUDA, "no CUDA device: the PT-MCMC engine has no CPU path");
     CUDA_TRY(nullptr, cudaSetDevice(cfg->device));
-    cudaDeviceProp prop;
-    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
-    e->sm_count = prop.multiProcessorCount;
+    // (cudaGetDeviceProperties costs tens of milliseconds per call; one attribute is all that is needed)
+    CUDA_TRY(nullptr, cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     keep_pool_cached(cfg->device);
     g_alloc_stream = e->stream;  // allocations, fills and uploads below are ordered on the engine's stream
@@ -699,11 +702,16 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         frag_build_kernel<<<((int)nf + 255) / 256, 256, 0, e->stream>>>(e->d_gPfull, d, e->mma_nt, 0, e->d_Pf);
         CUDA_TRY(nullptr, cudaGetLastError());
     }
+    const double t_alloc = now();
     // initial factor (ref :138-145)
     cudaError_t st = launch_factor(e, nullptr, 0.0, 0);
     if (st != cudaSuccess) return fail(nullptr, PTMCMC_ERR_CUDA, "initial factorisation: %s", cudaGetErrorString(st));
     e->tm.launches[PTMCMC_K_ADAPT] += 1;
+    const double t_launch = now();
     CUDA_TRY(nullptr, cudaStreamSynchronize(e->stream));
+    if (tlog)
+        fprintf(stderr, "ptmcmc_create: setup+alloc+upload %.2f ms, factor launch %.2f ms, sync %.2f ms\n", t_alloc - t_begin,
+                t_launch - t_alloc, now() - t_launch);
     return 0;
 }
 
@@ -993,16 +1001,17 @@ int32_t ptmcmc_release_rows(ptmcmc_engine *h, int64_t upto_row)
     if (keep > 0) {
         const size_t per_row = (size_t)e->ntr * e->W;
         const size_t src = (size_t)(upto_row - e->rec_base) * per_row, n = (size_t)keep * per_row;
-        // windows are small relative to HBM; a staged device copy keeps this simple and overlap-safe
+        // staged through a pooled scratch buffer (source and destination overlap), all on the engine's stream
         double *tmp = nullptr;
-        CUDA_TRY(e, cudaMalloc((void **)&tmp, sizeof(double) * n * e->d));
-        CUDA_TRY(e, cudaMemcpy(tmp, e->d_rec_x + src * e->d, sizeof(double) * n * e->d, cudaMemcpyDeviceToDevice));
-        CUDA_TRY(e, cudaMemcpy(e->d_rec_x, tmp, sizeof(double) * n * e->d, cudaMemcpyDeviceToDevice));
-        CUDA_TRY(e, cudaMemcpy(tmp, e->d_rec_lnl + src, sizeof(double) * n, cudaMemcpyDeviceToDevice));
-        CUDA_TRY(e, cudaMemcpy(e->d_rec_lnl, tmp, sizeof(double) * n, cudaMemcpyDeviceToDevice));
-        CUDA_TRY(e, cudaMemcpy(tmp, e->d_rec_lnp + src, sizeof(double) * n, cudaMemcpyDeviceToDevice));
-        CUDA_TRY(e, cudaMemcpy(e->d_rec_lnp, tmp, sizeof(double) * n, cudaMemcpyDeviceToDevice));
-        CUDA_TRY(e, cudaFree(tmp));
+        g_alloc_stream = e->stream;
+        CUDA_TRY(e, cudaMallocAsync((void **)&tmp, sizeof(double) * n * e->d, e->stream));
+        struct { double *buf; size_t width; } parts[3] = {{e->d_rec_x, (size_t)e->d}, {e->d_rec_lnl, 1}, {e->d_rec_lnp, 1}};
+        for (auto &pt : parts) {
+            const size_t bytes = sizeof(double) * n * pt.width;
+            CUDA_TRY(e, cudaMemcpyAsync(tmp, pt.buf + src * pt.width, bytes, cudaMemcpyDeviceToDevice, e->stream));
+            CUDA_TRY(e, cudaMemcpyAsync(pt.buf, tmp, bytes, cudaMemcpyDeviceToDevice, e->stream));
+        }
+        CUDA_TRY(e, cudaFreeAsync(tmp, e->stream));
     }
     e->rec_base = upto_row;
     return 0;

@@ -164,6 +164,16 @@ def _small_sampler(outdir, W, T, seed=5, **kw):
     return s, p0
 
 
+def test_walker_chain_export(tmp_path):
+    s, p0 = _small_sampler(str(tmp_path / "w"), 8, 2)
+    s.sample(p0, 200, burn=100, covUpdate=50, Tskip=10, thin=5, isave=100)
+    f = s.write_walker_chain(3)
+    data = np.loadtxt(f)
+    assert data.shape == (41, 10) and np.allclose(data[:, :6], s._chain_all[:, 3], atol=0)
+    w0 = np.loadtxt(os.path.join(str(tmp_path / "w"), "chain_1.0.txt"))
+    assert np.array_equal(np.loadtxt(s.write_walker_chain(0))[:, :8], w0[:, :8])
+
+
 def test_checkpoint_resume_is_exact(tmp_path):
     """Engine checkpoint: a run stopped at 300 and resumed to 600 equals the straight 600-iteration run bit
     for bit (the reference cannot do this: it does not save generator state)."""
