@@ -83,6 +83,10 @@ class PTSampler(object):
     :param walker_offset: global id of this process's walker 0 (walker sharding over several GPUs)
     :param dist_group: ``torch.distributed`` process group this sampler is sharded over (``True`` =
         the default group); ``None`` keeps this sampler independent
+    :param vectorized: Python ``logl`` / ``logp`` (and custom jumps flagged ``func.vectorized = True``)
+        take all chains at once: ``logl(X[n, ndim]) -> [n]``, ``logp(X) -> [n]`` (``-inf`` where the prior
+        rejects), ``jump(X[n, ndim], iter, beta[n]) -> (Q[n, ndim], qxy[n])``, auxiliary jumps
+        ``aux(X, Q, iter, beta) -> (Q, qxy)``.  One host call per iteration instead of one per chain.
     :param checkpoint: write ``<outDir>/engine_state.npy`` (the complete device state) at every
         ``isave``; with ``resume=True`` such a file is preferred over replaying the chain file and the run
         continues exactly where it stopped (the draws are counter-based, so state + iteration is all
@@ -96,7 +100,7 @@ class PTSampler(object):
     def __init__(self, ndim, logl, logp, cov, groups=None, loglargs=[], loglkwargs={}, logpargs=[],
                  logpkwargs={}, logl_grad=None, logp_grad=None, comm=MPI.COMM_WORLD, outDir="./chains",
                  verbose=True, resume=False, seed=None, ntemps=None, nwalkers=1, device=0, record_rows=None,
-                 walker_offset=0, dist_group=None, shard="walkers", checkpoint=False):
+                 walker_offset=0, dist_group=None, shard="walkers", checkpoint=False, vectorized=False):
         self.comm = comm
         self.MPIrank = 0
         if comm is not None and hasattr(comm, "Get_size") and comm.Get_size() > 1:
@@ -140,6 +144,7 @@ class PTSampler(object):
         self.verbose = verbose
         self.resume = resume
         self.checkpoint = bool(checkpoint)
+        self.vectorized = bool(vectorized)
         if not os.path.exists(self.outDir):
             try:
                 os.makedirs(self.outDir)
@@ -506,12 +511,26 @@ class PTSampler(object):
         T, W = x.shape[:2]
         lp = np.zeros((T, W))
         lnl = np.zeros((T, W))
+        if self.vectorized:
+            return self._host_eval_vectorized(x.reshape(T * W, -1), lnl, lp)
         for t in range(T):
             for w in range(W):
                 if self._dev_logp is None:
                     lp[t, w] = self.logp(x[t, w])
                 if self._dev_logl is None and (self._dev_logp is not None or lp[t, w] != -np.inf):
                     lnl[t, w] = self.logl(x[t, w])
+        return lnl, lp
+
+    def _host_eval_vectorized(self, X, lnl, lp):
+        """All chains in one call; logl only sees the points the prior accepts (ref :607-612)."""
+        if self._dev_logp is None:
+            lp.ravel()[:] = np.asarray(self.logp(X), dtype=np.float64)
+        if self._dev_logl is None:
+            ok = np.isfinite(lp.ravel()) | (lp.ravel() == np.inf) if self._dev_logp is None else np.ones(len(X), bool)
+            if ok.all():
+                lnl.ravel()[:] = np.asarray(self.logl(X), dtype=np.float64)
+            elif ok.any():
+                lnl.ravel()[ok] = np.asarray(self.logl(X[ok]), dtype=np.float64)
         return lnl, lp
 
     def _maybe_add_de(self, iter):
@@ -531,6 +550,30 @@ class PTSampler(object):
         qxy = np.zeros((T, W))
         lnl = np.zeros((T, W))
         lp = np.zeros((T, W))
+        if self.vectorized:
+            d = self.ndim
+            X, Q, J = x.reshape(T * W, d), q.reshape(T * W, d), jump.ravel()
+            betas = np.repeat(1.0 / self._mh_temp, W)
+            for k, f in enumerate(self._ext_jumps):
+                sel = np.nonzero(J == _cabi.JUMP_EXT0 + k)[0]
+                if len(sel) == 0:
+                    continue
+                if getattr(f, "vectorized", False):
+                    Q[sel], qxy.ravel()[sel] = f(X[sel].copy(), iter, betas[sel])
+                else:
+                    for i in sel:
+                        Q[i], qxy.ravel()[i] = f(X[i].copy(), iter, betas[i])
+            for aux in self.aux:
+                if getattr(aux, "vectorized", False):
+                    Q[:], add = aux(X.copy(), Q.copy(), iter, betas)
+                    qxy.ravel()[:] += add
+                else:
+                    for i in range(T * W):
+                        Q[i], add = aux(X[i].copy(), Q[i].copy(), iter, betas[i])
+                        qxy.ravel()[i] += add
+            self._host_eval_vectorized(Q, lnl, lp)
+            eng.accept(q, qxy, lnl, lp)
+            return
         for t in range(T):
             beta = 1 / self._mh_temp[t]
             for w in range(W):
