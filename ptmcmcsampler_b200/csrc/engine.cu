@@ -22,6 +22,7 @@
 #include "mh_kernels.cuh"
 #include "mh_mma_kernel.cuh"
 #include "mh_pipe_kernel.cuh"
+#include "mh_shadow_kernel.cuh"
 #include "mh_sorted_kernel.cuh"
 #include "params.h"
 #include "swap_kernels.cuh"
@@ -234,6 +235,8 @@ cudaError_t launch_sorted_minb(const Engine *e, const DevParams &p)
         cudaError_t st = cudaFuncSetAttribute(mh_sorted_kernel<DP, SORT_NC, MINB>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (st != cudaSuccess) return st;
+        if (const char *v = getenv("PTMCMC_SORT_CARVEOUT"))  // experiment: shared-memory carve-out in percent
+            cudaFuncSetAttribute(mh_sorted_kernel<DP, SORT_NC, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v));
         attr_done = true;
     }
     const int nc = e->sort_nc;
@@ -248,6 +251,22 @@ template <int DP>
 cudaError_t launch_sorted(const Engine *e, const DevParams &p)
 {
     return launch_sorted_minb<DP, 2>(e, p);
+}
+
+template <int DP>
+cudaError_t launch_shadow(const Engine *e, const DevParams &p)
+{
+    const size_t smem = sizeof(ShadowSmem<DP, SORT_NC>);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t st = cudaFuncSetAttribute(mh_shadow_kernel<DP, SORT_NC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem);
+        if (st != cudaSuccess) return st;
+        attr_done = true;
+    }
+    const int blocks = (int)(((long long)e->T * e->W + SORT_NC - 1) / SORT_NC);
+    mh_shadow_kernel<DP, SORT_NC, 2><<<blocks, SORT_NC, smem, e->stream>>>(p);
+    return cudaGetLastError();
 }
 
 template <int DP, int NPW>
@@ -360,7 +379,8 @@ cudaError_t launch_mh(Engine *e, long long it0, long long it1, bool tail)
         }
     }
     if (fast_reg_path(e) && e->mh_variant == 4 && e->d > 16 && e->d <= 20) return launch_pipe_npw<20>(e, p);
-    if (fast_reg_path(e) && (e->mh_variant == 0 || e->mh_variant == 4)) {
+    if (fast_reg_path(e) && e->mh_variant == 5 && e->d > 16 && e->d <= 20) return launch_shadow<20>(e, p);
+    if (fast_reg_path(e) && (e->mh_variant == 0 || e->mh_variant == 4 || e->mh_variant == 5)) {
         const int d = e->d;
         if (d <= 4) return launch_sorted<4>(e, p);
         if (d <= 8) return launch_sorted<8>(e, p);

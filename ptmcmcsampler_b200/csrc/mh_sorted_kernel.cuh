@@ -199,10 +199,23 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const DevParams p)
                 if (!(prob > 0.5)) scale = word_to_unit(st.next()) * 2.4 / sqrt(2.0 * d) * sqrt(1.0 / beta);
                 const double *bm = p.de + de_row_offset(mm, bufsize, W, p.burn, p.de_head) * d;
                 const double *bn = p.de + de_row_offset(nn, bufsize, W, p.burn, p.de_head) * d;
+                if ((d & 1) == 0) {  // rows are 16-byte aligned: half as many load instructions
 #pragma unroll
-                for (int i = 0; i < DP; ++i) {
-                    const double sigma = (i < d) ? (__ldg(bm + i) - __ldg(bn + i)) : 0.0;
-                    q[i] = fma(scale, sigma, S.xs[i * NC + cl]);
+                    for (int i = 0; i < DP; i += 2) {
+                        double2 vm = make_double2(0.0, 0.0), vn = vm;
+                        if (i < d) {
+                            vm = __ldg(reinterpret_cast<const double2 *>(bm + i));
+                            vn = __ldg(reinterpret_cast<const double2 *>(bn + i));
+                        }
+                        q[i] = fma(scale, vm.x - vn.x, S.xs[i * NC + cl]);
+                        if (i + 1 < DP) q[i + 1] = fma(scale, vm.y - vn.y, S.xs[(i + 1) * NC + cl]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < DP; ++i) {
+                        const double sigma = (i < d) ? (__ldg(bm + i) - __ldg(bn + i)) : 0.0;
+                        q[i] = fma(scale, sigma, S.xs[i * NC + cl]);
+                    }
                 }
             }
             bool inside = true;

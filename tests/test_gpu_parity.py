@@ -122,6 +122,19 @@ def test_warp_specialised_kernel_matches_oracle(d, W, T):
     compare(o, g, x0, niter, tskip, T, chunks=(0.33, 0.7, 1.0))
 
 
+@pytest.mark.parametrize("d,W,T,cycle,dew", [(20, 64, 4, ((0, 20), (1, 20)), 20), (20, 300, 2, ((0, 20), (1, 20)), 20),
+                                             (18, 33, 3, ((0, 5), (1, 40)), 5), (20, 256, 1, ((1, 20),), 0)])
+def test_shadow_kernel_matches_oracle(d, W, T, cycle, dew):
+    """mh_shadow_kernel: AM draws of iteration it+1 made during iteration it; same draws, same decisions.
+    The AM-heavy cycles overflow the draw queue (more than 128 AM chains of a block in one iteration)."""
+    niter, tskip = 320, 10
+    cov0 = np.diag(0.01 * (1.0 + np.arange(d)))
+    o, g = make_pair(d, W, T, cov0, seed=11 + d, target=gaussian_target(d, d), niter=niter, tskip=tskip, variant=5,
+                     cycle=cycle, de_weight=dew)
+    x0 = np.random.default_rng(d).uniform(0, 10, (T, W, d))
+    compare(o, g, x0, niter, tskip, T, chunks=(0.33, 0.7, 1.0))
+
+
 def test_tensor_core_kernel_truncated_box_and_outside_start():
     d, W, T, niter = 6, 40, 3, 250
     tgt = gaussian_target(d, 3, lo=3.0, hi=7.0)
