@@ -91,10 +91,12 @@ __global__ void transpose_kernel(const double *src, int d, double *dst)
 
 struct MmaArgs {
     const double *Uf;     // [NT*NT*64] fragment order of U^T   (global)
-    const double *Pf;     // [NT*NT*64] fragment order of -1/2 sym(icov) (global)
+    const double *Pf;     // [NT*NT*64] fragment order of -1/2 sym(icov), or of L / sqrt(2) when tri (global)
     const double *Ut;     // [d*d] U transposed: row k = eigenvector k (global; SCAM reads one row)
     int nc;               // chains per block (multiple of 8)
     int ld;               // row stride of the per-chain shared-memory rows (doubles, = 8 mod 16)
+    int tri;              // 1: Pf holds the Cholesky factor L of sym(icov) (lower triangular) scaled by 1/sqrt(2):
+                          //    lnl = offset - |d^T L / sqrt(2)|^2, and the all-zero tiles kk < nt are skipped
     MmaLayout L;          // computed on the host: the offsets are then plain constant-bank operands
 };
 
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
     constexpr int KP = 8 * NT;
     const int d = p.d, W = p.W, T = p.T;
     const int nc = a.nc, ld = a.ld;
+    const bool tri = a.tri != 0;
     const MmaLayout &L = a.L;
     double *xs = reinterpret_cast<double *>(smem_raw + L.xs);
     double *zq = reinterpret_cast<double *>(smem_raw + L.zq);
@@ -305,6 +308,51 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
         // ================= phase P: the AM chains, 8 at a time: zq <- U (z * cd * sqrt(S)) on the tensor
         // cores (q = x + U delta equals the reference's U (U^T x + delta), ref :923-931)
         const int nTA = (nA + 7) >> 3;
+        // few AM tiles (large ndim: 8 tiles per block, ~3 of them AM): split each tile's n-tiles over NG warps
+        // so that all warps work; every item reads the whole z row, so the results are written after a barrier
+        const int NG = (nTA > 0 && nTA <= MMA_WARPS / 2) ? min(NT, MMA_WARPS / nTA) : 1;
+        if (NG > 1) {
+            const int ta = warp / NG, g = warp % NG, NTG = (NT + NG - 1) / NG;
+            const int n0 = g * NTG, n1 = min(NT, n0 + NTG);
+            const bool item = ta < nTA && n0 < n1;
+            const int ai = ta * 8 + r;
+            const bool live = item && ai < nA;
+            const int cl = s_list[(item && ai < nA) ? ai : nA - 1];
+            double acc[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+            if (item) {
+                const double cd = s_sca[cl];
+                double dl[NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int col = 8 * nt + 2 * t;
+                    const double2 z = *reinterpret_cast<const double2 *>(zq + cl * ld + col);
+                    const double2 sv = *reinterpret_cast<const double2 *>(sSs + col);
+                    dl[nt][0] = (live && col < d) ? z.x * cd * sv.x : 0.0;
+                    dl[nt][1] = (live && col + 1 < d) ? z.y * cd * sv.y : 0.0;
+                }
+                const double2 *uf = reinterpret_cast<const double2 *>(USMEM ? Ufs : a.Uf) + lane;
+#pragma unroll
+                for (int kk = 0; kk < NT; ++kk) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        if (nt >= n0 && nt < n1) {
+                            const double2 b = USMEM ? uf[(kk * NT + nt) * 32] : __ldg(uf + (kk * NT + nt) * 32);
+                            dmma884(acc[nt][0], acc[nt][1], dl[kk][0], b.x);
+                            dmma884(acc[nt][0], acc[nt][1], dl[kk][1], b.y);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (live) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    if (nt >= n0 && nt < n1)
+                        *reinterpret_cast<double2 *>(zq + cl * ld + 8 * nt + 2 * t) = make_double2(acc[nt][0], acc[nt][1]);
+            }
+        } else
         for (int ta = warp; ta < nTA; ta += MMA_WARPS) {
             const int ai = ta * 8 + r;
             const bool live = ai < nA;
@@ -407,7 +455,7 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
                 for (int kk = 0; kk < NT; ++kk) {
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
-                        if (nb + j < NT) {
+                        if (nb + j < NT && (!tri || kk >= nb + j)) {
                             const double2 b = pf[(kk * NT + nb + j) * 32];
                             dmma884(y[j][0], y[j][1], dv[kk][0], b.x);
                             dmma884(y[j][0], y[j][1], dv[kk][1], b.y);
@@ -417,14 +465,14 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {
                     if (nb + j < NT) {
-                        part = fma(y[j][0], dv[nb + j][0], part);
-                        part = fma(y[j][1], dv[nb + j][1], part);
+                        part = fma(y[j][0], tri ? y[j][0] : dv[nb + j][0], part);
+                        part = fma(y[j][1], tri ? y[j][1] : dv[nb + j][1], part);
                     }
                 }
             }
             part += __shfl_xor_sync(0xffffffffu, part, 1);
             part += __shfl_xor_sync(0xffffffffu, part, 2);
-            const double lnln = part + p.g_offset;
+            const double lnln = tri ? p.g_offset - part : part + p.g_offset;
             const double beta = s_beta[cl];
             const double lpn = inside ? p.p_inside : neg_inf();
             const double lnpn = inside ? beta * lnln + lpn : neg_inf();  // ref :607-612
