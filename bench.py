@@ -61,9 +61,11 @@ def problem():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  The sampler is started before the warm-up
+    (the tool takes a few hundred ms to come up) and only the samples stamped inside the window given to
+    stop() are summarised."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -77,12 +79,14 @@ class ClockSampler(object):
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -91,20 +95,24 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in open(self.path):
             f = [c.strip() for c in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[5:9]) if v == "Active"]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[5:9]):
-                if v == "Active":
-                    reasons.add(n)
+        inside = [r for r in rows if t0 is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+        if inside:
+            out["window"] = "timed region"
+            rows = inside
+        elif rows:
+            out["window"] = "whole run (no sample fell inside the timed region)"
+        sm, mx, reasons = [r[1] for r in rows], [r[2] for r in rows], set(n for r in rows for n in r[3])
         os.unlink(self.path)
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
@@ -202,18 +210,19 @@ def run_engine(args, rank, world, local_rank):
         else:
             eng.run(ITERS)
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         step()
     eng.sync()
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     eng.reset_timing()
-    if rank == 0:
-        clocks.start()
+    t_wall0 = time.time()
     # timed region: exactly K steps, nothing but the engine's own launches on its stream
     ev0.record(stream)
     for _ in range(args.steps):
@@ -223,6 +232,7 @@ def run_engine(args, rank, world, local_rank):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    t_wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
     gpu_launches = int(sum(eng.timing()["launches"].values()))
     # same K steps again with every launch bracketed by CUDA events on the engine's stream: the
@@ -233,7 +243,7 @@ def run_engine(args, rank, world, local_rank):
     for _ in range(args.steps):
         step()
     eng.sync()
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
     tm = eng.timing()
     eng.set_timing(False)
     if world > 1:
