@@ -91,7 +91,7 @@ struct Engine {
     unsigned char *d_trace = nullptr;
     short *d_swapmaps = nullptr;
     int *d_map = nullptr;
-    double *d_part = nullptr, *d_part2 = nullptr, *d_batch = nullptr, *d_gram = nullptr;
+    double *d_part2 = nullptr, *d_batch = nullptr, *d_gram = nullptr;
     double *d_stage = nullptr;  // [T][W][d] staging in the host layout
     int mom_blocks = 0, gram_kp = 0;
     // host-callback path staging
@@ -207,6 +207,14 @@ struct LaunchTimer {
     }
 };
 
+// every entry point makes the engine's device current (one host thread may drive engines on several devices)
+Engine *engine_of(const ptmcmc_engine *h)
+{
+    Engine *e = (Engine *)h;
+    if (e) cudaSetDevice(e->cfg.device);
+    return e;
+}
+
 int chain_blocks(const Engine *e) { return (int)(((long long)e->T * e->W + MH_THREADS - 1) / MH_THREADS); }
 
 bool fast_reg_path(const Engine *e) { return e->identity_group && e->d <= MAX_REG_DIM; }
@@ -215,7 +223,8 @@ template <int DP>
 cudaError_t launch_reg(const Engine *e, const DevParams &p)
 {
     const size_t smem = sizeof(double) * (2 * DP * DP + 4 * DP);
-    static bool attr_done = false;
+    static bool attr_dev[64] = {};
+    bool &attr_done = attr_dev[e->cfg.device & 63];  // function attributes are per device
     if (!attr_done && smem > 48 * 1024) {
         cudaFuncSetAttribute(mh_reg_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
@@ -230,7 +239,8 @@ template <int DP, int MINB>
 cudaError_t launch_sorted_minb(const Engine *e, const DevParams &p)
 {
     const size_t smem = sizeof(SortedSmem<DP, SORT_NC>);
-    static bool attr_done = false;
+    static bool attr_dev[64] = {};
+    bool &attr_done = attr_dev[e->cfg.device & 63];  // function attributes are per device
     if (!attr_done) {
         cudaError_t st = cudaFuncSetAttribute(mh_sorted_kernel<DP, SORT_NC, MINB>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -257,7 +267,8 @@ template <int DP>
 cudaError_t launch_shadow(const Engine *e, const DevParams &p)
 {
     const size_t smem = sizeof(ShadowSmem<DP, SORT_NC>);
-    static bool attr_done = false;
+    static bool attr_dev[64] = {};
+    bool &attr_done = attr_dev[e->cfg.device & 63];  // function attributes are per device
     if (!attr_done) {
         cudaError_t st = cudaFuncSetAttribute(mh_shadow_kernel<DP, SORT_NC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)smem);
@@ -273,7 +284,8 @@ template <int DP, int NPW>
 cudaError_t launch_pipe(const Engine *e, const DevParams &p)
 {
     const size_t smem = sizeof(PipeSmem<DP>);
-    static bool attr_done = false;
+    static bool attr_dev[64] = {};
+    bool &attr_done = attr_dev[e->cfg.device & 63];  // function attributes are per device
     if (!attr_done) {
         cudaError_t st = cudaFuncSetAttribute(mh_pipe_kernel<DP, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (st != cudaSuccess) return st;
@@ -297,7 +309,8 @@ cudaError_t launch_mma(const Engine *e, const DevParams &p)
 {
     constexpr bool USMEM = NT <= 4;
     constexpr int MINB = NT <= 4 ? MMA_SMALL_MINB : 1;
-    static bool attr_done = false;
+    static bool attr_dev[64] = {};
+    bool &attr_done = attr_dev[e->cfg.device & 63];  // function attributes are per device
     if (!attr_done) {
         cudaError_t st = cudaFuncSetAttribute(mh_mma_kernel<NT, USMEM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               227 * 1024);
@@ -770,14 +783,14 @@ ptmcmc_engine *ptmcmc_create(const ptmcmc_config *cfg)
 
 void ptmcmc_destroy(ptmcmc_engine *h)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return;
     if (e->stream) cudaStreamSynchronize(e->stream);
     void *ptrs[] = {e->x[0], e->x[1], e->lnl[0], e->lnl[1], e->lp[0], e->lp[1], e->d_ladder, e->d_mh_temp,
                     e->d_cov, e->d_mu, e->d_m2, e->d_U, e->d_S, e->d_sqrtS, e->d_goff, e->d_gidx, e->d_uoff,
                     e->d_soff, e->d_ord, e->d_work_a, e->d_work_v, e->d_am, e->d_de, e->d_gmu, e->d_gP,
                     e->d_plo, e->d_phi, e->d_rec_x, e->d_rec_lnl, e->d_rec_lnp, e->d_prop, e->d_acc,
-                    e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_part, e->d_part2, e->d_batch, e->d_gram,
+                    e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_part2, e->d_batch, e->d_gram,
                     e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos, e->d_stage,
                     e->d_carry_code, e->d_carry_L, e->d_Uf, e->d_Pf, e->d_gPfull, e->d_Ut};
     for (void *p : ptrs)
@@ -821,7 +834,7 @@ static int finish_set_state(Engine *e)
 
 int32_t ptmcmc_set_state(ptmcmc_engine *h, const double *x0)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !x0) return PTMCMC_ERR_ARG;
     if (e->cfg.logl_kind == PTMCMC_LOGL_EXTERNAL || e->cfg.logp_kind == PTMCMC_LOGP_EXTERNAL)
         return fail(e, PTMCMC_ERR_STATE, "external targets: use ptmcmc_set_state_external");
@@ -838,7 +851,7 @@ int32_t ptmcmc_set_state(ptmcmc_engine *h, const double *x0)
 
 int32_t ptmcmc_set_state_external(ptmcmc_engine *h, const double *x0, const double *lnl, const double *lnprior)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !x0 || !lnl || !lnprior) return PTMCMC_ERR_ARG;
     int rc = upload_state(e, x0);
     if (rc) return rc;
@@ -851,7 +864,7 @@ int32_t ptmcmc_set_state_external(ptmcmc_engine *h, const double *x0, const doub
 
 int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_run before ptmcmc_set_state");
     if (e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_run between propose and accept");
@@ -895,7 +908,7 @@ int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
 
 int32_t ptmcmc_propose(ptmcmc_engine *h, double *q, int32_t *jump)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !q || !jump) return PTMCMC_ERR_ARG;
     if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose before set_state");
     if (e->sharded) return fail(e, PTMCMC_ERR_STATE, "host callbacks are not available on a ladder-sharded engine");
@@ -932,7 +945,7 @@ int32_t ptmcmc_propose(ptmcmc_engine *h, double *q, int32_t *jump)
 
 int32_t ptmcmc_accept(ptmcmc_engine *h, const double *q, const double *qxy, const double *lnl, const double *lnprior)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !q || !qxy || !lnl || !lnprior) return PTMCMC_ERR_ARG;
     if (!e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_accept without ptmcmc_propose");
     const size_t C = (size_t)e->T * e->W;
@@ -969,7 +982,7 @@ int64_t ptmcmc_iteration(const ptmcmc_engine *h) { return h ? ((const Engine *)h
 
 int32_t ptmcmc_sync(ptmcmc_engine *h)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     return 0;
@@ -977,7 +990,7 @@ int32_t ptmcmc_sync(ptmcmc_engine *h)
 
 int32_t ptmcmc_get_state(ptmcmc_engine *h, double *x, double *lnl, double *lnprior, double *lnprob)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     const int d = e->d, W = e->W, T = e->T;
     const size_t C = (size_t)T * W;
@@ -1015,7 +1028,7 @@ int64_t ptmcmc_row_base(const ptmcmc_engine *h) { return h ? ((const Engine *)h)
 
 int32_t ptmcmc_get_chain(ptmcmc_engine *h, int64_t row0, int64_t nrows, double *chain, double *lnl, double *lnprob)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     if (row0 < e->rec_base || row0 + nrows > e->rows || nrows < 0)
         return fail(e, PTMCMC_ERR_ARG, "rows [%lld, %lld) are not resident (window [%lld, %lld))", (long long)row0,
@@ -1031,7 +1044,7 @@ int32_t ptmcmc_get_chain(ptmcmc_engine *h, int64_t row0, int64_t nrows, double *
 
 int32_t ptmcmc_release_rows(ptmcmc_engine *h, int64_t upto_row)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     if (upto_row < e->rec_base || upto_row > e->rows) return fail(e, PTMCMC_ERR_ARG, "release_rows out of range");
     const long long keep = e->rows - upto_row;  // rows that stay resident
@@ -1057,7 +1070,7 @@ int32_t ptmcmc_release_rows(ptmcmc_engine *h, int64_t upto_row)
 
 int32_t ptmcmc_get_adapt(ptmcmc_engine *h, double *cov, double *mu, double *m2, int64_t *nsamp)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     const int d = e->d;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -1070,7 +1083,7 @@ int32_t ptmcmc_get_adapt(ptmcmc_engine *h, double *cov, double *mu, double *m2, 
 
 int32_t ptmcmc_get_factor(ptmcmc_engine *h, double *U, double *S)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     if (U) CUDA_TRY(e, cudaMemcpy(U, e->d_U, sizeof(double) * e->uoff[e->ngroups], cudaMemcpyDeviceToHost));
@@ -1080,7 +1093,7 @@ int32_t ptmcmc_get_factor(ptmcmc_engine *h, double *U, double *S)
 
 int32_t ptmcmc_set_factor(ptmcmc_engine *h, const double *U, const double *S)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !U || !S) return PTMCMC_ERR_ARG;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(e->d_U, U, sizeof(double) * e->uoff[e->ngroups], cudaMemcpyHostToDevice, e->stream));
@@ -1095,7 +1108,7 @@ int32_t ptmcmc_set_factor(ptmcmc_engine *h, const double *U, const double *S)
 
 int32_t ptmcmc_get_buffers(ptmcmc_engine *h, double *am, double *de)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     const int d = e->d, W = e->W;
     const long long cu = e->cfg.cov_update, burn = e->cfg.burn;
@@ -1120,7 +1133,7 @@ int32_t ptmcmc_get_buffers(ptmcmc_engine *h, double *am, double *de)
 
 int32_t ptmcmc_adapt_begin(ptmcmc_engine *h, double *batch_out)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !batch_out) return PTMCMC_ERR_ARG;
     const long long b = e->iter;
     if (b == 0 || b % e->cfg.cov_update != 0 || e->adapt_done_iter == b) return 0;
@@ -1137,7 +1150,7 @@ int32_t ptmcmc_adapt_begin(ptmcmc_engine *h, double *batch_out)
 
 int32_t ptmcmc_adapt_finish(ptmcmc_engine *h, const double *batch_in)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !batch_in) return PTMCMC_ERR_ARG;
     const long long b = e->iter;
     if (b == 0 || b % e->cfg.cov_update != 0 || e->adapt_done_iter == b)
@@ -1167,7 +1180,7 @@ int32_t ptmcmc_swap_pending(const ptmcmc_engine *h) { return h && ((const Engine
 
 int32_t ptmcmc_swap_pack_top(ptmcmc_engine *h, double *dev_msg)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !dev_msg) return PTMCMC_ERR_ARG;
     if (!e->sharded || !e->pending_swap) return fail(e, PTMCMC_ERR_STATE, "no sharded swap is pending");
     DevParams p = make_params(e);
@@ -1182,7 +1195,7 @@ int32_t ptmcmc_swap_pack_top(ptmcmc_engine *h, double *dev_msg)
 
 int32_t ptmcmc_swap_sweep(ptmcmc_engine *h, const double *dev_carry_in, double *dev_carry_out)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     if (!e->sharded || !e->pending_swap || e->swept) return fail(e, PTMCMC_ERR_STATE, "no sharded swap sweep is due");
     const bool hottest = e->cfg.temp_offset + e->T == e->Tg, coldest = e->cfg.temp_offset == 0;
@@ -1203,7 +1216,7 @@ int32_t ptmcmc_swap_sweep(ptmcmc_engine *h, const double *dev_carry_in, double *
 
 int32_t ptmcmc_swap_finish(ptmcmc_engine *h, const double *dev_below_top)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     if (!e->sharded || !e->pending_swap || !e->swept) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_swap_finish before ptmcmc_swap_sweep");
     if ((dev_below_top == nullptr) != (e->cfg.temp_offset == 0))
@@ -1232,7 +1245,7 @@ int32_t ptmcmc_swap_finish(ptmcmc_engine *h, const double *dev_below_top)
 
 int32_t ptmcmc_am_ring(ptmcmc_engine *h, void **dev_ptr, int64_t *ndoubles)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !dev_ptr || !ndoubles) return PTMCMC_ERR_ARG;
     *dev_ptr = e->d_am;
     *ndoubles = (int64_t)e->cfg.cov_update * e->d * e->W;
@@ -1241,7 +1254,7 @@ int32_t ptmcmc_am_ring(ptmcmc_engine *h, void **dev_ptr, int64_t *ndoubles)
 
 int32_t ptmcmc_maintain(ptmcmc_engine *h)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_maintain before ptmcmc_set_state");
     if (e->pending_swap || e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_maintain inside an iteration");
@@ -1278,7 +1291,7 @@ std::vector<StateField> state_fields(Engine *e)
 
 int64_t ptmcmc_state_bytes(const ptmcmc_engine *h)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return -1;
     size_t n = sizeof(StateHeader);
     for (const StateField &f : state_fields(e)) n += f.bytes;
@@ -1287,7 +1300,7 @@ int64_t ptmcmc_state_bytes(const ptmcmc_engine *h)
 
 int32_t ptmcmc_save_state(ptmcmc_engine *h, void *buf, int64_t nbytes)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !buf) return PTMCMC_ERR_ARG;
     if (!e->has_state || e->pending_swap || e->pending_propose)
         return fail(e, PTMCMC_ERR_STATE, "ptmcmc_save_state: no state yet, or inside an iteration");
@@ -1314,7 +1327,7 @@ int32_t ptmcmc_save_state(ptmcmc_engine *h, void *buf, int64_t nbytes)
 
 int32_t ptmcmc_load_state(ptmcmc_engine *h, const void *buf, int64_t nbytes)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !buf) return PTMCMC_ERR_ARG;
     if (nbytes < (int64_t)sizeof(StateHeader)) return fail(e, PTMCMC_ERR_ARG, "checkpoint truncated");
     StateHeader hd;
@@ -1352,7 +1365,7 @@ int32_t ptmcmc_load_state(ptmcmc_engine *h, const void *buf, int64_t nbytes)
 int32_t ptmcmc_replay(ptmcmc_engine *h, int64_t niter, int64_t repeat, int64_t nrows, const double *x, const double *lnl,
                       const double *lnprior)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !x || !lnl || !lnprior || repeat < 1 || nrows < 1 || niter < 0) return PTMCMC_ERR_ARG;
     if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_replay before ptmcmc_set_state");
     if (e->sharded || e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_replay on a sharded engine or inside an iteration");
@@ -1398,7 +1411,7 @@ int32_t ptmcmc_njumps(const ptmcmc_engine *h) { return h ? ((const Engine *)h)->
 
 int32_t ptmcmc_get_counters(ptmcmc_engine *h, int64_t *prop, int64_t *acc, int64_t *swap_acc, int64_t *swap_proposed)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     const size_t C = (size_t)e->T * e->W;
     const int nj = e->njumps;
@@ -1412,7 +1425,7 @@ int32_t ptmcmc_get_counters(ptmcmc_engine *h, int64_t *prop, int64_t *acc, int64
 
 int32_t ptmcmc_get_trace(ptmcmc_engine *h, uint8_t *trace, int64_t iters, int16_t *swapmaps, int64_t events)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     if (!e->cfg.trace) return fail(e, PTMCMC_ERR_STATE, "engine created without trace");
     const size_t C = (size_t)e->T * e->W;
@@ -1425,7 +1438,7 @@ int32_t ptmcmc_get_trace(ptmcmc_engine *h, uint8_t *trace, int64_t iters, int16_
 
 int32_t ptmcmc_get_timing(ptmcmc_engine *h, ptmcmc_timing *out)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e || !out) return PTMCMC_ERR_ARG;
     *out = e->tm;
     return 0;
@@ -1433,7 +1446,7 @@ int32_t ptmcmc_get_timing(ptmcmc_engine *h, ptmcmc_timing *out)
 
 int32_t ptmcmc_reset_timing(ptmcmc_engine *h)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     e->tm = ptmcmc_timing{};
     return 0;
@@ -1443,7 +1456,7 @@ void *ptmcmc_stream(ptmcmc_engine *h) { return h ? (void *)((Engine *)h)->stream
 
 int32_t ptmcmc_set_timing(ptmcmc_engine *h, int32_t on)
 {
-    Engine *e = (Engine *)h;
+    Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     e->cfg.timing = on ? 1 : 0;

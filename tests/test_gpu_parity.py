@@ -227,3 +227,25 @@ def test_engine_reproduces_reference_trajectory(name):
     assert np.array_equal(sw[:, 0], gfx["swap_acc"][-1]) and nsw == int(gfx["swap_proposed"])
     cov, mu, m2, n = g.adapt()
     assert np.allclose(cov, gfx["cov"], rtol=1e-8, atol=1e-12)
+
+
+def test_engines_on_two_devices_in_one_process():
+    """One host thread driving engines on cuda:0 and cuda:1 (every ABI call makes its device current)."""
+    if _cabi.load().ptmcmc_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    d, W, T, niter = 20, 64, 3, 120
+    tgt = gaussian_target(d, 2)
+    lk, lpar, pk, ppar = tgt
+    ladder = orc.temperature_ladder(d, T)
+    x0 = np.random.default_rng(0).uniform(0, 10, (T, W, d))
+    engs = [_cabi.Engine(d, W, T, np.eye(d) * 0.01, ladder, seed=3, cov_update=50, burn=100, tskip=10, thin=5,
+                         logl_params=lpar, logp_params=ppar, record_rows=niter // 5 + 1, device=dev) for dev in (0, 1)]
+    for e in engs:
+        e.set_state(x0)
+    for _ in range(3):          # interleaved calls
+        for e in engs:
+            e.run(niter // 3)
+    a, b = engs[0].state(), engs[1].state()
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+    assert np.array_equal(engs[0].chain()[0], engs[1].chain()[0])
