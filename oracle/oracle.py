@@ -88,6 +88,8 @@ def lib():
         L.orc_swap_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_swap_finish.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_maintain.argtypes = [C.c_void_p]
+        L.orc_adapt_begin.argtypes = [C.c_void_p, dp]
+        L.orc_adapt_finish.argtypes = [C.c_void_p, dp]
         L.orc_am_ring.restype = C.c_void_p
         L.orc_am_ring.argtypes = [C.c_void_p]
         L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -323,6 +325,15 @@ class Oracle(object):
         rc = lib().orc_swap_finish(self._h, below_ptr or None)
         if rc:
             raise ValueError("oracle swap_finish failed rc=%d" % rc)
+
+    def adapt_begin(self):
+        batch = np.zeros(1 + self.d + self.d * self.d)
+        return batch if lib().orc_adapt_begin(self._h, _dp(batch)) == 1 else None
+
+    def adapt_finish(self, batch):
+        batch = np.ascontiguousarray(batch, dtype=np.float64)
+        if lib().orc_adapt_finish(self._h, _dp(batch)):
+            raise ValueError("oracle adapt_finish: no covariance update is due")
 
     def maintain(self):
         rc = lib().orc_maintain(self._h)

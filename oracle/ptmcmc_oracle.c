@@ -747,6 +747,54 @@ static int maintenance(orc_sampler *s, int64_t it0)
 
 int orc_maintain(orc_sampler *s) { return s->pending_swap ? -4 : maintenance(s, s->iter + 1); }
 
+/* Walker sharding: the covariance update split around an exchange of batch moments, the multi-process
+ * form of rank 0's send(cov) (ref :545-560).  begin: batch = {n, mean[d], M2c[d*d]} of this shard's AM
+ * ring if an update is due at the current iteration (returns 1, else 0); finish: Chan-merge a (pooled)
+ * batch into the running moments, refresh cov and the factor. */
+int orc_adapt_begin(orc_sampler *s, double *batch)
+{
+    int d = s->d, W = s->W;
+    int64_t b = s->iter, cu = s->c.cov_update;
+    if (b == 0 || b % cu != 0 || s->adapt_done == b) return 0;
+    double n = (double)cu * W;
+    double *mean = batch + 1, *m2 = batch + 1 + d;
+    memset(batch, 0, sizeof(double) * (size_t)(1 + d + d * d));
+    for (int64_t i = 0; i < cu * W; ++i)
+        for (int k = 0; k < d; ++k) mean[k] += s->am[(size_t)i * d + k];
+    for (int k = 0; k < d; ++k) mean[k] /= n;
+    for (int64_t i = 0; i < cu * W; ++i) {
+        const double *row = s->am + (size_t)i * d;
+        for (int a = 0; a < d; ++a)
+            for (int c = 0; c < d; ++c) m2[a * d + c] += (row[a] - mean[a]) * (row[c] - mean[c]);
+    }
+    batch[0] = n;
+    return 1;
+}
+
+int orc_adapt_finish(orc_sampler *s, const double *batch)
+{
+    int d = s->d;
+    int64_t b = s->iter, cu = s->c.cov_update;
+    if (b == 0 || b % cu != 0 || s->adapt_done == b) return -4;
+    double na = (b - cu == 0) ? 0.0 : (double)s->nsamp, nb = batch[0], ntot = na + nb;
+    const double *mb = batch + 1, *m2b = batch + 1 + d;
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) {
+            double mai = na > 0 ? s->mu[i] : 0.0, maj = na > 0 ? s->mu[j] : 0.0;
+            double m2a = na > 0 ? s->m2[i * d + j] : 0.0;
+            s->m2[i * d + j] = m2a + m2b[i * d + j] + (mb[i] - mai) * (mb[j] - maj) * (na * nb / ntot);
+        }
+    for (int k = 0; k < d; ++k) {
+        double ma = na > 0 ? s->mu[k] : 0.0;
+        s->mu[k] = ma + (mb[k] - ma) * (nb / ntot);
+    }
+    s->nsamp = (int64_t)ntot;
+    for (int i = 0; i < d * d; ++i) s->cov[i] = s->m2[i] / (ntot - 1.0);
+    factor_groups(s);
+    s->adapt_done = b;
+    return 0;
+}
+
 /* ref :495-528 driver loop and :530-629 PTMCMCOneStep */
 int orc_run(orc_sampler *s, int64_t niter)
 {

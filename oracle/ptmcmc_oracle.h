@@ -109,6 +109,9 @@ int orc_swap_finish(orc_sampler *s, const double *below_top);
 double *orc_am_ring(orc_sampler *s);
 /* run the covariance / DE maintenance due at the start of the next iteration now (idempotent) */
 int orc_maintain(orc_sampler *s);
+/* walker sharding: covariance update split around an exchange of batch moments {n, mean[d], M2c[d*d]} */
+int orc_adapt_begin(orc_sampler *s, double *batch);
+int orc_adapt_finish(orc_sampler *s, const double *batch);
 
 /* --- RNG primitives, exported so that the golden harness can feed the very
  *     same draws to the unmodified reference --- */

@@ -92,7 +92,8 @@ def gaussian_target(d, seed, lo=-50.0, hi=60.0):
             orc.uniform_params(lo * np.ones(d), hi * np.ones(d)))
 
 
-@pytest.mark.parametrize("d,W,T", [(20, 64, 4), (5, 33, 3), (8, 128, 1), (12, 7, 5), (32, 16, 2), (3, 1, 1)])
+@pytest.mark.parametrize("d,W,T", [(20, 64, 4), (5, 33, 3), (8, 128, 1), (12, 7, 5), (32, 16, 2), (3, 1, 1), (1, 5, 2),
+                                   (2, 9, 1)])
 def test_register_kernel_matches_oracle(d, W, T):
     niter, tskip = 320, 10
     cov0 = np.diag(0.01 * (1.0 + np.arange(d)))
@@ -102,7 +103,7 @@ def test_register_kernel_matches_oracle(d, W, T):
 
 
 @pytest.mark.parametrize("d,W,T", [(20, 64, 4), (5, 33, 3), (8, 128, 1), (12, 7, 5), (32, 16, 2), (3, 1, 1),
-                                   (24, 300, 2), (48, 40, 3), (100, 24, 2), (128, 9, 2)])
+                                   (24, 300, 2), (48, 40, 3), (100, 24, 2), (128, 9, 2), (1, 5, 2), (2, 9, 1)])
 def test_tensor_core_kernel_matches_oracle(d, W, T):
     """mh_mma_kernel (fp64 DMMA): same draws, same decisions; the quadratic form differs in summation order."""
     niter, tskip = 320, 10

@@ -120,6 +120,50 @@ def test_gloo_neighbour_exchange_matches_unsharded_oracle(Tg, G, tmp_path):
         assert np.array_equal(a["U"], full.factor()[0]) and np.array_equal(a["de"], full.buffers()[1])
 
 
+def _gloo_walker_worker(rank, world, port, N, out):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        d, Wtot, T = 5, 8, 3
+        kw, ladder, x0 = problem(d, Wtot, T)
+        W = Wtot // world
+        o = orc.Oracle(d, W, T, 0.01 * np.eye(d), ladder=ladder, max_rows=N // kw["thin"] + 1, walker_offset=rank * W, **kw)
+        o.set_trace(N, N // kw["tskip"])
+        o.set_state(x0[:, rank * W:(rank + 1) * W])
+        dist_mod.run(o, 70, None)
+        dist_mod.run(o, N - 70, None)
+        np.savez(out % rank, x=o.state()[0], trace=o.trace, cov=o.adapt()[0], n=o.adapt()[3])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_walker_sharding_pools_the_covariance(tmp_path):
+    """Walker sharding (bench.py's N > 1 path): two ranks with half the walkers each and an all-gather of
+    the batch moments at every covariance boundary reproduce the single-process run.  The pooled moments
+    are merged (Chan) instead of accumulated sample by sample, so covariances agree to rounding.  The run
+    stops at `burn`: from then on DE draws from the shard-local history, which by design differs from the
+    single-process pooled history."""
+    import torch.multiprocessing as mp
+
+    d, Wtot, T, N = 5, 8, 3, 100
+    kw, ladder, x0 = problem(d, Wtot, T)
+    full = orc.Oracle(d, Wtot, T, 0.01 * np.eye(d), ladder=ladder, max_rows=N // kw["thin"] + 1, **kw)
+    full.set_trace(N, N // kw["tskip"])
+    full.set_state(x0)
+    full.run(N)
+    out = str(tmp_path / "w%d.npz")
+    mp.spawn(_gloo_walker_worker, args=(2, _free_port(), N, out), nprocs=2, join=True)
+    r = [np.load(out % g) for g in range(2)]
+    assert r[0]["n"] == r[1]["n"] == full.adapt()[3]
+    assert np.allclose(r[0]["cov"], full.adapt()[0], rtol=1e-9, atol=1e-12) and np.array_equal(r[0]["cov"], r[1]["cov"])
+    tr = np.concatenate([a["trace"] for a in r], axis=2)
+    assert np.array_equal(tr, full.trace)
+    assert np.allclose(np.concatenate([a["x"] for a in r], axis=1), full.state()[0], rtol=1e-9, atol=1e-9)
+
+
 def test_merge_batches_is_chan_merge():
     rng = np.random.default_rng(1)
     d = 4
