@@ -127,6 +127,9 @@ class LadderComm(object):
             self.up_out, self.below_in, self.carry_in, self.carry_out = (
                 torch.zeros(n, dtype=torch.float64, device=self.device) for _ in range(4))
         self.maint_done = -1
+        self.am_sent = -1      # last iteration whose AM-ring slot has been broadcast from the cold shard
+        self.am_works = []     # broadcasts in flight
+        self._ring = None
 
     def _on_stream(self):
         import contextlib
@@ -179,6 +182,29 @@ def ladder_swap(engine, comm):
         engine.swap_finish(None if comm.coldest else comm.below_in.data_ptr())
 
 
+def ladder_am_progress(engine, comm, flush=False):
+    """Broadcast the AM-ring slots the cold shard has filled since the last call (asynchronously, so the
+    transfer overlaps the following MH segments instead of costing 1.3 GB at once before the DE update)."""
+    if comm.world == 1:
+        return
+    it, cu = engine.iteration, engine.cov_update
+    lo = max(comm.am_sent + 1, it - cu + 1, 0)
+    if it < lo or (not flush and it - lo + 1 < max(1, cu // 10)):
+        return
+    if comm._ring is None:
+        ptr, n = engine.am_ring()
+        comm._ring = (comm.alias(ptr, n), n // cu)
+    ring, per = comm._ring
+    with comm._on_stream():
+        while lo <= it:
+            s0 = lo % cu
+            run = min(it - lo + 1, cu - s0)
+            comm.am_works.append(comm.dist.broadcast(ring[s0 * per:(s0 + run) * per], comm._peer(0), group=comm.group,
+                                                     async_op=True))
+            lo += run
+    comm.am_sent = it
+
+
 def ladder_maintenance(engine, comm):
     """Covariance / DE maintenance due at the start of the next iteration, with the cold shard's
     AM ring broadcast before a DE update and its eigen-factor after a covariance update."""
@@ -191,8 +217,10 @@ def ladder_maintenance(engine, comm):
     torch = comm.torch
     with comm._on_stream():
         if due_de and comm.world > 1:
-            ptr, n = engine.am_ring()
-            comm.bcast(comm.alias(ptr, n))
+            ladder_am_progress(engine, comm, flush=True)
+            for w in comm.am_works:
+                w.wait()
+            comm.am_works = []
         engine.maintain()
         if due_cov and comm.world > 1:
             if comm.coldest:
@@ -218,6 +246,7 @@ def run_ladder(engine, niter, comm, tskip):
         done += step
         if engine.swap_pending:
             ladder_swap(engine, comm)
+        ladder_am_progress(engine, comm)
     return done
 
 
