@@ -371,7 +371,9 @@ bool use_mma(const Engine *e)
 {
     if (!e->mma_ok) return false;
     if (e->mh_variant == 3) return true;
-    return e->mh_variant == 0 && e->d > MAX_REG_DIM;  // larger ndim: the alternative is the local-memory kernel
+    // measured on B200 (8192 x 16 chains): ndim 24: sorted 3.9e9 vs tensor-core 3.1e9; ndim 32: 1.9e9 vs 2.2e9;
+    // beyond 32 the alternative is the local-memory kernel
+    return e->mh_variant == 0 && e->d > 24;
 }
 
 cudaError_t launch_mh(Engine *e, long long it0, long long it1, bool tail)
