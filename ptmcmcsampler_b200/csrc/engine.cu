@@ -395,7 +395,7 @@ cudaError_t launch_mh(Engine *e, long long it0, long long it1, bool tail)
     }
     if (fast_reg_path(e) && e->mh_variant == 4 && e->d > 16 && e->d <= 20) return launch_pipe_npw<20>(e, p);
     if (fast_reg_path(e) && e->mh_variant == 5 && e->d > 16 && e->d <= 20) return launch_shadow<20>(e, p);
-    if (fast_reg_path(e) && (e->mh_variant == 0 || e->mh_variant == 4 || e->mh_variant == 5)) {
+    if (fast_reg_path(e) && (e->mh_variant == 0 || e->mh_variant >= 4)) {  // 6: the sorted kernel for any ndim <= 32
         const int d = e->d;
         if (d <= 4) return launch_sorted<4>(e, p);
         if (d <= 8) return launch_sorted<8>(e, p);

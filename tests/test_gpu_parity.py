@@ -144,6 +144,15 @@ def test_tensor_core_kernel_truncated_box_and_outside_start():
     compare(o, g, x0, niter, 10, T)
 
 
+def test_sorted_kernel_widest_instance_matches_oracle():
+    """ndim in (24, 32] defaults to the tensor-core kernel; variant 6 keeps the sorted kernel's DP=32 instance covered."""
+    d, W, T, niter = 30, 40, 2, 200
+    o, g = make_pair(d, W, T, np.diag(0.01 * (1.0 + np.arange(d))), seed=41, target=gaussian_target(d, d), niter=niter,
+                     variant=6)
+    x0 = np.random.default_rng(d).uniform(0, 10, (T, W, d))
+    compare(o, g, x0, niter, 10, T)
+
+
 def test_truncated_box_and_outside_start():
     """Box prior tighter than the likelihood (ref examples/simple.py), with walkers that start
     outside the prior: lnprob0 = -inf, first in-prior proposal always accepted (ref :481-483)."""
