@@ -116,3 +116,30 @@ def test_shift_array_semantics():
     assert np.all(PTMCMCSampler.shift_array(a, -2)[4:] == 0)
     assert np.array_equal(PTMCMCSampler.shift_array(a, 2)[2:], a[:4])
     assert np.array_equal(PTMCMCSampler.shift_array(a, 0), a)
+
+
+def test_bench_accounting_and_clock_parsing(tmp_path):
+    """bench.py's roofline inputs are SURVEY section 8d's figures; the clock sampler keeps the samples
+    stamped inside the timed window and reports throttle reasons."""
+    import datetime
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert abs(bench.algorithmic_bytes_per_chain_step() - 513.2667) < 1e-3          # C2: 513 B
+    assert abs(bench.algorithmic_flops_per_chain_step() - (860 + 40 + 800 / 3 + 80 / 3 + 30)) < 1e-9
+    mu, cov, ladder = bench.problem()
+    assert cov.shape == (20, 20) and np.all(np.linalg.eigvalsh(cov) > 0) and len(ladder) == 32
+    cs = bench.ClockSampler(0)
+    cs.proc = type("P", (), {"terminate": lambda s: None, "wait": lambda s, timeout=None: 0, "kill": lambda s: None})()
+    cs.path = str(tmp_path / "clk.csv")
+    t0 = datetime.datetime(2026, 1, 1, 12, 0, 0)
+    rows = [(t0 + datetime.timedelta(milliseconds=50 * i), 1965 if i != 5 else 1200) for i in range(20)]
+    with open(cs.path, "w") as fh:
+        for ts, mhz in rows:
+            fh.write("%s, %d, 1965, 700.0, 0x0, Not Active, Not Active, Not Active, %s\n"
+                     % (ts.strftime("%Y/%m/%d %H:%M:%S.%f")[:-3], mhz, "Active" if mhz == 1200 else "Not Active"))
+    out = cs.stop(rows[4][0].timestamp(), rows[9][0].timestamp())
+    assert out["window"] == "timed region" and 6 <= out["samples"] <= 8
+    assert out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
