@@ -49,6 +49,15 @@ def fixture_cycle(g):
     return tuple(cyc)
 
 
+def fixture_mh_temp(g):
+    """MH temperatures: the ladder, with 1e80 on the last rung when the run used hotChain (ref :281-282)."""
+    if "kw_hotChain" in g and bool(g["kw_hotChain"]) and int(g["T"]) > 1:
+        mh = np.array(g["ladder"], dtype=float)
+        mh[-1] = 1e80
+        return mh
+    return None
+
+
 def oracle_from_fixture(g, inject=True, thin=1, **over):
     d, T, N = int(g["d"]), int(g["T"]), int(g["N"])
     lk, lpar, pk, ppar = fixture_target(g)
@@ -56,7 +65,8 @@ def oracle_from_fixture(g, inject=True, thin=1, **over):
     if int(g["ext"]):
         fn = golden_ext_jump_factory(g["pb_lo"], g["pb_hi"])
         ext = lambda k, x, it, beta, w, t: fn(x, it, beta)  # noqa: E731
-    kw = dict(seed=int(g["seed"]), ladder=g["ladder"], groups=fixture_groups(g), cycle=fixture_cycle(g),
+    kw = dict(seed=int(g["seed"]), ladder=g["ladder"], mh_temp=fixture_mh_temp(g), groups=fixture_groups(g),
+              cycle=fixture_cycle(g),
               de_weight=int(g["kw_DEweight"]), cov_update=int(g["kw_covUpdate"]), burn=int(g["kw_burn"]),
               tskip=int(g["kw_Tskip"]), thin=thin, logl_kind=lk, logl_params=lpar, logp_kind=pk,
               logp_params=ppar, record_hot=True, max_rows=N // thin + 1, ext_jump=ext)

@@ -103,6 +103,11 @@ def main():
     traj_case("traj_t3_curved_ext_d4", 4, 3, 400, 4242, kw3, curved=True, ext=True)
     kw4 = dict(burn=100, thin=10, covUpdate=100, SCAMweight=20, AMweight=20, DEweight=20, isave=1000, Tskip=100)
     traj_case("traj_t1_d20", 20, 1, 350, 7, kw4, pmin=0.0, pmax=10.0)
+    # hotChain=True with an explicit Tmax: the last rung samples at temp = 1e80 (ref :281-282) but swaps with
+    # ladder[-1] (ref :658, :673-676); the ladder comes from Tmax (ref :709-718)
+    kw5 = dict(burn=100, thin=2, covUpdate=50, SCAMweight=20, AMweight=20, DEweight=30, isave=1000, Tskip=5,
+               Tmax=20.0, hotChain=True)
+    traj_case("traj_t3_hot_tmax_d4", 4, 3, 300, 31, kw5, pmin=0.0, pmax=10.0)
     if "--traj-only" in sys.argv:  # the statistical bands do not depend on the oracle's draw functions
         return
     # statistical bands (reference's own PCG64 stream)

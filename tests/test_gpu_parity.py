@@ -12,7 +12,7 @@ import pytest
 from oracle import oracle as orc
 from ptmcmcsampler_b200 import _cabi
 
-from _helpers import fixture_cycle, fixture_groups, fixture_target, load
+from _helpers import fixture_cycle, fixture_groups, fixture_mh_temp, fixture_target, load
 
 pytestmark = pytest.mark.gpu
 FTOL = 1e-9
@@ -202,14 +202,15 @@ def test_hot_chain_temperature_override():
     compare(o, g, x0, niter, 10, T)
 
 
-@pytest.mark.parametrize("name", ["traj_t1_d5", "traj_t4_groups_d6", "traj_t1_d20"])
+@pytest.mark.parametrize("name", ["traj_t1_d5", "traj_t4_groups_d6", "traj_t1_d20", "traj_t3_hot_tmax_d4"])
 def test_engine_reproduces_reference_trajectory(name):
     """W=1: the engine fed the reference's own eigen-factors walks the reference's trajectory."""
     gfx = load(name)
     d, T, N = int(gfx["d"]), int(gfx["T"]), int(gfx["N"])
     cu, burn, tskip = int(gfx["kw_covUpdate"]), int(gfx["kw_burn"]), int(gfx["kw_Tskip"])
     lk, lpar, pk, ppar = fixture_target(gfx)
-    g = _cabi.Engine(d, 1, T, gfx["cov0"], gfx["ladder"], seed=int(gfx["seed"]), groups=fixture_groups(gfx),
+    g = _cabi.Engine(d, 1, T, gfx["cov0"], gfx["ladder"], mh_temp=fixture_mh_temp(gfx), seed=int(gfx["seed"]),
+                     groups=fixture_groups(gfx),
                      cycle=fixture_cycle(gfx), de_weight=int(gfx["kw_DEweight"]), cov_update=cu, burn=burn,
                      tskip=tskip, thin=1, logl_kind=lk, logl_params=lpar, logp_kind=pk, logp_params=ppar,
                      record_hot=True, record_rows=N + 1, trace_iters=N)
