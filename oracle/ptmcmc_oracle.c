@@ -183,52 +183,72 @@ void orc_sym_factor(int n, const double *a_in, double *U, double *S)
     memcpy(a, a_in, sizeof(double) * n * n);
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) v[i * n + j] = (i == j) ? 1.0 : 0.0;
+    /* parallel (round-robin) ordering, the same phases and fused operations as the CUDA jacobi_block:
+     * a sweep is m-1 rounds of the circle tournament; the pairs of a round are disjoint, so the column phase
+     * (A J, V J) and the row phase (J^T A) touch every entry once and the execution order is irrelevant */
+    int m = (n + 1) & ~1, npair = m >> 1;
+    int *pp = (int *)malloc(sizeof(int) * npair), *qq = (int *)malloc(sizeof(int) * npair);
+    int *rot = (int *)malloc(sizeof(int) * npair);
+    double *sns = (double *)malloc(sizeof(double) * npair), *taus = (double *)malloc(sizeof(double) * npair);
     for (int sweep = 0; sweep < 60; ++sweep) {
         double off = 0.0;
         for (int p = 0; p < n; ++p)
             for (int q = p + 1; q < n; ++q) off += fabs(a[p * n + q]);
         if (off == 0.0) break;
-        for (int p = 0; p < n - 1; ++p) {
-            for (int q = p + 1; q < n; ++q) {
-                double apq = a[p * n + q];
-                double app = a[p * n + p], aqq = a[q * n + q];
+        for (int step = 0; step < m - 1; ++step) {
+            for (int k = 0; k < npair; ++k) {
+                int i = (k == 0) ? m - 1 : (step + k) % (m - 1);
+                int j = (k == 0) ? step : (step + m - 1 - k) % (m - 1);
+                int p = i < j ? i : j, q = i < j ? j : i;
+                pp[k] = p; qq[k] = q; rot[k] = 0; sns[k] = 0.0; taus[k] = 0.0;
+                if (q >= n) continue;
+                double apq = a[p * n + q], app = a[p * n + p], aqq = a[q * n + q];
                 double g = 100.0 * fabs(apq);
                 if (sweep > 3 && fabs(app) + g == fabs(app) && fabs(aqq) + g == fabs(aqq)) {
-                    a[p * n + q] = 0.0;
-                    a[q * n + p] = 0.0;
-                    continue;
-                }
-                if (apq == 0.0) continue;
-                double h = aqq - app, t;
-                if (fabs(h) + g == fabs(h)) {
-                    t = apq / h;
-                } else {
-                    double theta = 0.5 * h / apq;
-                    t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
-                    if (theta < 0.0) t = -t;
-                }
-                double c = 1.0 / sqrt(1.0 + t * t);
-                double sn = t * c;
-                double tau = sn / (1.0 + c);
-                a[p * n + p] = app - t * apq;
-                a[q * n + q] = aqq + t * apq;
-                a[p * n + q] = 0.0;
-                a[q * n + p] = 0.0;
-                for (int r = 0; r < n; ++r) {
-                    if (r != p && r != q) {
-                        double arp = a[r * n + p], arq = a[r * n + q];
-                        double nrp = arp - sn * (arq + tau * arp);
-                        double nrq = arq + sn * (arp - tau * arq);
-                        a[r * n + p] = nrp; a[p * n + r] = nrp;
-                        a[r * n + q] = nrq; a[q * n + r] = nrq;
+                    rot[k] = 2;
+                } else if (apq != 0.0) {
+                    double h = aqq - app, t;
+                    if (fabs(h) + g == fabs(h)) {
+                        t = apq / h;
+                    } else {
+                        double theta = 0.5 * h / apq;
+                        t = 1.0 / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                        if (theta < 0.0) t = -t;
                     }
-                    double vrp = v[r * n + p], vrq = v[r * n + q];
-                    v[r * n + p] = vrp - sn * (vrq + tau * vrp);
-                    v[r * n + q] = vrq + sn * (vrp - tau * vrq);
+                    double c = 1.0 / sqrt(fma(t, t, 1.0));
+                    sns[k] = t * c;
+                    taus[k] = sns[k] / (1.0 + c);
+                    rot[k] = 1;
                 }
             }
+            for (int k = 0; k < npair; ++k) { /* column phase */
+                if (rot[k] != 1) continue;
+                int p = pp[k], q = qq[k];
+                double sn = sns[k], tau = taus[k];
+                for (int r = 0; r < n; ++r) {
+                    double g = a[r * n + p], h = a[r * n + q];
+                    a[r * n + p] = fma(-sn, fma(g, tau, h), g);
+                    a[r * n + q] = fma(sn, fma(-h, tau, g), h);
+                    g = v[r * n + p]; h = v[r * n + q];
+                    v[r * n + p] = fma(-sn, fma(g, tau, h), g);
+                    v[r * n + q] = fma(sn, fma(-h, tau, g), h);
+                }
+            }
+            for (int k = 0; k < npair; ++k) { /* row phase */
+                if (rot[k] != 1) continue;
+                int p = pp[k], q = qq[k];
+                double sn = sns[k], tau = taus[k];
+                for (int c = 0; c < n; ++c) {
+                    double g = a[p * n + c], h = a[q * n + c];
+                    a[p * n + c] = fma(-sn, fma(g, tau, h), g);
+                    a[q * n + c] = fma(sn, fma(-h, tau, g), h);
+                }
+            }
+            for (int k = 0; k < npair; ++k)
+                if (rot[k] != 0) { a[pp[k] * n + qq[k]] = 0.0; a[qq[k] * n + pp[k]] = 0.0; }
         }
     }
+    free(pp); free(qq); free(rot); free(sns); free(taus);
     /* order by descending |lambda|, ties by original index (stable selection) */
     int *ord = (int *)malloc(sizeof(int) * n);
     for (int i = 0; i < n; ++i) ord[i] = i;

@@ -124,67 +124,94 @@ __global__ void moments_gram_batch_kernel(const double *G, int KP, int d, const 
     if (idx == 0) batch[0] = n;
 }
 
-// Cyclic Jacobi eigen-decomposition of the n x n symmetric matrix a (destroyed); v receives the
-// eigenvectors.  One thread block; rotations are applied by n threads in parallel, in the same
-// (p, q) order and with the same formulas as the CPU oracle's orc_sym_factor.
+// Jacobi eigen-decomposition of the n x n symmetric matrix a (destroyed); v receives the eigenvectors.
+// Parallel (round-robin) ordering: a sweep is m-1 steps (m = n rounded up to even), step s rotating the m/2
+// disjoint index pairs of round s of the circle tournament at once -- the rotation of a pair depends only on
+// its own 2x2 block, which the other rotations of the step do not touch.  A step is  A <- J^T A J  done as a
+// column phase (A J and V J) and a row phase (J^T A), each entry touched by exactly one rotation per phase, so
+// the result does not depend on the order in which a phase is executed: the CPU oracle (orc_sym_factor) runs
+// the same phases sequentially with the same explicitly fused operations and gets the same bits.
+constexpr int JAC_THREADS = 256;
+constexpr int JAC_MAXPAIRS = 64;  // n <= 128
+
 __device__ inline void jacobi_block(int n, double *a, double *v, double *scratch)
 {
-    const int r = threadIdx.x;
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) v[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
+    __shared__ int s_p[JAC_MAXPAIRS], s_q[JAC_MAXPAIRS];
+    __shared__ double s_s[JAC_MAXPAIRS], s_tau[JAC_MAXPAIRS];
+    __shared__ int s_rot[JAC_MAXPAIRS];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int m = (n + 1) & ~1, npair = m >> 1;
+    for (int idx = tid; idx < n * n; idx += nth) v[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
     __syncthreads();
     for (int sweep = 0; sweep < 60; ++sweep) {
-        if (threadIdx.x == 0) {
-            double off = 0.0;
-            for (int p = 0; p < n; ++p)
-                for (int q = p + 1; q < n; ++q) off += fabs(a[p * n + q]);
-            scratch[0] = off;
-        }
-        __syncthreads();
-        if (scratch[0] == 0.0) break;
-        __syncthreads();
-        for (int p = 0; p < n - 1; ++p) {
-            for (int q = p + 1; q < n; ++q) {
-                const double apq = a[p * n + q], app = a[p * n + p], aqq = a[q * n + q];
-                const double g = 100.0 * fabs(apq);
-                __syncthreads();  // everyone has read the pivot entries
-                if (sweep > 3 && fabs(app) + g == fabs(app) && fabs(aqq) + g == fabs(aqq)) {
-                    if (threadIdx.x == 0) { a[p * n + q] = 0.0; a[q * n + p] = 0.0; }
-                    __syncthreads();
-                    continue;
-                }
-                if (apq == 0.0) continue;
-                const double h = aqq - app;
-                double t;
-                if (fabs(h) + g == fabs(h)) {
-                    t = apq / h;
-                } else {
-                    const double theta = 0.5 * h / apq;
-                    t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
-                    if (theta < 0.0) t = -t;
-                }
-                const double c = 1.0 / sqrt(1.0 + t * t);
-                const double sn = t * c;
-                const double tau = sn / (1.0 + c);
-                if (r < n) {
-                    if (r != p && r != q) {
-                        const double arp = a[r * n + p], arq = a[r * n + q];
-                        const double nrp = arp - sn * (arq + tau * arp);
-                        const double nrq = arq + sn * (arp - tau * arq);
-                        a[r * n + p] = nrp; a[p * n + r] = nrp;
-                        a[r * n + q] = nrq; a[q * n + r] = nrq;
+        // converged when every off-diagonal element is exactly zero (the oracle tests sum |a_pq| == 0)
+        int nonzero = 0;
+        for (int idx = tid; idx < n * n; idx += nth)
+            if (idx / n < idx % n && a[idx] != 0.0) nonzero = 1;
+        if (!__syncthreads_or(nonzero)) break;
+        for (int step = 0; step < m - 1; ++step) {
+            // ---- rotation of every pair of this round, from its own 2x2 block
+            if (tid < npair) {
+                const int k = tid;
+                const int i = (k == 0) ? m - 1 : (step + k) % (m - 1);
+                const int j = (k == 0) ? step : (step + m - 1 - k) % (m - 1);
+                const int p = i < j ? i : j, q = i < j ? j : i;
+                int rot = 0;
+                double sn = 0.0, tau = 0.0;
+                if (q < n) {
+                    const double apq = a[p * n + q], app = a[p * n + p], aqq = a[q * n + q];
+                    const double g = 100.0 * fabs(apq);
+                    if (sweep > 3 && fabs(app) + g == fabs(app) && fabs(aqq) + g == fabs(aqq)) {
+                        rot = 2;  // negligible: just clear it
+                    } else if (apq != 0.0) {
+                        const double h = aqq - app;
+                        double t;
+                        if (fabs(h) + g == fabs(h)) {
+                            t = apq / h;
+                        } else {
+                            const double theta = 0.5 * h / apq;
+                            t = 1.0 / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                            if (theta < 0.0) t = -t;
+                        }
+                        const double c = 1.0 / sqrt(fma(t, t, 1.0));
+                        sn = t * c;
+                        tau = sn / (1.0 + c);
+                        rot = 1;
                     }
-                    const double vrp = v[r * n + p], vrq = v[r * n + q];
-                    v[r * n + p] = vrp - sn * (vrq + tau * vrp);
-                    v[r * n + q] = vrq + sn * (vrp - tau * vrq);
                 }
-                if (threadIdx.x == 0) {
-                    a[p * n + p] = app - t * apq;
-                    a[q * n + q] = aqq + t * apq;
-                    a[p * n + q] = 0.0;
-                    a[q * n + p] = 0.0;
-                }
-                __syncthreads();
+                s_p[k] = p; s_q[k] = q; s_s[k] = sn; s_tau[k] = tau; s_rot[k] = rot;
             }
+            __syncthreads();
+            // ---- column phase: A <- A J, V <- V J
+            for (int idx = tid; idx < n * npair; idx += nth) {
+                const int k = idx % npair, r = idx / npair;
+                if (s_rot[k] != 1) continue;
+                const int p = s_p[k], q = s_q[k];
+                const double sn = s_s[k], tau = s_tau[k];
+                double g = a[r * n + p], h = a[r * n + q];
+                a[r * n + p] = fma(-sn, fma(g, tau, h), g);
+                a[r * n + q] = fma(sn, fma(-h, tau, g), h);
+                g = v[r * n + p]; h = v[r * n + q];
+                v[r * n + p] = fma(-sn, fma(g, tau, h), g);
+                v[r * n + q] = fma(sn, fma(-h, tau, g), h);
+            }
+            __syncthreads();
+            // ---- row phase: A <- J^T A, then the rotated pair's off-diagonal is zero by construction
+            for (int idx = tid; idx < n * npair; idx += nth) {
+                const int k = idx % npair, c = idx / npair;
+                if (s_rot[k] != 1) continue;
+                const int p = s_p[k], q = s_q[k];
+                const double sn = s_s[k], tau = s_tau[k];
+                const double g = a[p * n + c], h = a[q * n + c];
+                a[p * n + c] = fma(-sn, fma(g, tau, h), g);
+                a[q * n + c] = fma(sn, fma(-h, tau, g), h);
+            }
+            __syncthreads();
+            if (tid < npair && s_rot[tid] != 0) {
+                a[s_p[tid] * n + s_q[tid]] = 0.0;
+                a[s_q[tid] * n + s_p[tid]] = 0.0;
+            }
+            __syncthreads();
         }
     }
     __syncthreads();
@@ -198,14 +225,15 @@ struct FactorArgs {
     double n_prev;              // samples already in (mu, m2)
     int reset;                  // it == 0 in ref :781-783: forget the running state first
     double *U, *S, *sqrtS;      // outputs, concatenated per group
-    double *work_a, *work_v;    // [dmax*dmax] scratch each
+    double *work_a, *work_v;    // [dmax*dmax] scratch each (global; used when a block does not fit shared memory)
+    int smem_doubles;           // dynamic shared memory of the launch, in doubles
     int *ord;                   // [dmax] scratch
 };
 
 // One block: merge the batch into the running moments (ref :785-794), then factor every group
 // (ref :797-803): eigenvalues by descending magnitude (ties keep index order), S = |lambda|, each
 // eigenvector's largest-magnitude component made positive.
-__global__ void __launch_bounds__(128) adapt_finalize_kernel(const FactorArgs f)
+__global__ void __launch_bounds__(JAC_THREADS) adapt_finalize_kernel(const FactorArgs f)
 {
     __shared__ double scratch[2];
     const int d = f.d;
@@ -233,7 +261,11 @@ __global__ void __launch_bounds__(128) adapt_finalize_kernel(const FactorArgs f)
     for (int g = 0; g < f.ngroups; ++g) {
         const int g0 = f.goff[g], n = f.goff[g + 1] - g0;
         const int *gi = f.gidx + g0;
-        double *a = f.work_a, *v = f.work_v;
+        // the block and its eigenvectors live in shared memory when they fit (n <= 119): the rotation phases are
+        // latency bound, and an L2 round trip per element made the d=100 factorisation 18.7 ms
+        extern __shared__ double jac_smem[];
+        const bool in_smem = 2 * n * n <= f.smem_doubles;
+        double *a = in_smem ? jac_smem : f.work_a, *v = in_smem ? jac_smem + n * n : f.work_v;
         for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x)
             a[idx] = f.cov[gi[idx / n] * d + gi[idx % n]];
         __syncthreads();

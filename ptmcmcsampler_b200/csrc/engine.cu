@@ -93,7 +93,7 @@ struct Engine {
     int *d_map = nullptr;
     double *d_part2 = nullptr, *d_batch = nullptr, *d_gram = nullptr;
     double *d_stage = nullptr;  // [T][W][d] staging in the host layout
-    int mom_blocks = 0, gram_kp = 0;
+    int mom_blocks = 0, gram_kp = 0, jac_smem_doubles = 0;
     // host-callback path staging
     double *d_q = nullptr, *d_qxy = nullptr, *d_lnl_new = nullptr, *d_lp_new = nullptr;
     int *d_jump = nullptr;
@@ -444,7 +444,8 @@ cudaError_t launch_factor(Engine *e, const double *batch, double n_prev, int res
     f.batch = batch; f.n_prev = n_prev; f.reset = reset;
     f.U = e->d_U; f.S = e->d_S; f.sqrtS = e->d_sqrtS;
     f.work_a = e->d_work_a; f.work_v = e->d_work_v; f.ord = e->d_ord;
-    adapt_finalize_kernel<<<1, 128, 0, e->stream>>>(f);
+    f.smem_doubles = e->jac_smem_doubles;
+    adapt_finalize_kernel<<<1, JAC_THREADS, sizeof(double) * e->jac_smem_doubles, e->stream>>>(f);
     cudaError_t st = cudaGetLastError();
     return st != cudaSuccess ? st : build_u_frags(e);
 }
@@ -462,6 +463,8 @@ cudaError_t launch_batch_moments(Engine *e)
         moments_gram_kernel<1><<<e->mom_blocks, GRAM_THREADS, smem, e->stream>>>(e->d_am, d, W, cu, e->d_mu, KP, e->d_part2);
     else if (KP <= 56)
         moments_gram_kernel<4><<<e->mom_blocks, GRAM_THREADS, smem, e->stream>>>(e->d_am, d, W, cu, e->d_mu, KP, e->d_part2);
+    else if (KP <= 104)
+        moments_gram_kernel<12><<<e->mom_blocks, GRAM_THREADS, smem, e->stream>>>(e->d_am, d, W, cu, e->d_mu, KP, e->d_part2);
     else
         moments_gram_kernel<GRAM_MAXT><<<e->mom_blocks, GRAM_THREADS, smem, e->stream>>>(e->d_am, d, W, cu, e->d_mu, KP,
                                                                                          e->d_part2);
@@ -709,14 +712,31 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         CUDA_TRY(nullptr, dalloc(&e->d_swapmaps, (size_t)cfg->trace_iters * C));
     }
     e->gram_kp = ((d + 1) + 7) / 8 * 8;  // ndim + the column of ones, padded to the 8x8 tile
-    e->mom_blocks = (e->gram_kp <= 56 ? 8 : 2) * e->sm_count;  // small tiles: many blocks per SM hide the staging latency
+    e->mom_blocks = (e->gram_kp <= 56 ? 8 : e->gram_kp <= 104 ? 3 : 2) * e->sm_count;  // small tiles: many blocks per SM hide the staging latency
     CUDA_TRY(nullptr, dalloc(&e->d_part2, (size_t)e->mom_blocks * e->gram_kp * e->gram_kp));
     CUDA_TRY(nullptr, dalloc(&e->d_gram, (size_t)e->gram_kp * e->gram_kp));
     CUDA_TRY(nullptr, dalloc(&e->d_batch, (size_t)1 + d + (size_t)d * d));
     {
         const size_t smem = sizeof(double) * e->gram_kp * GRAM_LDT;
         if (smem > 48 * 1024)
+        {
             CUDA_TRY(nullptr, cudaFuncSetAttribute(moments_gram_kernel<GRAM_MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(nullptr, cudaFuncSetAttribute(moments_gram_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+    }
+    // the factorisation keeps the largest group's block and eigenvectors in shared memory when they fit
+    {
+        const size_t want = sizeof(double) * 2 * (size_t)dmax * dmax;
+        if (want + 4096 <= 227 * 1024) {  // the kernel's static shared memory (rotation tables) comes on top
+            e->jac_smem_doubles = 2 * dmax * dmax;
+            if (want > 48 * 1024) {
+                static size_t jac_attr[64] = {};
+                if (jac_attr[cfg->device & 63] < want) {
+                    CUDA_TRY(nullptr, cudaFuncSetAttribute(adapt_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+                    jac_attr[cfg->device & 63] = want;
+                }
+            }
+        }
     }
     // tensor-core path: dense Gaussian target, one identity group, box or flat prior
     e->mma_nt = mma_pick_nt(d);
