@@ -174,7 +174,7 @@ static double draw_normal(orc_stream *st)
 /* -------------------------------------------------- symmetric factor (U,S) */
 
 /* Stand-in for np.linalg.svd of a symmetric PSD block (ref :145, :560, :803):
- * cyclic Jacobi eigen-decomposition, eigenvalues by descending magnitude,
+ * Jacobi eigen-decomposition in round-robin (parallel) order, eigenvalues by descending magnitude,
  * S = |lambda|, each eigenvector's largest-magnitude component made positive. */
 void orc_sym_factor(int n, const double *a_in, double *U, double *S)
 {

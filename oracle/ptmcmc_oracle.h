@@ -122,7 +122,7 @@ uint64_t orc_word_to_int(uint64_t word, uint64_t n);
 double orc_word_to_unit(uint64_t word);
 void orc_word_to_normals(uint64_t word, double *z0, double *z1);
 
-/* symmetric eigen-factorisation used for U,S (cyclic Jacobi, sorted, sign-fixed) */
+/* symmetric eigen-factorisation used for U,S (round-robin Jacobi, sorted, sign-fixed) */
 void orc_sym_factor(int n, const double *a, double *U, double *S);
 void orc_temperature_ladder(int ndim, int ntemps, double tmin, double tmax, double *ladder);
 
