@@ -1,39 +1,44 @@
-"""Single-process stand-in for ``mpi4py.MPI`` with the surface of the reference's
-``PTMCMCSampler/nompi4py.py``: rank 0 of a world of size 1.
+"""Single-process stand-in for ``mpi4py.MPI``: a world of one rank.
 
-The engine keeps every temperature on the GPU, so no rank-to-rank traffic exists; this module is
-here so that code written against the reference (``comm=nompi4py.COMM_WORLD``,
-ref tests/test_simple.py:100-102) keeps working.
+The engine keeps every temperature on the GPU, so there is no rank-to-rank traffic to carry; this
+module only keeps code written against the reference working (``comm=nompi4py.COMM_WORLD`` as in ref
+tests/test_simple.py:100-102, and the communicator surface listed in SURVEY.md section 2b).
 """
 
 
 class MPIDummy(object):
-    def Get_rank(self):
-        return 0
+    """Communicator of a world with a single member.  Point-to-point calls have no peer and do
+    nothing; collectives return what rank 0 of a one-rank world would receive."""
 
+    rank, size = 0, 1
+
+    # ---- identity
     def Get_size(self):
-        return 1
+        return self.size
+
+    def Get_rank(self):
+        return self.rank
+
+    # ---- collectives over one rank
+    def gather(self, sendobj, root=0, **kw):
+        """Everything gathered from the world: the caller's own contribution."""
+        return [sendobj]
+
+    def scatter(self, sendobj, root=0, **kw):
+        """The slice of ``sendobj`` addressed to rank 0 (``None`` scatters nothing)."""
+        return sendobj[0] if sendobj is not None else None
+
+    def bcast(self, obj, root=0, **kw):
+        return obj
 
     def barrier(self):
         return None
 
-    def send(self, obj, dest=1, tag=55):
+    # ---- point to point: nobody to talk to
+    def _no_peer(self, *args, **kw):
         return None
 
-    def recv(self, source=1, tag=55):
-        return None
-
-    def Iprobe(self, source=1, tag=55):
-        return None
-
-    def scatter(self, sendobj, **kwargs):
-        return None if sendobj is None else sendobj[0]
-
-    def bcast(self, obj, **kwargs):
-        return obj
-
-    def gather(self, sendobj, **kwargs):
-        return [sendobj]
+    send = recv = Iprobe = _no_peer
 
 
 COMM_WORLD = MPIDummy()
