@@ -28,11 +28,13 @@
 extern "C" {
 #endif
 
-#define PTMCMC_ABI_VERSION 2
+#define PTMCMC_ABI_VERSION 3
 
-/* jump ids: the reference's built-in proposals; ids >= PTMCMC_JUMP_EXT0 are
- * host-side (Python) proposals registered with addProposalToCycle (ref :988-1014) */
-enum { PTMCMC_JUMP_SCAM = 0, PTMCMC_JUMP_AM = 1, PTMCMC_JUMP_DE = 2, PTMCMC_JUMP_EXT0 = 3 };
+/* jump ids: the reference's built-in proposals (ref :820-985); PRIOR = a draw from the uniform prior
+ * box, the device-side form of the "UniformJump" plugin of ref tests/test_simple.py:44-62 (needs
+ * PTMCMC_LOGP_UNIFORM); ids >= PTMCMC_JUMP_EXT0 are host-side (Python) proposals registered with
+ * addProposalToCycle (ref :988-1014) */
+enum { PTMCMC_JUMP_SCAM = 0, PTMCMC_JUMP_AM = 1, PTMCMC_JUMP_DE = 2, PTMCMC_JUMP_PRIOR = 3, PTMCMC_JUMP_EXT0 = 4 };
 /* built-in log-likelihoods (ref examples/simple.py:34-36, examples/curved_likelihood.ipynb) */
 enum { PTMCMC_LOGL_EXTERNAL = 0, PTMCMC_LOGL_GAUSSIAN = 1, PTMCMC_LOGL_CURVED = 2, PTMCMC_LOGL_ROSENBROCK = 3 };
 /* built-in log-priors (ref examples/simple.py:38-44) */

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libptmcmc_oracle.so")
 
-JUMP_SCAM, JUMP_AM, JUMP_DE, JUMP_EXT0 = 0, 1, 2, 3
+JUMP_SCAM, JUMP_AM, JUMP_DE, JUMP_PRIOR, JUMP_EXT0 = 0, 1, 2, 3, 4
 LOGL_EXTERNAL, LOGL_GAUSSIAN, LOGL_CURVED, LOGL_ROSENBROCK = 0, 1, 2, 3
 LOGP_EXTERNAL, LOGP_UNIFORM, LOGP_FLAT = 0, 1, 2
 PURPOSE_MH, PURPOSE_SWAP = 0, 1

@@ -668,6 +668,11 @@ static void mh_step(orc_sampler *s, int64_t iter, int w, int t, double *q, doubl
             double sigma = bm[gi[i]] - bn[gi[i]];
             q[gi[i]] += scale * sigma;
         }
+    } else if (jump == ORC_JUMP_PRIOR) {
+        /* draw from the uniform prior box, one stream.random() per parameter (the UniformJump plugin of ref
+         * tests/test_simple.py:44-62 with the sampler's stream); symmetric, qxy = 0 */
+        const double *lo = s->logp_par, *hi = lo + d;
+        for (int k = 0; k < d; ++k) q[k] = lo[k] + (hi[k] - lo[k]) * draw_unit(&st);
     } else {
         s->c.ext_jump(jump - ORC_JUMP_EXT0, x, d, iter, beta, s->c.walker_offset + w,
                       s->c.temp_offset + t, q, &qxy, s->c.user);
@@ -821,7 +826,7 @@ int orc_run(orc_sampler *s, int64_t niter)
     int d = s->d, W = s->W, T = s->T;
     int64_t end = s->iter + niter;
     int nth = s->c.nthreads > 0 ? s->c.nthreads : 1;
-    if (s->c.logl_kind == ORC_LOGL_EXTERNAL || s->c.logp_kind == ORC_LOGP_EXTERNAL || s->njumps > 3) nth = 1;
+    if (s->c.logl_kind == ORC_LOGL_EXTERNAL || s->c.logp_kind == ORC_LOGP_EXTERNAL || s->njumps > ORC_JUMP_EXT0) nth = 1;
     if (s->pending_swap) return -4; /* a sharded swap must be completed first */
     while (s->iter < end) {
         int64_t it0 = s->iter + 1;

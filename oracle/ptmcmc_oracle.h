@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-enum { ORC_JUMP_SCAM = 0, ORC_JUMP_AM = 1, ORC_JUMP_DE = 2, ORC_JUMP_EXT0 = 3 };
+enum { ORC_JUMP_SCAM = 0, ORC_JUMP_AM = 1, ORC_JUMP_DE = 2, ORC_JUMP_PRIOR = 3, ORC_JUMP_EXT0 = 4 };
 enum { ORC_LOGL_EXTERNAL = 0, ORC_LOGL_GAUSSIAN = 1, ORC_LOGL_CURVED = 2, ORC_LOGL_ROSENBROCK = 3 };
 enum { ORC_LOGP_EXTERNAL = 0, ORC_LOGP_UNIFORM = 1, ORC_LOGP_FLAT = 2 };
 enum { ORC_PURPOSE_MH = 0, ORC_PURPOSE_SWAP = 1 };

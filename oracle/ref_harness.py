@@ -233,7 +233,10 @@ def run_reference(ndim, logl, logp, cov0, p0s, niter, seed, ntemps=1, shim=True,
                                     outDir=outdir, verbose=False, seed=seed)
             if shim:
                 sampler.stream = ShimStream(seed, 0, rank)
-            for fn, wgt in ext_jumps:
+            for entry in ext_jumps:
+                fn, wgt = entry[0], entry[1]
+                if getattr(fn, "bind_sampler", False):  # a jump that draws from the sampler's own stream
+                    fn = fn(sampler)
                 sampler.addProposalToCycle(fn, wgt)
             tr = dict(x=[], lnl=[], lnp=[], jump=[], acc=[], U=[], S=[], swap_acc=[])
             orig = sampler.PTMCMCOneStep
@@ -285,8 +288,20 @@ def run_reference(ndim, logl, logp, cov0, p0s, niter, seed, ntemps=1, shim=True,
     s0 = out[0]["sampler"]
     names = {"covarianceJumpProposalSCAM": orc.JUMP_SCAM, "covarianceJumpProposalAM": orc.JUMP_AM,
              "DEJump": orc.JUMP_DE}
-    for k, (fn, _) in enumerate(ext_jumps):
-        names[fn.__name__] = orc.JUMP_EXT0 + k
+    next_ext = orc.JUMP_EXT0
+    for entry in ext_jumps:  # (fn, weight) -> next external id; (fn, weight, jump_id) -> that built-in id
+        if len(entry) > 2:
+            names[getattr(entry[0], "jump_name", entry[0].__name__)] = entry[2]
+        else:
+            names[entry[0].__name__] = next_ext
+            next_ext += 1
+    def _by_id(col):
+        arr = np.zeros((ntemps, max(names.values()) + 1), dtype=np.int64)
+        for nm, jid in names.items():
+            for t in range(ntemps):
+                arr[t, jid] = out[t]["sampler"].jumpDict.get(nm, [0, 0])[col]
+        return arr
+
     res = dict(
         x=np.array([[out[t]["x"][i] for t in range(ntemps)] for i in range(niter)]),
         lnl=np.array([[out[t]["lnl"][i] for t in range(ntemps)] for i in range(niter)]),
@@ -301,10 +316,7 @@ def run_reference(ndim, logl, logp, cov0, p0s, niter, seed, ntemps=1, shim=True,
         ladder=np.array(s0.ladder, dtype=float),
         naccepted=np.array([out[t]["sampler"].naccepted for t in range(ntemps)]),
         swap_proposed=np.array(s0.swapProposed),
-        jump_prop=np.array([[out[t]["sampler"].jumpDict.get(n, [0, 0])[0] for n in sorted(names, key=names.get)]
-                            for t in range(ntemps)]),
-        jump_acc=np.array([[out[t]["sampler"].jumpDict.get(n, [0, 0])[1] for n in sorted(names, key=names.get)]
-                           for t in range(ntemps)]),
+        jump_prop=_by_id(0), jump_acc=_by_id(1),  # [T][jump id]: proposed / accepted (ref jumpDict :602, :622)
     )
     res["_samplers"] = [o["sampler"] for o in out]
     res["_outdir"] = outdir

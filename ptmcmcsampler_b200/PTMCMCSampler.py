@@ -173,6 +173,9 @@ class PTSampler(object):
         self.covarianceJumpProposalAM = _BuiltinJump(
             "covarianceJumpProposalAM", _cabi.JUMP_AM, "adaptive-Metropolis jump (ref :879-933)")
         self.DEJump = _BuiltinJump("DEJump", _cabi.JUMP_DE, "differential-evolution jump (ref :936-985)")
+        # beyond the reference: a draw from the uniform prior box on the device (the UniformJump plugin of the
+        # reference's tests/test_simple.py:44-62); add with addProposalToCycle(sampler.priorDrawJump, weight)
+        self.priorDrawJump = _BuiltinJump("priorDrawJump", _cabi.JUMP_PRIOR, "draw from the UniformPrior box")
 
     # ------------------------------------------------------------------ plugin surface --------
     def addProposalToCycle(self, func, weight):
@@ -409,7 +412,7 @@ class PTSampler(object):
             prop, acc, sw, nsw = self._engine.counters()
         self._prop, self._acc, self._swap_acc = prop, acc, sw
         names = {_cabi.JUMP_SCAM: "covarianceJumpProposalSCAM", _cabi.JUMP_AM: "covarianceJumpProposalAM",
-                 _cabi.JUMP_DE: "DEJump"}
+                 _cabi.JUMP_DE: "DEJump", _cabi.JUMP_PRIOR: "priorDrawJump"}
         for k, f in enumerate(self._ext_jumps):
             names[_cabi.JUMP_EXT0 + k] = f.__name__
         for jid, name in names.items():

@@ -10,10 +10,10 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libptmcmc_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_CYCLE = 16
 
-JUMP_SCAM, JUMP_AM, JUMP_DE, JUMP_EXT0 = 0, 1, 2, 3
+JUMP_SCAM, JUMP_AM, JUMP_DE, JUMP_PRIOR, JUMP_EXT0 = 0, 1, 2, 3, 4
 LOGL_EXTERNAL, LOGL_GAUSSIAN, LOGL_CURVED, LOGL_ROSENBROCK = 0, 1, 2, 3
 LOGP_EXTERNAL, LOGP_UNIFORM, LOGP_FLAT = 0, 1, 2
 ERR_ARG, ERR_DE_SHAPE, ERR_CUDA, ERR_STATE, ERR_CAPACITY = -1, -2, -3, -4, -5

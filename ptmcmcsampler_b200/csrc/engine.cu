@@ -217,7 +217,8 @@ Engine *engine_of(const ptmcmc_engine *h)
 
 int chain_blocks(const Engine *e) { return (int)(((long long)e->T * e->W + MH_THREADS - 1) / MH_THREADS); }
 
-bool fast_reg_path(const Engine *e) { return e->identity_group && e->d <= MAX_REG_DIM; }
+// the specialised kernels know the three reference proposals; a cycle with the prior-draw jump runs in the generic one
+bool fast_reg_path(const Engine *e) { return e->identity_group && e->d <= MAX_REG_DIM && e->njumps == 3; }
 
 template <int DP>
 cudaError_t launch_reg(const Engine *e, const DevParams &p)
@@ -369,7 +370,7 @@ cudaError_t build_u_frags(Engine *e)
 
 bool use_mma(const Engine *e)
 {
-    if (!e->mma_ok) return false;
+    if (!e->mma_ok || e->njumps != 3) return false;
     if (e->mh_variant == 3) return true;
     // measured on B200 (8192 x 16 chains): ndim 24: sorted 3.9e9 vs tensor-core 3.1e9; ndim 32: 1.9e9 vs 2.2e9;
     // beyond 32 the alternative is the local-memory kernel
@@ -617,6 +618,8 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         e->cyc_w.push_back(cfg->cycle_weight[i]);
         if (cfg->cycle_jump[i] + 1 > e->njumps) e->njumps = cfg->cycle_jump[i] + 1;
         if (cfg->cycle_jump[i] == PTMCMC_JUMP_DE) e->de_in_cycle = true;
+        if (cfg->cycle_jump[i] == PTMCMC_JUMP_PRIOR && cfg->logp_kind != PTMCMC_LOGP_UNIFORM)
+            return fail(nullptr, PTMCMC_ERR_ARG, "the prior-draw jump needs the uniform box prior");
     }
     if (e->cyc_jump.empty()) return fail(nullptr, PTMCMC_ERR_ARG, "No jump proposals specified!");
     e->ntr = cfg->record_hot ? T : 1;
@@ -890,7 +893,7 @@ int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
     if (!e) return PTMCMC_ERR_ARG;
     if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_run before ptmcmc_set_state");
     if (e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_run between propose and accept");
-    if (e->cfg.logl_kind == PTMCMC_LOGL_EXTERNAL || e->cfg.logp_kind == PTMCMC_LOGP_EXTERNAL || e->njumps > 3)
+    if (e->cfg.logl_kind == PTMCMC_LOGL_EXTERNAL || e->cfg.logp_kind == PTMCMC_LOGP_EXTERNAL || e->njumps > PTMCMC_JUMP_EXT0)
         return fail(e, PTMCMC_ERR_STATE, "external targets or jumps: drive with ptmcmc_propose / ptmcmc_accept");
     if (niter < 0) return fail(e, PTMCMC_ERR_ARG, "niter < 0");
     if (e->pending_swap) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_run with a sharded swap pending (ptmcmc_swap_*)");

@@ -298,6 +298,15 @@ __device__ inline int propose_generic(const DevParams &p, Stream &st, double tem
 {
     const int jump = pick_jump(p, st);
     if (jump >= JUMP_EXT0) return jump;
+    if (jump == JUMP_PRIOR) {
+        // a fresh draw from the uniform prior box, one uniform per parameter (the "UniformJump" plugin of
+        // ref tests/test_simple.py:44-62 on the device); symmetric: qxy = 0
+        for (int k = 0; k < p.d; ++k) {
+            const double lo = __ldg(p.p_lo + k), hi = __ldg(p.p_hi + k);
+            q[k] = lo + (hi - lo) * word_to_unit(st.next());
+        }
+        return jump;
+    }
     const int g = (int)word_to_int(st.next(), (unsigned long long)p.ngroups);
     const int g0 = p.goff[g], dg = p.goff[g + 1] - g0;
     const int *gi = p.gidx + g0;

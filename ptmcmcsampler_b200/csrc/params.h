@@ -9,7 +9,7 @@ constexpr int MAX_REG_DIM = 32;       // register-resident kernel covers ndim <=
 constexpr int MAX_GENERIC_DIM = 128;  // local-memory kernel covers ndim <= 128
 constexpr int MH_THREADS = 128;
 
-enum : int { JUMP_SCAM = 0, JUMP_AM = 1, JUMP_DE = 2, JUMP_EXT0 = 3 };
+enum : int { JUMP_SCAM = 0, JUMP_AM = 1, JUMP_DE = 2, JUMP_PRIOR = 3, JUMP_EXT0 = 4 };
 enum : int { LOGL_EXTERNAL = 0, LOGL_GAUSSIAN = 1, LOGL_CURVED = 2, LOGL_ROSENBROCK = 3 };
 enum : int { LOGP_EXTERNAL = 0, LOGP_UNIFORM = 1, LOGP_FLAT = 2 };
 

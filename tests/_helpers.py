@@ -42,6 +42,8 @@ def fixture_cycle(g):
     cyc = []
     if int(g["ext"]):
         cyc.append((orc.JUMP_EXT0, 7))
+    if "prior_weight" in g and int(g["prior_weight"]):
+        cyc.append((orc.JUMP_PRIOR, int(g["prior_weight"])))
     if int(g["kw_SCAMweight"]):
         cyc.append((orc.JUMP_SCAM, int(g["kw_SCAMweight"])))
     if int(g["kw_AMweight"]):

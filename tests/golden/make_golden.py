@@ -39,7 +39,7 @@ def save(name, **kw):
 
 
 def traj_case(name, d, T, N, seed, sample_kwargs, groups=None, curved=False, pmin=-50.0, pmax=60.0,
-              ext=False):
+              ext=False, prior_weight=0):
     rng = np.random.default_rng(seed + 1000)
     if curved:
         pb = rh.CurvedProblem(d)
@@ -61,12 +61,25 @@ def traj_case(name, d, T, N, seed, sample_kwargs, groups=None, curved=False, pmi
             return lo + (hi - lo) * (0.45 + 0.1 * frac), 0.05 * np.sin(it) * beta
 
         ext_jumps = [(golden_ext_jump, 7)]
+    if prior_weight:
+        lo, hi = (pb.pmin, pb.pmax) if curved else (pb.a, pb.b)
+
+        def bind(sampler):
+            # the reference's UniformJump (tests/test_simple.py:44-62) drawing from the sampler's own stream,
+            # one random() per parameter: what the engine's built-in prior-draw jump restates
+            def priorDrawJump(x, it, beta):
+                return lo + (hi - lo) * np.array([sampler.stream.random() for _ in range(len(x))]), 0.0
+            return priorDrawJump
+
+        bind.bind_sampler = True
+        bind.jump_name = "priorDrawJump"
+        ext_jumps = ext_jumps + [(bind, prior_weight, rh.orc.JUMP_PRIOR)]
     r = rh.run_reference(d, pb.lnlikefn, pb.lnpriorfn, cov0, p0, N, seed=seed, ntemps=T,
                          sample_kwargs=sample_kwargs, groups=groups, ext_jumps=ext_jumps)
     gflat = np.concatenate(groups) if groups is not None else np.arange(d)
     goff = np.cumsum([0] + [len(g) for g in groups]) if groups is not None else np.array([0, d])
     save(name, d=d, T=T, N=N, seed=seed, cov0=cov0, p0=p0, group_offsets=goff, group_indices=gflat,
-         has_groups=int(groups is not None), ext=int(ext),
+         has_groups=int(groups is not None), ext=int(ext), prior_weight=int(prior_weight),
          **{"kw_" + k: v for k, v in sample_kwargs.items()}, **meta, **r)
 
 
@@ -108,6 +121,9 @@ def main():
     kw5 = dict(burn=100, thin=2, covUpdate=50, SCAMweight=20, AMweight=20, DEweight=30, isave=1000, Tskip=5,
                Tmax=20.0, hotChain=True)
     traj_case("traj_t3_hot_tmax_d4", 4, 3, 300, 31, kw5, pmin=0.0, pmax=10.0)
+    # the device-side prior-draw jump against the reference running the equivalent plugin
+    kw6 = dict(burn=100, thin=1, covUpdate=50, SCAMweight=15, AMweight=15, DEweight=20, isave=1000, Tskip=10)
+    traj_case("traj_t2_prior_d4", 4, 2, 300, 77, kw6, pmin=0.0, pmax=10.0, prior_weight=10)
     if "--traj-only" in sys.argv:  # the statistical bands do not depend on the oracle's draw functions
         return
     # statistical bands (reference's own PCG64 stream)

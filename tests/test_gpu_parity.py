@@ -153,6 +153,17 @@ def test_sorted_kernel_widest_instance_matches_oracle():
     compare(o, g, x0, niter, 10, T)
 
 
+def test_prior_draw_jump_matches_oracle():
+    """The device-side prior-draw jump (cycle id 3) in the generic kernel, W walkers, against the oracle."""
+    d, W, T, niter = 7, 50, 3, 260
+    tgt = gaussian_target(d, 5, lo=0.0, hi=10.0)
+    o, g = make_pair(d, W, T, np.eye(d) * 0.05, seed=8, target=tgt, niter=niter,
+                     cycle=((orc.JUMP_PRIOR, 5), (orc.JUMP_SCAM, 20), (orc.JUMP_AM, 20)))
+    x0 = np.random.default_rng(6).uniform(0, 10, (T, W, d))
+    compare(o, g, x0, niter, 10, T)
+    assert g.counters()[0][..., orc.JUMP_PRIOR].sum() > 0
+
+
 def test_truncated_box_and_outside_start():
     """Box prior tighter than the likelihood (ref examples/simple.py), with walkers that start
     outside the prior: lnprob0 = -inf, first in-prior proposal always accepted (ref :481-483)."""
@@ -202,7 +213,7 @@ def test_hot_chain_temperature_override():
     compare(o, g, x0, niter, 10, T)
 
 
-@pytest.mark.parametrize("name", ["traj_t1_d5", "traj_t4_groups_d6", "traj_t1_d20", "traj_t3_hot_tmax_d4"])
+@pytest.mark.parametrize("name", ["traj_t1_d5", "traj_t4_groups_d6", "traj_t1_d20", "traj_t3_hot_tmax_d4", "traj_t2_prior_d4"])
 def test_engine_reproduces_reference_trajectory(name):
     """W=1: the engine fed the reference's own eigen-factors walks the reference's trajectory."""
     gfx = load(name)

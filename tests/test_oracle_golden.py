@@ -11,7 +11,8 @@ from oracle import oracle as orc
 
 from _helpers import load, oracle_from_fixture
 
-TRAJ = ["traj_t1_d5", "traj_t4_groups_d6", "traj_t3_curved_ext_d4", "traj_t1_d20", "traj_t3_hot_tmax_d4"]
+TRAJ = ["traj_t1_d5", "traj_t4_groups_d6", "traj_t3_curved_ext_d4", "traj_t1_d20", "traj_t3_hot_tmax_d4",
+        "traj_t2_prior_d4"]
 FTOL = 1e-10
 
 
