@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PTMCMC_ABI_VERSION 3
+#define PTMCMC_ABI_VERSION 4
 
 /* jump ids: the reference's built-in proposals (ref :820-985); PRIOR = a draw from the uniform prior
  * box, the device-side form of the "UniformJump" plugin of ref tests/test_simple.py:44-62 (needs
@@ -36,9 +36,11 @@ extern "C" {
  * addProposalToCycle (ref :988-1014) */
 enum { PTMCMC_JUMP_SCAM = 0, PTMCMC_JUMP_AM = 1, PTMCMC_JUMP_DE = 2, PTMCMC_JUMP_PRIOR = 3, PTMCMC_JUMP_EXT0 = 4 };
 /* built-in log-likelihoods (ref examples/simple.py:34-36, examples/curved_likelihood.ipynb) */
-enum { PTMCMC_LOGL_EXTERNAL = 0, PTMCMC_LOGL_GAUSSIAN = 1, PTMCMC_LOGL_CURVED = 2, PTMCMC_LOGL_ROSENBROCK = 3 };
+enum { PTMCMC_LOGL_EXTERNAL = 0, PTMCMC_LOGL_GAUSSIAN = 1, PTMCMC_LOGL_CURVED = 2, PTMCMC_LOGL_ROSENBROCK = 3,
+       PTMCMC_LOGL_USER = 4 /* CUDA source supplied by the caller, compiled with NVRTC (logl_source) */ };
 /* built-in log-priors (ref examples/simple.py:38-44) */
-enum { PTMCMC_LOGP_EXTERNAL = 0, PTMCMC_LOGP_UNIFORM = 1, PTMCMC_LOGP_FLAT = 2 };
+enum { PTMCMC_LOGP_EXTERNAL = 0, PTMCMC_LOGP_UNIFORM = 1, PTMCMC_LOGP_FLAT = 2,
+       PTMCMC_LOGP_USER = 3 /* CUDA source supplied by the caller (logp_source) */ };
 
 enum {
     PTMCMC_OK = 0,
@@ -90,6 +92,19 @@ typedef struct ptmcmc_config {
     int32_t reserved2;
     double ladder_above;        /* ladder sharding: temperature of rung temp_offset+ntemps (hotter neighbour) */
     double ladder_below;        /* ladder sharding: temperature of rung temp_offset-1 (colder neighbour) */
+    /* User targets on the device (the reference's arbitrary logl / logp callables, ref :108-109, :605-612,
+     * :1072-1086, as CUDA source instead of Python).  logl_source defines
+     *     __device__ double user_logl(const double *x, int ndim, const double *par);
+     * logp_source defines  __device__ double user_logp(const double *x, int ndim, const double *par);
+     * returning -inf outside the prior support (ref :607-608).  Either may be NULL when the matching kind is a
+     * built-in.  The sources are compiled with NVRTC for the device's architecture together with the MH
+     * kernel at ptmcmc_create (cached by content hash); a compile error fails the create with the NVRTC log.
+     * par points at a device copy of user_params. */
+    const char *logl_source;
+    const char *logp_source;
+    const double *user_params;  /* [n_user_params] */
+    int32_t n_user_params;
+    int32_t reserved3;
 } ptmcmc_config;
 
 typedef struct ptmcmc_engine ptmcmc_engine;
@@ -218,6 +233,12 @@ int32_t ptmcmc_get_timing(ptmcmc_engine *e, ptmcmc_timing *out);
 int32_t ptmcmc_reset_timing(ptmcmc_engine *e);
 /* switch the per-launch CUDA-event bracketing on or off (same as cfg.timing) */
 int32_t ptmcmc_set_timing(ptmcmc_engine *e, int32_t on);
+/* name of the kernel ptmcmc_run launches for the MH segments of this engine (for profiles and bench records) */
+const char *ptmcmc_mh_kernel_name(ptmcmc_engine *e);
+/* measured fp64 FMA throughput of `device` in TFLOP/s (a short DFMA kernel; the compute-side roofline denominator) */
+int32_t ptmcmc_measure_fp64_peak(int32_t device, double *tflops);
+/* test hook: the device's Box-Muller pairs of n 64-bit words (word_to_normals) on `device`; host buffers */
+int32_t ptmcmc_test_normals(int32_t device, const uint64_t *words, int64_t n, double *z0, double *z1);
 /* the engine's CUDA stream (cudaStream_t) for callers that time with their own events */
 void *ptmcmc_stream(ptmcmc_engine *e);
 /* page-locked host memory for the caller-owned buffers (faster DMA); plain malloc memory works too */

@@ -100,6 +100,7 @@ def lib():
         L.orc_word_to_unit.restype = C.c_double
         L.orc_word_to_unit.argtypes = [C.c_uint64]
         L.orc_word_to_normals.argtypes = [C.c_uint64, dp, dp]
+        L.orc_word_to_normals_many.argtypes = [C.POINTER(C.c_uint64), C.c_int64, dp, dp]
         L.orc_sym_factor.argtypes = [C.c_int, dp, dp, dp]
         L.orc_temperature_ladder.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, dp]
         _lib = L
@@ -138,6 +139,13 @@ def word_to_normals(word):
     a, b = C.c_double(), C.c_double()
     lib().orc_word_to_normals(word, C.byref(a), C.byref(b))
     return a.value, b.value
+
+
+def word_to_normals_many(words):
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    z0, z1 = np.empty(words.size), np.empty(words.size)
+    lib().orc_word_to_normals_many(words.ctypes.data_as(C.POINTER(C.c_uint64)), words.size, _dp(z0), _dp(z1))
+    return z0, z1
 
 
 def sym_factor(a):

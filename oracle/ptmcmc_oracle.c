@@ -162,6 +162,13 @@ void orc_word_to_normals(uint64_t word, double *z0, double *z1)
     *z1 = (double)(r * s);
 }
 
+/* batch form for the distribution tests (tests/test_oracle_golden.py, tests/test_gpu_parity.py) */
+void orc_word_to_normals_many(const uint64_t *words, int64_t n, double *z0, double *z1)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) orc_word_to_normals(words[i], &z0[i], &z1[i]);
+}
+
 static uint64_t draw_int(orc_stream *st, uint64_t n) { return orc_word_to_int(stream_next(st), n); }
 static double draw_unit(orc_stream *st) { return orc_word_to_unit(stream_next(st)); }
 static double draw_normal(orc_stream *st)

@@ -121,6 +121,7 @@ uint64_t orc_draw_word(uint64_t seed, uint32_t purpose, uint64_t iter, uint32_t 
 uint64_t orc_word_to_int(uint64_t word, uint64_t n);
 double orc_word_to_unit(uint64_t word);
 void orc_word_to_normals(uint64_t word, double *z0, double *z1);
+void orc_word_to_normals_many(const uint64_t *words, int64_t n, double *z0, double *z1);
 
 /* symmetric eigen-factorisation used for U,S (round-robin Jacobi, sorted, sign-fixed) */
 void orc_sym_factor(int n, const double *a, double *U, double *S);

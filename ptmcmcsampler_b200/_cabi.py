@@ -10,12 +10,12 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libptmcmc_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_CYCLE = 16
 
 JUMP_SCAM, JUMP_AM, JUMP_DE, JUMP_PRIOR, JUMP_EXT0 = 0, 1, 2, 3, 4
-LOGL_EXTERNAL, LOGL_GAUSSIAN, LOGL_CURVED, LOGL_ROSENBROCK = 0, 1, 2, 3
-LOGP_EXTERNAL, LOGP_UNIFORM, LOGP_FLAT = 0, 1, 2
+LOGL_EXTERNAL, LOGL_GAUSSIAN, LOGL_CURVED, LOGL_ROSENBROCK, LOGL_USER = 0, 1, 2, 3, 4
+LOGP_EXTERNAL, LOGP_UNIFORM, LOGP_FLAT, LOGP_USER = 0, 1, 2, 3
 ERR_ARG, ERR_DE_SHAPE, ERR_CUDA, ERR_STATE, ERR_CAPACITY = -1, -2, -3, -4, -5
 K_NAMES = ["mh", "swap", "adapt", "de", "init", "propose", "accept", "reserved"]
 
@@ -41,6 +41,8 @@ class Config(C.Structure):
         ("record_rows", C.c_int64), ("trace_iters", C.c_int64),
         ("timing", C.c_int32), ("reserved2", C.c_int32),
         ("ladder_above", C.c_double), ("ladder_below", C.c_double),
+        ("logl_source", C.c_char_p), ("logp_source", C.c_char_p), ("user_params", _dp),
+        ("n_user_params", C.c_int32), ("reserved3", C.c_int32),
     ]
 
 
@@ -57,7 +59,8 @@ SYMBOLS = [
     "ptmcmc_get_trace", "ptmcmc_get_timing", "ptmcmc_reset_timing", "ptmcmc_stream", "ptmcmc_set_timing",
     "ptmcmc_host_alloc", "ptmcmc_host_free", "ptmcmc_swap_msg_doubles", "ptmcmc_swap_pending",
     "ptmcmc_swap_pack_top", "ptmcmc_swap_sweep", "ptmcmc_swap_finish", "ptmcmc_am_ring", "ptmcmc_maintain",
-    "ptmcmc_state_bytes", "ptmcmc_save_state", "ptmcmc_load_state", "ptmcmc_replay",
+    "ptmcmc_state_bytes", "ptmcmc_save_state", "ptmcmc_load_state", "ptmcmc_replay", "ptmcmc_mh_kernel_name",
+    "ptmcmc_test_normals", "ptmcmc_measure_fp64_peak",
 ]
 
 _lib = None
@@ -129,6 +132,10 @@ def load():
     L.ptmcmc_save_state.argtypes = [h, C.c_void_p, C.c_int64]
     L.ptmcmc_load_state.argtypes = [h, C.c_void_p, C.c_int64]
     L.ptmcmc_replay.argtypes = [h, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, _dp]
+    L.ptmcmc_mh_kernel_name.restype = C.c_char_p
+    L.ptmcmc_mh_kernel_name.argtypes = [h]
+    L.ptmcmc_measure_fp64_peak.argtypes = [C.c_int32, _dp]
+    L.ptmcmc_test_normals.argtypes = [C.c_int32, C.POINTER(C.c_uint64), C.c_int64, _dp, _dp]
     for name in SYMBOLS:
         getattr(L, name)
     if L.ptmcmc_abi_version() != ABI_VERSION:
@@ -457,3 +464,26 @@ class Engine(object):
     @property
     def stream(self):
         return self._L.ptmcmc_stream(self._h)
+
+    @property
+    def mh_kernel_name(self):
+        return self._L.ptmcmc_mh_kernel_name(self._h).decode()
+
+
+def measure_fp64_peak(device=0):
+    """Measured fp64 FMA throughput of the device in TFLOP/s."""
+    v = C.c_double()
+    rc = load().ptmcmc_measure_fp64_peak(int(device), C.byref(v))
+    if rc < 0:
+        raise EngineError(rc, "ptmcmc_measure_fp64_peak failed")
+    return v.value
+
+
+def device_normals(words, device=0):
+    """Box-Muller pairs of 64-bit words as the device computes them (test hook)."""
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    z0, z1 = np.empty(words.size), np.empty(words.size)
+    rc = load().ptmcmc_test_normals(int(device), words.ctypes.data_as(C.POINTER(C.c_uint64)), words.size, _d(z0), _d(z1))
+    if rc < 0:
+        raise EngineError(rc, "ptmcmc_test_normals failed")
+    return z0, z1

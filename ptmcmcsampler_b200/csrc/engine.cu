@@ -19,11 +19,8 @@
 
 #include "../../include/ptmcmc_b200.h"
 #include "adapt_kernels.cuh"
+#include "launch.h"
 #include "mh_kernels.cuh"
-#include "mh_mma_kernel.cuh"
-#include "mh_pipe_kernel.cuh"
-#include "mh_shadow_kernel.cuh"
-#include "mh_sorted_kernel.cuh"
 #include "params.h"
 #include "swap_kernels.cuh"
 
@@ -53,6 +50,30 @@ __global__ void __launch_bounds__(256) to_host_layout_kernel(const double *src, 
         const int w = (int)(idx / d), k = (int)(idx % d);
         dst[((size_t)t * W + w) * d + k] = src[((size_t)t * d + k) * W + w];
     }
+}
+
+__global__ void __launch_bounds__(256) normals_kernel(const unsigned long long *w, long long n, double *z0, double *z1)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        word_to_normals((uint64_t)w[i], z0[i], z1[i]);
+}
+
+// fp64 roofline probe: 8 independent DFMA chains per thread, 512 threads per SM (the denominators bench.py
+// reports against are measured on the device it runs on, not copied from a data sheet)
+__global__ void __launch_bounds__(512) fp64_peak_kernel(double *out, int iters, double a0, double b0)
+{
+    double c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = threadIdx.x * 1e-9 + i;
+    const double a = a0 + threadIdx.x * 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = fma(c[i], a, b0);
+    }
+    double sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += c[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sum;
 }
 
 struct Engine {
@@ -102,12 +123,13 @@ struct Engine {
     ptmcmc_timing tm{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
-    int mh_variant = 0;  // 0: sorted shared-memory kernel, 1: thread-per-chain register kernel, 2: generic
-    int sort_nc = 256;   // chains (= threads) per block of the sorted kernel
-    int pipe_npw = 6;    // draw warps of the warp-specialised kernel
+    int mh_variant = 0;  // 0: default choice, 2: generic kernel, 3: tensor-core kernel, 6: sorted kernel for any ndim <= 32
+    uint32_t rk[20] = {};  // Philox round keys of the seed
+    SortedGeom sorted{};   // launch geometry of the sorted shared-memory kernel
+    SortedHostTables sorted_tb{};  // its static tables (Gaussian form, mean, prior box)
     // tensor-core (DMMA) kernel: fragment-order matrices and launch geometry
-    bool mma_ok = false, mma_tri = false;
-    int mma_nt = 0, mma_nc = 0, mma_ld = 0, mma_smem = 0;
+    bool mma_ok = false;
+    MmaGeom mma{};
     double *d_Uf = nullptr, *d_Pf = nullptr, *d_gPfull = nullptr, *d_Ut = nullptr;
 };
 
@@ -163,6 +185,7 @@ DevParams make_params(const Engine *e)
     p.walker_offset = e->cfg.walker_offset; p.temp_offset = e->cfg.temp_offset;
     p.ngroups = e->ngroups; p.identity_group = e->identity_group; p.njumps = e->njumps;
     p.seed = e->cfg.seed;
+    memcpy(p.rk, e->rk, sizeof p.rk);
     p.x = e->x[e->cur]; p.lnl = e->lnl[e->cur]; p.lp = e->lp[e->cur];
     p.mh_temp = e->d_mh_temp; p.ladder = e->d_ladder;
     p.U = e->d_U; p.sqrtS = e->d_sqrtS;
@@ -220,152 +243,13 @@ int chain_blocks(const Engine *e) { return (int)(((long long)e->T * e->W + MH_TH
 // the specialised kernels know the three reference proposals; a cycle with the prior-draw jump runs in the generic one
 bool fast_reg_path(const Engine *e) { return e->identity_group && e->d <= MAX_REG_DIM && e->njumps == 3; }
 
-template <int DP>
-cudaError_t launch_reg(const Engine *e, const DevParams &p)
-{
-    const size_t smem = sizeof(double) * (2 * DP * DP + 4 * DP);
-    static bool attr_dev[64] = {};
-    bool &attr_done = attr_dev[e->cfg.device & 63];  // function attributes are per device
-    if (!attr_done && smem > 48 * 1024) {
-        cudaFuncSetAttribute(mh_reg_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-    }
-    mh_reg_kernel<DP><<<chain_blocks(e), MH_THREADS, smem, e->stream>>>(p);
-    return cudaGetLastError();
-}
-
-constexpr int SORT_NC = 256;
-
-template <int DP, int MINB>
-cudaError_t launch_sorted_minb(const Engine *e, const DevParams &p)
-{
-    const size_t smem = sizeof(SortedSmem<DP, SORT_NC>);
-    static bool attr_dev[64] = {};
-    bool &attr_done = attr_dev[e->cfg.device & 63];  // function attributes are per device
-    if (!attr_done) {
-        cudaError_t st = cudaFuncSetAttribute(mh_sorted_kernel<DP, SORT_NC, MINB>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (st != cudaSuccess) return st;
-        if (const char *v = getenv("PTMCMC_SORT_CARVEOUT"))  // experiment: shared-memory carve-out in percent
-            cudaFuncSetAttribute(mh_sorted_kernel<DP, SORT_NC, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v));
-        attr_done = true;
-    }
-    const int nc = e->sort_nc;
-    const int blocks = (int)(((long long)e->T * e->W + nc - 1) / nc);
-    mh_sorted_kernel<DP, SORT_NC, MINB><<<blocks, nc, smem, e->stream>>>(p);
-    return cudaGetLastError();
-}
-
-// 2 blocks per SM (128 registers).  Bounding the allocation for 3 blocks (<= 85 registers) was measured at
-// 2.7e9 vs 4.4e9 chain-steps/s on C2: the spills cost more than the extra warps hide.
-template <int DP>
-cudaError_t launch_sorted(const Engine *e, const DevParams &p)
-{
-    return launch_sorted_minb<DP, 2>(e, p);
-}
-
-template <int DP>
-cudaError_t launch_shadow(const Engine *e, const DevParams &p)
-{
-    const size_t smem = sizeof(ShadowSmem<DP, SORT_NC>);
-    static bool attr_dev[64] = {};
-    bool &attr_done = attr_dev[e->cfg.device & 63];  // function attributes are per device
-    if (!attr_done) {
-        cudaError_t st = cudaFuncSetAttribute(mh_shadow_kernel<DP, SORT_NC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem);
-        if (st != cudaSuccess) return st;
-        attr_done = true;
-    }
-    const int blocks = (int)(((long long)e->T * e->W + SORT_NC - 1) / SORT_NC);
-    mh_shadow_kernel<DP, SORT_NC, 2><<<blocks, SORT_NC, smem, e->stream>>>(p);
-    return cudaGetLastError();
-}
-
-template <int DP, int NPW>
-cudaError_t launch_pipe(const Engine *e, const DevParams &p)
-{
-    const size_t smem = sizeof(PipeSmem<DP>);
-    static bool attr_dev[64] = {};
-    bool &attr_done = attr_dev[e->cfg.device & 63];  // function attributes are per device
-    if (!attr_done) {
-        cudaError_t st = cudaFuncSetAttribute(mh_pipe_kernel<DP, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (st != cudaSuccess) return st;
-        attr_done = true;
-    }
-    const int blocks = (int)(((long long)e->T * e->W + PIPE_NC - 1) / PIPE_NC);
-    mh_pipe_kernel<DP, NPW><<<blocks, PIPE_NC + 32 * NPW, smem, e->stream>>>(p);
-    return cudaGetLastError();
-}
-
-template <int DP>
-cudaError_t launch_pipe_npw(const Engine *e, const DevParams &p)
-{
-    return launch_pipe<DP, 6>(e, p);  // 4 / 6 / 8 draw warps measured alike
-}
-
-constexpr int MMA_SMALL_MINB = 4;  // ndim <= 32: four 256-thread blocks per SM (<= 64 registers per thread)
-
-template <int NT>
-cudaError_t launch_mma(const Engine *e, const DevParams &p)
-{
-    constexpr bool USMEM = NT <= 4;
-    constexpr int MINB = NT <= 4 ? MMA_SMALL_MINB : 1;
-    static bool attr_dev[64] = {};
-    bool &attr_done = attr_dev[e->cfg.device & 63];  // function attributes are per device
-    if (!attr_done) {
-        cudaError_t st = cudaFuncSetAttribute(mh_mma_kernel<NT, USMEM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              227 * 1024);
-        if (st != cudaSuccess) return st;
-        attr_done = true;
-    }
-    MmaArgs a{e->d_Uf, e->d_Pf, e->d_Ut, e->mma_nc, e->mma_ld, e->mma_tri ? 1 : 0, mma_layout(NT, e->mma_nc, e->mma_ld, USMEM)};
-    const int blocks = (int)(((long long)e->T * e->W + e->mma_nc - 1) / e->mma_nc);
-    mh_mma_kernel<NT, USMEM, MINB><<<blocks, MMA_THREADS, e->mma_smem, e->stream>>>(p, a);
-    return cudaGetLastError();
-}
-
-// instantiated n-tile counts (ndim <= 8 NT); the smallest one that covers ndim is used
-int mma_pick_nt(int d)
-{
-    const int need = (d + 7) / 8;
-    for (int nt : {1, 2, 3, 4, 8, 13, 16})
-        if (nt >= need) return nt;
-    return 0;
-}
-
-// chains per block: two blocks per SM when at least 128 chains fit that way, else one block per SM
-void mma_geometry(Engine *e)
-{
-    const int NT = e->mma_nt, KP = 8 * NT;
-    e->mma_ld = (KP % 16 == 8) ? KP : KP + 8;
-    const bool usmem = NT <= 4;
-    auto fits = [&](int nc, int budget) { return mma_layout(NT, nc, e->mma_ld, usmem).total <= budget; };
-    int nc = 0;
-    if (NT <= 4)  // MMA_SMALL_MINB blocks per SM
-        for (int c : {128, 96, 64})
-            if (!nc && fits(c, (228 / MMA_SMALL_MINB - 1) * 1024)) nc = c;
-    for (int c : {256, 192, 128})
-        if (!nc && fits(c, 113 * 1024)) nc = c;
-    if (!nc)
-        for (int c = 256; c >= 8 && !nc; c -= 8)
-            if ((c % 64 == 0 || c < 64) && fits(c, 227 * 1024)) nc = c;
-    if (const char *v = getenv("PTMCMC_MMA_NC")) {
-        const int c = atoi(v);
-        if (c >= 8 && c <= 256 && c % 8 == 0 && fits(c, 227 * 1024)) nc = c;
-    }
-    e->mma_nc = nc;
-    e->mma_smem = nc ? mma_layout(NT, nc, e->mma_ld, usmem).total : 0;
-    if (!nc) e->mma_ok = false;
-}
-
 cudaError_t build_u_frags(Engine *e)
 {
     if (!e->mma_ok) return cudaSuccess;
-    const int n = e->mma_nt * e->mma_nt * 64;
-    frag_build_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_U, e->d, e->mma_nt, 1, e->d_Uf);
-    transpose_kernel<<<(e->d * e->d + 255) / 256, 256, 0, e->stream>>>(e->d_U, e->d, e->d_Ut);
+    cudaError_t st = launch_frag_build(e->d_U, e->d, e->mma.nt, 1, e->d_Uf, e->stream);
+    if (st == cudaSuccess) st = launch_transpose(e->d_U, e->d, e->d_Ut, e->stream);
     e->tm.launches[PTMCMC_K_ADAPT] += 2;
-    return cudaGetLastError();
+    return st;
 }
 
 bool use_mma(const Engine *e)
@@ -383,39 +267,8 @@ cudaError_t launch_mh(Engine *e, long long it0, long long it1, bool tail)
     p.it0 = it0; p.it1 = it1; p.tail = tail ? 1 : 0;
     LaunchTimer lt(e, PTMCMC_K_MH);
     e->tm.chain_steps += (it1 - it0 + 1) * (long long)e->T * e->W;
-    if (use_mma(e)) {
-        switch (e->mma_nt) {
-        case 1: return launch_mma<1>(e, p);
-        case 2: return launch_mma<2>(e, p);
-        case 3: return launch_mma<3>(e, p);
-        case 4: return launch_mma<4>(e, p);
-        case 8: return launch_mma<8>(e, p);
-        case 13: return launch_mma<13>(e, p);
-        default: return launch_mma<16>(e, p);
-        }
-    }
-    if (fast_reg_path(e) && e->mh_variant == 4 && e->d > 16 && e->d <= 20) return launch_pipe_npw<20>(e, p);
-    if (fast_reg_path(e) && e->mh_variant == 5 && e->d > 16 && e->d <= 20) return launch_shadow<20>(e, p);
-    if (fast_reg_path(e) && (e->mh_variant == 0 || e->mh_variant >= 4)) {  // 6: the sorted kernel for any ndim <= 32
-        const int d = e->d;
-        if (d <= 4) return launch_sorted<4>(e, p);
-        if (d <= 8) return launch_sorted<8>(e, p);
-        if (d <= 12) return launch_sorted<12>(e, p);
-        if (d <= 16) return launch_sorted<16>(e, p);
-        if (d <= 20) return launch_sorted<20>(e, p);
-        if (d <= 24) return launch_sorted<24>(e, p);
-        return launch_sorted<32>(e, p);
-    }
-    if (fast_reg_path(e) && e->mh_variant == 1) {
-        const int d = e->d;
-        if (d <= 4) return launch_reg<4>(e, p);
-        if (d <= 8) return launch_reg<8>(e, p);
-        if (d <= 12) return launch_reg<12>(e, p);
-        if (d <= 16) return launch_reg<16>(e, p);
-        if (d <= 20) return launch_reg<20>(e, p);
-        if (d <= 24) return launch_reg<24>(e, p);
-        return launch_reg<32>(e, p);
-    }
+    if (use_mma(e)) return launch_mma(p, e->mma, e->d_Uf, e->d_Pf, e->d_Ut, e->cfg.device, e->stream);
+    if (fast_reg_path(e) && e->mh_variant != 2) return launch_sorted(p, e->sorted_tb, e->sorted, e->cfg.device, e->stream);
     mh_generic_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p);
     return cudaGetLastError();
 }
@@ -568,6 +421,8 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     if (T > 32767) return fail(nullptr, PTMCMC_ERR_ARG, "ntemps must be < 32768");
     if (cfg->cov_update < 1 || cfg->burn < 1 || cfg->tskip < 1 || cfg->thin < 1)
         return fail(nullptr, PTMCMC_ERR_ARG, "covUpdate, burn, Tskip and thin must be >= 1");
+    if (cfg->cov_update > 0x7FFFFFFF || cfg->thin > 0x7FFFFFFF)
+        return fail(nullptr, PTMCMC_ERR_ARG, "covUpdate and thin must be < 2^31");
     if (!cfg->ladder || !cfg->cov) return fail(nullptr, PTMCMC_ERR_ARG, "ladder and cov are required");
     if (cfg->ncycle < 1 || cfg->ncycle >= PTMCMC_MAX_CYCLE) return fail(nullptr, PTMCMC_ERR_ARG, "No jump proposals specified!");
     if (cfg->record_rows < 1) return fail(nullptr, PTMCMC_ERR_ARG, "record_rows must be >= 1");
@@ -630,11 +485,8 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     e->sharded = e->Tg > T;
     if (e->Tg > 32767) return fail(nullptr, PTMCMC_ERR_ARG, "ntemps_global must be < 32768");
     if (const char *v = getenv("PTMCMC_MH_VARIANT")) e->mh_variant = atoi(v);
-    if (const char *v = getenv("PTMCMC_PIPE_NPW")) e->pipe_npw = atoi(v);
-    if (const char *v = getenv("PTMCMC_SORT_NC")) {
-        const int nc = atoi(v);
-        if (nc >= 32 && nc <= 256 && nc % 32 == 0) e->sort_nc = nc;
-    }
+    philox_round_keys(cfg->seed, e->rk);
+    e->sorted = sorted_geometry(d, (long long)T * W, e->sm_count, -1, 0);
     const size_t C = (size_t)T * W;
     for (int b = 0; b < 2; ++b) {
         CUDA_TRY(nullptr, dalloc(&e->x[b], C * d));
@@ -697,6 +549,29 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     } else if (cfg->logp_kind != PTMCMC_LOGP_FLAT && cfg->logp_kind != PTMCMC_LOGP_EXTERNAL) {
         return fail(nullptr, PTMCMC_ERR_ARG, "unknown logp_kind %d", cfg->logp_kind);
     }
+    if (d <= MAX_REG_DIM) {  // static tables of the sorted kernel
+        SortedHostTables &tb = e->sorted_tb;
+        tb.d = d;
+        for (int i = 0; i < d; ++i) {
+            tb.mu[i] = cfg->logl_kind == PTMCMC_LOGL_GAUSSIAN ? cfg->logl_params[i] : 0.0;
+            tb.lo[i] = -std::numeric_limits<double>::infinity();
+            tb.hi[i] = std::numeric_limits<double>::infinity();
+            if (cfg->logp_kind == PTMCMC_LOGP_UNIFORM) {
+                // the open interval of an exclusive prior is the closed interval of the neighbouring doubles
+                const double lo = cfg->logp_params[i], hi = cfg->logp_params[d + i];
+                tb.lo[i] = e->p_inclusive ? lo : std::nextafter(lo, std::numeric_limits<double>::infinity());
+                tb.hi[i] = e->p_inclusive ? hi : std::nextafter(hi, -std::numeric_limits<double>::infinity());
+            }
+            for (int j = 0; j < d; ++j) tb.P[i * d + j] = 0.0;
+        }
+        if (cfg->logl_kind == PTMCMC_LOGL_GAUSSIAN) {
+            const double *A = cfg->logl_params + d;
+            for (int i = 0; i < d; ++i) {
+                tb.P[i * d + i] = -0.5 * A[(size_t)i * d + i];
+                for (int j = i + 1; j < d; ++j) tb.P[i * d + j] = -0.5 * (A[(size_t)i * d + j] + A[(size_t)j * d + i]);
+            }
+        }
+    }
     // record window, counters, trace
     const size_t rrows = (size_t)cfg->record_rows * e->ntr * W;
     CUDA_TRY(nullptr, dalloc(&e->d_rec_x, rrows * d));
@@ -742,12 +617,15 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         }
     }
     // tensor-core path: dense Gaussian target, one identity group, box or flat prior
-    e->mma_nt = mma_pick_nt(d);
-    e->mma_ok = cfg->logl_kind == PTMCMC_LOGL_GAUSSIAN && e->identity_group && e->mma_nt > 0 &&
+    e->mma.nt = mma_pick_nt(d);
+    e->mma_ok = cfg->logl_kind == PTMCMC_LOGL_GAUSSIAN && e->identity_group && e->mma.nt > 0 &&
                 (cfg->logp_kind == PTMCMC_LOGP_UNIFORM || cfg->logp_kind == PTMCMC_LOGP_FLAT);
-    if (e->mma_ok) mma_geometry(e);
     if (e->mma_ok) {
-        const size_t nf = (size_t)e->mma_nt * e->mma_nt * 64;
+        mma_geometry(e->mma, 0);
+        e->mma_ok = e->mma.nt > 0;
+    }
+    if (e->mma_ok) {
+        const size_t nf = (size_t)e->mma.nt * e->mma.nt * 64;
         CUDA_TRY(nullptr, dalloc(&e->d_Uf, nf));
         CUDA_TRY(nullptr, dalloc(&e->d_Pf, nf));
         CUDA_TRY(nullptr, dalloc(&e->d_gPfull, (size_t)d * d));
@@ -772,11 +650,10 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
                 Lc[(size_t)i * d + j] = v / ljj;
             }
         }
-        e->mma_tri = spd;
+        e->mma.tri = spd;
         if (spd) Pn = Lc;
         CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_gPfull, Pn.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice, e->stream));
-        frag_build_kernel<<<((int)nf + 255) / 256, 256, 0, e->stream>>>(e->d_gPfull, d, e->mma_nt, 0, e->d_Pf);
-        CUDA_TRY(nullptr, cudaGetLastError());
+        CUDA_TRY(nullptr, launch_frag_build(e->d_gPfull, d, e->mma.nt, 0, e->d_Pf, e->stream));
     }
     const double t_alloc = now();
     // initial factor (ref :138-145)
@@ -1478,6 +1355,71 @@ int32_t ptmcmc_reset_timing(ptmcmc_engine *h)
 }
 
 void *ptmcmc_stream(ptmcmc_engine *h) { return h ? (void *)((Engine *)h)->stream : nullptr; }
+
+const char *ptmcmc_mh_kernel_name(ptmcmc_engine *h)
+{
+    Engine *e = (Engine *)h;
+    if (!e) return "";
+    if (use_mma(e)) {
+        static thread_local char buf[64];
+        snprintf(buf, sizeof buf, "mh_mma_kernel<%d> (%d chains per block)", e->mma.nt, e->mma.nc);
+        return buf;
+    }
+    if (fast_reg_path(e) && e->mh_variant != 2) return sorted_kernel_name(e->d, e->sorted);
+    return "mh_generic_kernel";
+}
+
+int32_t ptmcmc_measure_fp64_peak(int32_t device, double *tflops)
+{
+    if (!tflops) return PTMCMC_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return PTMCMC_ERR_CUDA;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return PTMCMC_ERR_CUDA;
+    const int blocks = 2 * sms, threads = 512, iters = 40000;
+    double *out = nullptr;
+    cudaEvent_t e0, e1;
+    if (cudaMalloc((void **)&out, sizeof(double) * blocks * threads) != cudaSuccess) return PTMCMC_ERR_CUDA;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 0.999999);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * blocks * (double)threads * iters * 8 / (ms * 1e-3) / 1e12;
+        if (rep && tf > best) best = tf;
+    }
+    cudaError_t st = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return st == cudaSuccess ? 0 : PTMCMC_ERR_CUDA;
+}
+
+int32_t ptmcmc_test_normals(int32_t device, const uint64_t *words, int64_t n, double *z0, double *z1)
+{
+    if (!words || !z0 || !z1 || n < 0) return PTMCMC_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return PTMCMC_ERR_CUDA;
+    unsigned long long *dw = nullptr;
+    double *d0 = nullptr, *d1 = nullptr;
+    const size_t m = (size_t)(n ? n : 1);
+    cudaError_t st = cudaMalloc((void **)&dw, 8 * m);
+    if (st == cudaSuccess) st = cudaMalloc((void **)&d0, 8 * m);
+    if (st == cudaSuccess) st = cudaMalloc((void **)&d1, 8 * m);
+    if (st == cudaSuccess) st = cudaMemcpy(dw, words, 8 * (size_t)n, cudaMemcpyHostToDevice);
+    if (st == cudaSuccess) {
+        normals_kernel<<<(unsigned)std::min<long long>((n + 255) / 256 + 1, 4096), 256>>>(dw, n, d0, d1);
+        st = cudaGetLastError();
+    }
+    if (st == cudaSuccess) st = cudaMemcpy(z0, d0, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+    if (st == cudaSuccess) st = cudaMemcpy(z1, d1, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(dw); cudaFree(d0); cudaFree(d1);
+    return st == cudaSuccess ? 0 : PTMCMC_ERR_CUDA;
+}
 
 int32_t ptmcmc_set_timing(ptmcmc_engine *h, int32_t on)
 {

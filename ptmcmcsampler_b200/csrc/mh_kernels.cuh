@@ -5,248 +5,9 @@
 // Follows ref PTMCMCSampler.py: PTMCMCOneStep :601-627, _jump :1048-1067, SCAM :820-876,
 // AM :879-933, DE :936-985, updateChains :321-335.
 #pragma once
-#include "params.h"
-#include "rng.cuh"
+#include "mh_common.cuh"
 
 namespace ptm {
-
-__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xFFF0000000000000LL); }
-__device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7FF0000000000000LL); }
-
-__device__ __forceinline__ int pick_jump(const DevParams &p, Stream &st)
-{
-    // ind = integers(0, len(propCycle)) over the weight-replicated cycle (ref :1007-1008, :1058)
-    const int ind = (int)word_to_int(st.next(), (unsigned long long)p.total_weight);
-    int jump = p.cyc_jump[p.ncycle - 1];
-    for (int i = 0; i < p.ncycle; ++i)
-        if (ind < p.cyc_cum[i]) { jump = p.cyc_jump[i]; break; }
-    return jump;
-}
-
-__device__ __forceinline__ double cov_jump_scale(double prob, double temp)
-{
-    // ref :843-862 / :900-920
-    double scale = (prob > 0.97) ? 10.0 : (prob > 0.9) ? 0.2 : 1.0;
-    if (temp <= 100.0) scale *= sqrt(temp);
-    return scale;
-}
-
-__device__ __forceinline__ bool in_box(double v, double lo, double hi, int inclusive)
-{
-    return inclusive ? (lo <= v && hi >= v) : (lo < v && hi > v);
-}
-
-// updateChains (ref :321-335) for one chain: AM ring slot for the cold rung, thinned record.
-template <typename XGet>
-__device__ __forceinline__ void bookkeep(const DevParams &p, long long it, int t, int w, XGet xget,
-                                         double lnl, double lp, double beta)
-{
-    const int d = p.d, W = p.W;
-    if (t == 0 && p.temp_offset == 0 && p.am) {
-        double *dst = p.am + (size_t)(it % p.cov_update) * d * W + w;
-        for (int k = 0; k < d; ++k) dst[(size_t)k * W] = xget(k);
-    }
-    if (t < p.ntr && it % p.thin == 0) {
-        const long long row = it / p.thin - p.rec_base;
-        if (row >= 0 && row < p.rec_cap) {
-            const size_t r = ((size_t)row * p.ntr + t) * W + w;
-            double *dst = p.rec_x + r * d;
-            for (int k = 0; k < d; ++k) dst[k] = xget(k);
-            p.rec_lnl[r] = lnl;
-            p.rec_lnp[r] = beta * lnl + lp;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Register-resident kernel: one thread per chain, ndim <= DP <= 32, one parameter group that is
-// the identity.  U, sqrt(S), the Gaussian form and the box are staged in shared memory, padded
-// with zeros / infinities to DP so the unrolled loops need no guards.
-// ---------------------------------------------------------------------------------------------
-template <int DP>
-__global__ void __launch_bounds__(MH_THREADS) mh_reg_kernel(const DevParams p)
-{
-    extern __shared__ double sm[];
-    double *Us = sm;                 // [DP][DP]
-    double *Ps = Us + DP * DP;       // [DP][DP] upper-triangular Gaussian form
-    double *sS = Ps + DP * DP;       // [DP]
-    double *mus = sS + DP;
-    double *los = mus + DP;
-    double *his = los + DP;
-    const int d = p.d, W = p.W, T = p.T;
-    for (int idx = threadIdx.x; idx < DP * DP; idx += blockDim.x) {
-        const int i = idx / DP, j = idx % DP;
-        const bool in = (i < d && j < d);
-        Us[idx] = in ? p.U[i * d + j] : 0.0;
-        Ps[idx] = (in && p.logl_kind == LOGL_GAUSSIAN) ? p.g_P[i * d + j] : 0.0;
-    }
-    for (int k = threadIdx.x; k < DP; k += blockDim.x) {
-        const bool in = k < d;
-        sS[k] = in ? p.sqrtS[k] : 0.0;
-        mus[k] = (in && p.logl_kind == LOGL_GAUSSIAN) ? p.g_mu[k] : 0.0;
-        los[k] = (in && p.logp_kind == LOGP_UNIFORM) ? p.p_lo[k] : neg_inf();
-        his[k] = (in && p.logp_kind == LOGP_UNIFORM) ? p.p_hi[k] : pos_inf();
-    }
-    __syncthreads();
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= (long long)T * W) return;
-    const int t = (int)(c / W), w = (int)(c % W);
-    const uint32_t gw = (uint32_t)(p.walker_offset + w), gt = (uint32_t)(p.temp_offset + t);
-    const double temp = p.mh_temp[t];
-    const double beta = 1.0 / temp;
-    const int inclusive = p.p_inclusive;
-
-    double x[DP];
-    const double *xg = p.x + (size_t)t * d * W + w;
-#pragma unroll
-    for (int k = 0; k < DP; ++k) x[k] = (k < d) ? xg[(size_t)k * W] : 0.0;
-    double lnl = p.lnl[c], lp = p.lp[c];
-    unsigned np0 = 0, np1 = 0, np2 = 0, na0 = 0, na1 = 0, na2 = 0;
-
-    for (long long it = p.it0; it <= p.it1; ++it) {
-        Stream st(p.seed, PURPOSE_MH, (unsigned long long)it, gw, gt);
-        const int jump = pick_jump(p, st);
-        (void)word_to_int(st.next(), 1ull);  // jumpind = integers(0, 1): the single group
-        double q[DP];
-        if (jump == JUMP_AM) {
-            const double prob = word_to_unit(st.next());
-            const double cd = 2.4 / sqrt(2.0 * d) * cov_jump_scale(prob, temp);
-            double dl[DP];
-#pragma unroll
-            for (int j = 0; j < DP; j += 2) {
-                double z0 = 0.0, z1 = 0.0;
-                if (j < d) word_to_normals(st.next(), z0, z1);
-                dl[j] = z0 * cd * sS[j];
-                if (j + 1 < DP) dl[j + 1] = z1 * cd * sS[j + 1];
-            }
-            // q = U (U^T x + delta) == x + U delta for orthogonal U (ref :923-931)
-#pragma unroll
-            for (int i = 0; i < DP; ++i) {
-                double a = x[i];
-#pragma unroll
-                for (int j = 0; j < DP; ++j) a = fma(Us[i * DP + j], dl[j], a);
-                q[i] = a;
-            }
-        } else if (jump == JUMP_SCAM) {
-            const double prob = word_to_unit(st.next());
-            const double scale = cov_jump_scale(prob, temp);
-            const int k = (int)word_to_int(st.next(), (unsigned long long)d);
-            const double cd = 2.4 / sqrt(2.0) * scale;
-            double z0, z1;
-            word_to_normals(st.next(), z0, z1);
-            const double coef = z0 * cd * sS[k];
-#pragma unroll
-            for (int i = 0; i < DP; ++i) q[i] = fma(coef, Us[i * DP + k], x[i]);
-        } else {  // DE (ref :936-985)
-            const unsigned long long bufsize = (unsigned long long)p.burn * (unsigned long long)W;
-            const unsigned long long mm = word_to_int(st.next(), bufsize);
-            unsigned long long nn = word_to_int(st.next(), bufsize);
-            while (mm == nn) nn = word_to_int(st.next(), bufsize);
-            const double prob = word_to_unit(st.next());
-            double scale = 1.0;
-            if (!(prob > 0.5)) scale = word_to_unit(st.next()) * 2.4 / sqrt(2.0 * d) * sqrt(1.0 / beta);
-            const unsigned long long sm_ = mm / W, sn_ = nn / W;
-            const double *bm = p.de + (((sm_ + p.de_head) % p.burn) * W + (mm - sm_ * W)) * d;
-            const double *bn = p.de + (((sn_ + p.de_head) % p.burn) * W + (nn - sn_ * W)) * d;
-#pragma unroll
-            for (int i = 0; i < DP; ++i) {
-                const double sigma = (i < d) ? (__ldg(bm + i) - __ldg(bn + i)) : 0.0;
-                q[i] = fma(scale, sigma, x[i]);
-            }
-        }
-        // log-prior (ref :605-608)
-        bool inside = true;
-#pragma unroll
-        for (int k = 0; k < DP; ++k) inside = inside && in_box(q[k], los[k], his[k], inclusive);
-        double lpn = inside ? p.p_inside : neg_inf();
-        double lnln = 0.0, lnpn = neg_inf();
-        if (inside) {  // ref :610-612: logl only inside the prior support
-            if (p.logl_kind == LOGL_GAUSSIAN) {
-                double dl[DP];
-#pragma unroll
-                for (int k = 0; k < DP; ++k) dl[k] = q[k] - mus[k];
-                double acc = 0.0;
-#pragma unroll
-                for (int i = 0; i < DP; ++i) {
-                    double row = 0.0;
-#pragma unroll
-                    for (int j = i; j < DP; ++j) row = fma(Ps[i * DP + j], dl[j], row);
-                    acc = fma(dl[i], row, acc);
-                }
-                lnln = acc + p.g_offset;
-            } else if (p.logl_kind == LOGL_CURVED) {
-                double tot = 0.0;
-#pragma unroll
-                for (int b = 0; b + 1 < DP; b += 2) {
-                    if (b + 1 < d) {
-                        const double a = q[b], y = q[b + 1];
-                        const double t0 = 9.0 + 4.0 * a * a + 9.0 * y;
-                        const double ll = exp(-a * a - t0 * t0) +
-                                          0.5 * exp(-8.0 * a * a - 8.0 * (y - 2.0) * (y - 2.0));
-                        tot += log(ll);
-                    }
-                }
-                lnln = tot;
-            } else {  // LOGL_ROSENBROCK
-                double tot = 0.0;
-#pragma unroll
-                for (int i = 0; i + 1 < DP; ++i) {
-                    if (i + 1 < d) {
-                        const double a = q[i + 1] - q[i] * q[i], b = 1.0 - q[i];
-                        tot -= 100.0 * a * a + b * b;
-                    }
-                }
-                lnln = tot / 20.0;
-            }
-            lnpn = beta * lnln + lpn;
-        }
-        // Hastings test (ref :614-622); qxy = 0 for the built-in proposals
-        const double lnp0 = beta * lnl + lp;
-        const double diff = lnpn - lnp0;
-        const double u = word_to_unit(st.next());
-        const bool accept = diff > log(u);
-        if (accept) {
-#pragma unroll
-            for (int k = 0; k < DP; ++k) x[k] = q[k];
-            lnl = lnln;
-            lp = lpn;
-        }
-        np0 += (jump == JUMP_SCAM); np1 += (jump == JUMP_AM); np2 += (jump == JUMP_DE);
-        if (accept) { na0 += (jump == JUMP_SCAM); na1 += (jump == JUMP_AM); na2 += (jump == JUMP_DE); }
-        if (p.trace && it - 1 < p.trace_cap)
-            p.trace[((size_t)(it - 1) * T + t) * W + w] = (unsigned char)(jump | ((int)accept << 7));
-        if (it < p.it1 || p.tail) {
-            // x[] must stay in registers: the accessor is unrolled by hand
-            if (t == 0 && p.temp_offset == 0 && p.am) {
-                double *dst = p.am + (size_t)(it % p.cov_update) * d * W + w;
-#pragma unroll
-                for (int k = 0; k < DP; ++k)
-                    if (k < d) dst[(size_t)k * W] = x[k];
-            }
-            if (t < p.ntr && it % p.thin == 0) {
-                const long long row = it / p.thin - p.rec_base;
-                if (row >= 0 && row < p.rec_cap) {
-                    const size_t r = ((size_t)row * p.ntr + t) * W + w;
-                    double *dst = p.rec_x + r * d;
-#pragma unroll
-                    for (int k = 0; k < DP; ++k)
-                        if (k < d) dst[k] = x[k];
-                    p.rec_lnl[r] = lnl;
-                    p.rec_lnp[r] = beta * lnl + lp;
-                }
-            }
-        }
-    }
-    double *xo = p.x + (size_t)t * d * W + w;
-#pragma unroll
-    for (int k = 0; k < DP; ++k)
-        if (k < d) xo[(size_t)k * W] = x[k];
-    p.lnl[c] = lnl;
-    p.lp[c] = lp;
-    const size_t TW = (size_t)T * W;
-    p.prop[0 * TW + c] += np0; p.prop[1 * TW + c] += np1; p.prop[2 * TW + c] += np2;
-    p.acc[0 * TW + c] += na0; p.acc[1 * TW + c] += na1; p.acc[2 * TW + c] += na2;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Generic path (any ndim <= MAX_GENERIC_DIM, arbitrary parameter groups): thread per chain with
@@ -370,7 +131,7 @@ __global__ void __launch_bounds__(MH_THREADS) mh_generic_kernel(const DevParams 
     double lnl = p.lnl[c], lp = p.lp[c];
     const size_t TW = (size_t)T * W;
     for (long long it = p.it0; it <= p.it1; ++it) {
-        Stream st(p.seed, PURPOSE_MH, (unsigned long long)it, gw, gt);
+        Stream st(p, PURPOSE_MH, (unsigned long long)it, gw, gt);
         for (int k = 0; k < d; ++k) q[k] = x[k];
         const int jump = propose_generic(p, st, temp, beta, x, q, dl);
         const double lpn = eval_logp_generic(p, q);
@@ -381,8 +142,7 @@ __global__ void __launch_bounds__(MH_THREADS) mh_generic_kernel(const DevParams 
         }
         const double lnp0 = beta * lnl + lp;
         const double diff = lnpn - lnp0;
-        const double u = word_to_unit(st.next());
-        const bool accept = diff > log(u);
+        const bool accept = hastings_accept(diff, st.next());
         if (accept) {
             for (int k = 0; k < d; ++k) x[k] = q[k];
             lnl = lnln;
@@ -468,7 +228,7 @@ __global__ void __launch_bounds__(MH_THREADS) propose_kernel(const DevParams p, 
     double x[MAX_GENERIC_DIM], q[MAX_GENERIC_DIM], dl[MAX_GENERIC_DIM];
     const double *xg = p.x + (size_t)t * d * W + w;
     for (int k = 0; k < d; ++k) q[k] = x[k] = xg[(size_t)k * W];
-    Stream st(p.seed, PURPOSE_MH, (unsigned long long)p.it0, (uint32_t)(p.walker_offset + w),
+    Stream st(p, PURPOSE_MH, (unsigned long long)p.it0, (uint32_t)(p.walker_offset + w),
               (uint32_t)(p.temp_offset + t));
     const int jump = propose_generic(p, st, temp, 1.0 / temp, x, q, dl);
     for (int k = 0; k < d; ++k) q_out[c * d + k] = q[k];
@@ -486,7 +246,7 @@ __global__ void __launch_bounds__(MH_THREADS) accept_kernel(const DevParams p, c
     if (c >= (long long)T * W) return;
     const int t = (int)(c / W), w = (int)(c % W);
     const double beta = 1.0 / p.mh_temp[t];
-    Stream st(p.seed, PURPOSE_MH, (unsigned long long)p.it0, (uint32_t)(p.walker_offset + w),
+    Stream st(p, PURPOSE_MH, (unsigned long long)p.it0, (uint32_t)(p.walker_offset + w),
               (uint32_t)(p.temp_offset + t));
     st.seek(word_pos[c]);
     const int jump = jump_in[c];
@@ -501,8 +261,7 @@ __global__ void __launch_bounds__(MH_THREADS) accept_kernel(const DevParams p, c
     }
     const double lnp0 = beta * p.lnl[c] + p.lp[c];
     const double diff = lnpn - lnp0 + qxy[c];
-    const double u = word_to_unit(st.next());
-    const bool accept = diff > log(u);
+    const bool accept = hastings_accept(diff, st.next());
     const size_t TW = (size_t)T * W;
     if (accept) {
         double *xg = p.x + (size_t)t * d * W + w;

@@ -26,8 +26,7 @@
 // Draw order and arithmetic of every scalar follow the thread-per-chain kernels (mh_kernels.cuh), so the
 // jump / accept / swap streams are identical; the quadratic form differs in summation order only.
 #pragma once
-#include "mh_kernels.cuh"
-#include "mh_sorted_kernel.cuh"
+#include "mh_common.cuh"
 #include "mma_f64.cuh"
 
 namespace ptm {
@@ -100,8 +99,6 @@ struct MmaArgs {
     MmaLayout L;          // computed on the host: the offsets are then plain constant-bank operands
 };
 
-__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-
 // MINB (blocks per SM the register allocation must allow): small ndim runs many small blocks to hide the
 // fp64 latency of the draw phase; large ndim needs the registers for the fragment arrays.
 template <int NT, bool USMEM, int MINB>
@@ -129,7 +126,7 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
     double *s_sca = reinterpret_cast<double *>(smem_raw + L.sca);    // AM: cd; SCAM: coefficient; DE: scale
     unsigned long long *s_rowm = reinterpret_cast<unsigned long long *>(smem_raw + L.rowm);  // DE row offsets;
     unsigned long long *s_rown = reinterpret_cast<unsigned long long *>(smem_raw + L.rown);  // SCAM: rowm = k
-    double *s_logu = reinterpret_cast<double *>(smem_raw + L.logu);
+    unsigned long long *s_uword = reinterpret_cast<unsigned long long *>(smem_raw + L.logu);  // accept-uniform word
     int *s_ct = reinterpret_cast<int *>(smem_raw + L.ct);
     int *s_cw = reinterpret_cast<int *>(smem_raw + L.cw);
     unsigned *s_cnt = reinterpret_cast<unsigned *>(smem_raw + L.cnt);
@@ -181,7 +178,6 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
     const bool recorded = have && tme < p.ntr;
     const int npairs = (d + 1) >> 1, uword = 3 + npairs, am_tasks = ((uword + 2) >> 1) - 1;
     const unsigned long long bufsize = (unsigned long long)p.burn * (unsigned long long)W;
-    const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
     const int ntiles = nc >> 3;
     __syncthreads();
 
@@ -212,7 +208,7 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
         int *count = s_count + 4 * (int)(it & 1);
         int kind = 3;
         if (have) {
-            Stream st(p.seed, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + wme),
+            Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + wme),
                       (uint32_t)(p.temp_offset + tme));
             const int jump = pick_jump(p, st);
             s_jt[tid] = (unsigned char)jump;
@@ -244,9 +240,9 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
                     const int qa = q - nSD;
                     const int ai = qa % nA, b = 1 + qa / nA;
                     const int cl = s_list[ai];
-                    const uint4 blk = philox4x32_10((uint32_t)it, (PURPOSE_MH << 24) | (uint32_t)b,
+                    const uint4 blk = philox4x32_10(p, (uint32_t)it, (PURPOSE_MH << 24) | (uint32_t)b,
                                                     (uint32_t)(p.walker_offset + s_cw[cl]),
-                                                    (uint32_t)(p.temp_offset + s_ct[cl]), k0, k1);
+                                                    (uint32_t)(p.temp_offset + s_ct[cl]));
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int wi = 2 * b + h;
@@ -261,14 +257,14 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
                             zq[cl * ld + j] = z0;
                             if (j + 1 < KP) zq[cl * ld + j + 1] = z1;
                         } else if (wi == uword) {
-                            s_logu[cl] = log(word_to_unit(word));
+                            s_uword[cl] = word;
                         }
                     }
                 } else {
                     const bool scam = q >= nD;
                     const int cl = scam ? s_list[nc + q - nD] : s_list[2 * nc + q];
                     const double temp = s_temp[cl];
-                    Stream st(p.seed, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + s_cw[cl]),
+                    Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + s_cw[cl]),
                               (uint32_t)(p.temp_offset + s_ct[cl]));
                     st.j = 2;
                     if (scam) {  // ref :839-873
@@ -299,7 +295,7 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
                         s_rowm[cl] = om;
                         s_rown[cl] = on;
                     }
-                    s_logu[cl] = log(word_to_unit(st.next()));
+                    s_uword[cl] = st.next();
                 }
             }
         }
@@ -478,7 +474,7 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
             const double lnpn = inside ? beta * lnln + lpn : neg_inf();  // ref :607-612
             const double lnp0 = beta * s_lnl[cl] + s_lp[cl];
             const double diff = lnpn - lnp0;
-            const bool accept = live && (diff > s_logu[cl]);  // ref :614-616
+            const bool accept = live && hastings_accept(diff, s_uword[cl]);  // ref :614-616
             __syncwarp();  // every lane of the quad has read lnl / lp / jt before lane t == 0 updates them
             if (accept) {
 #pragma unroll

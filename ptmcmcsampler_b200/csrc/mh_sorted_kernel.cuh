@@ -3,136 +3,146 @@
 // The three built-in proposals cost very different amounts (AM: d normals + a d x d mat-vec, SCAM and
 // DE: O(d)), and every chain picks its proposal independently each iteration (ref _jump :1048-1067),
 // so a thread-per-chain warp executes all three paths every step.  Because the draws are
-// counter-based, a chain's jump kind for an iteration is known before any state is touched.  Each
-// iteration the block therefore
-//   A. lets thread i draw the jump kind of "its" chain i and append the chain to that kind's list
-//      (warp-aggregated shared-memory atomics), after doing the previous iteration's
-//      buffer/record bookkeeping for chain i with coalesced global stores;
-//   B. lets thread r process the r-th chain of the concatenated lists (AM | SCAM | DE), so that
-//      warps are proposal-uniform except at the two list boundaries.
-// Chain state (x, lnL, lnprior, counters) lives in shared memory for the whole launch; two block
-// barriers per iteration.  Results are identical to the thread-per-chain kernel draw for draw.
+// counter-based, a chain's jump kind for an iteration is known before any state is touched.  Per
+// iteration `it` a block of nc chains therefore runs
+//   B(it)     thread r steps the r-th chain of the concatenated lists (AM | SCAM | DE) of iteration it, so that
+//             warps are proposal-uniform except at the two list boundaries, and does that chain's
+//             buffer / record bookkeeping (ref updateChains :321-335) with the state it just decided;
+//   A(it+1)   the same thread then draws the jump kind of iteration it+1 for the chain it OWNS (chain tid) and
+//             appends it to that kind's list (warp-aggregated shared-memory atomics); this needs no chain state,
+//             so the short SCAM / DE warps do it while the AM warps are still stepping;
+// and ONE block barrier.  Lists are double-buffered, their lengths triple-buffered.  Chain state (x, lnL,
+// lnprior, counters) lives in shared memory for the whole launch.  The static tables of the target -- the
+// Gaussian form (upper triangle, -1/2 folded in), its mean and the prior box -- arrive as a kernel parameter
+// and are read as constant-bank operands of the fp64 instructions: the shared-memory data pipe is the
+// busiest unit of this kernel (57-65 % in the round-1 capture) and those tables were 40 % of its wavefronts.
+// The eigen-factor changes at every covariance update on the device, so it stays in shared memory.
+// Results are identical to the thread-per-chain kernel draw for draw.
 #pragma once
-#include "mh_kernels.cuh"
+#include "mh_common.cuh"
 
 namespace ptm {
 
-// physical row of logical DE-history row r (ring with head slot); 32-bit arithmetic when it fits
-__device__ __forceinline__ unsigned long long de_row_offset(unsigned long long r, unsigned long long bufsize, int W,
-                                                            long long burn, long long head)
-{
-    unsigned long long slot, wsel;
-    if (bufsize <= 0xFFFFFFFFull) {
-        const unsigned r32 = (unsigned)r, s32 = r32 / (unsigned)W;
-        slot = s32;
-        wsel = r32 - s32 * (unsigned)W;
-    } else {
-        slot = r / (unsigned long long)W;
-        wsel = r - slot * (unsigned long long)W;
-    }
-    slot += (unsigned long long)head;
-    if (slot >= (unsigned long long)burn) slot -= (unsigned long long)burn;
-    return slot * (unsigned long long)W + wsel;
-}
+// static per engine; d < DP is padded with zeros / an unbounded interval
+template <int DP>
+struct SortedTables {
+    double P[DP * (DP + 1) / 2];  // upper triangle of the Gaussian form, packed by rows
+    double mu[DP];
+    double lo[DP], hi[DP];        // prior box as an inclusive interval (exclusive bounds moved one ulp inwards)
+};
 
 template <int DP, int NC>
 struct SortedSmem {
-    double Us[DP * DP];
-    double Ps[DP * DP];
-    double sS[DP], mus[DP], los[DP], his[DP];
-    double xs[DP * NC];      // [k][chain]
+    double Us[DP * DP];                        // eigenvectors, row-major
+    double sS[DP];
+    double xs[DP * NC];                        // [k][chain]
     double lnl[NC], lp[NC];
-    double temp[NC], beta[NC];
-    int ct[NC], cw[NC];      // rung and walker of each chain of the block
-    unsigned cnt[6 * NC];    // [prop scam, am, de, acc scam, am, de][chain]
-    unsigned short list[3 * NC];
-    unsigned char jt[NC];    // jump id | accepted << 7 of the current iteration
-    int count[8];            // list lengths (AM, SCAM, DE), double-buffered by iteration parity
+    double beta[NC], sct[NC], dsc[NC];         // 1/T; sqrt(T) if T <= 100 else 1; 2.4/sqrt(2d) * sqrt(T)
+    unsigned long long cnt[3 * NC];            // per jump: proposed (low word) | accepted (high word)
+    int ct[NC], cw[NC];                        // rung and walker of each chain of the block
+    unsigned short list[2][3 * NC];            // per-kind lists of two consecutive iterations
+    int count[3][4];                           // list lengths (AM, SCAM, DE) of three consecutive iterations
 };
 
-template <int DP, int NC, int MINB>
-__global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const DevParams p)
+template <int DP>
+__device__ __forceinline__ constexpr int tri_index(int i, int j) { return i * DP - (i * (i - 1)) / 2 + (j - i); }
+
+// log-likelihood of the built-in targets from a full proposal in registers
+template <int DP>
+__device__ __forceinline__ double logl_builtin(const DevParams &p, const SortedTables<DP> &tb, const double (&q)[DP])
 {
+    const int d = p.d;
+    if (p.logl_kind == LOGL_GAUSSIAN) {
+        double dv[DP];
+#pragma unroll
+        for (int j = 0; j < DP; ++j) dv[j] = q[j] - tb.mu[j];
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < DP; ++i) {
+            double row = 0.0;
+#pragma unroll
+            for (int j = i; j < DP; ++j) row = fma(tb.P[tri_index<DP>(i, j)], dv[j], row);
+            acc = fma(dv[i], row, acc);
+        }
+        return acc + p.g_offset;
+    }
+    if (p.logl_kind == LOGL_CURVED) {
+        double tot = 0.0;
+#pragma unroll
+        for (int b = 0; b + 1 < DP; b += 2) {
+            if (b + 1 < d) {
+                const double a = q[b], y = q[b + 1];
+                const double t0 = 9.0 + 4.0 * a * a + 9.0 * y;
+                tot += log(exp(-a * a - t0 * t0) + 0.5 * exp(-8.0 * a * a - 8.0 * (y - 2.0) * (y - 2.0)));
+            }
+        }
+        return tot;
+    }
+    double tot = 0.0;
+#pragma unroll
+    for (int i = 0; i + 1 < DP; ++i) {
+        if (i + 1 < d) {
+            const double a = q[i + 1] - q[i] * q[i], b = 1.0 - q[i];
+            tot -= 100.0 * a * a + b * b;
+        }
+    }
+    return tot / 20.0;
+}
+
+template <int DP, int NC, int MINB>
+__global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const __grid_constant__ DevParams p,
+                                                             const __grid_constant__ SortedTables<DP> tb, const int nc)
+{
+    static_assert(NC % 32 == 0, "whole warps");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortedSmem<DP, NC> &S = *reinterpret_cast<SortedSmem<DP, NC> *>(smem_raw);
+    using Smem = SortedSmem<DP, NC>;
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int d = p.d, W = p.W, T = p.T;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int nc = blockDim.x;  // chains of this block (<= NC, the capacity the arrays are laid out for)
-    for (int idx = tid; idx < DP * DP; idx += nc) {
+    for (int idx = tid; idx < DP * DP; idx += NC) {
         const int i = idx / DP, j = idx % DP;
-        const bool in = (i < d && j < d);
-        S.Us[idx] = in ? p.U[i * d + j] : 0.0;
-        S.Ps[idx] = (in && p.logl_kind == LOGL_GAUSSIAN) ? p.g_P[i * d + j] : 0.0;
+        S.Us[idx] = (i < d && j < d) ? p.U[i * d + j] : 0.0;
     }
-    for (int k = tid; k < DP; k += nc) {
-        const bool in = k < d;
-        S.sS[k] = in ? p.sqrtS[k] : 0.0;
-        S.mus[k] = (in && p.logl_kind == LOGL_GAUSSIAN) ? p.g_mu[k] : 0.0;
-        S.los[k] = (in && p.logp_kind == LOGP_UNIFORM) ? p.p_lo[k] : neg_inf();
-        S.his[k] = (in && p.logp_kind == LOGP_UNIFORM) ? p.p_hi[k] : pos_inf();
-    }
+    for (int k = tid; k < DP; k += NC) S.sS[k] = (k < d) ? p.sqrtS[k] : 0.0;
     const long long TW = (long long)T * W;
     const long long c0 = (long long)blockIdx.x * nc;       // first chain of this block
     const long long cme = c0 + tid;                        // the chain this thread owns in phase A
-    const bool have = cme < TW;
+    const bool have = tid < nc && cme < TW;
     const int tme = have ? (int)(cme / W) : 0, wme = have ? (int)(cme % W) : 0;
+    const double c_am = 2.4 / sqrt(2.0 * d);
     if (have) {
         const double *xg = p.x + (size_t)tme * d * W + wme;
 #pragma unroll
         for (int k = 0; k < DP; ++k) S.xs[k * NC + tid] = (k < d) ? xg[(size_t)k * W] : 0.0;
         S.lnl[tid] = p.lnl[cme];
         S.lp[tid] = p.lp[cme];
-        S.temp[tid] = p.mh_temp[tme];
-        S.beta[tid] = 1.0 / p.mh_temp[tme];
+        const double temp = p.mh_temp[tme], beta = 1.0 / temp;
+        S.beta[tid] = beta;
+        S.sct[tid] = (temp <= 100.0) ? sqrt(temp) : 1.0;   // ref :861-862, :919-920
+        S.dsc[tid] = c_am * sqrt(1.0 / beta);               // ref :976
         S.ct[tid] = tme;
         S.cw[tid] = wme;
     }
 #pragma unroll
-    for (int j = 0; j < 6; ++j) S.cnt[j * NC + tid] = 0;
-    if (tid < 8) S.count[tid] = 0;
-    const int inclusive = p.p_inclusive;
+    for (int j = 0; j < 3; ++j) S.cnt[j * NC + tid] = 0ull;
+    if (tid < 12) (&S.count[0][0])[tid] = 0;
     // incremental forms of it % covUpdate, it % thin and it / thin (64-bit div/mod is ~100 instructions)
-    long long am_slot = p.it0 % p.cov_update, thin_ctr = p.it0 % p.thin, row = p.it0 / p.thin - p.rec_base;
-    const bool cold = have && tme == 0 && p.temp_offset == 0 && p.am != nullptr;
-    const bool recorded = have && tme < p.ntr;
+    // (positions of iteration it0 - 1; the loop advances them first)
+    int am_slot = (int)((p.it0 - 1) % p.cov_update), thin_ctr = (int)((p.it0 - 1) % p.thin);
+    long long row = (p.it0 - 1) / p.thin - p.rec_base;
+    const int cov_update = (int)p.cov_update, thin = (int)p.thin;  // both < 2^31 (checked at create)
+    const bool ring = p.temp_offset == 0 && p.am != nullptr;
+    const unsigned long long bufsize = (unsigned long long)p.burn * (unsigned long long)W;
+    const bool small_buf = bufsize <= 0xFFFFFFFFull;
     __syncthreads();
 
-    for (long long it = p.it0; it <= p.it1 + 1; ++it) {
-        // ---- phase A: bookkeeping of iteration it-1 for the owned chain (ref :627), then the
-        //      jump kind of iteration it (ref :1058) and the per-kind lists
-        if (have && it > p.it0) {
-            const long long ib = it - 1;
-            if (p.trace && ib - 1 < p.trace_cap) p.trace[((size_t)(ib - 1) * T + tme) * W + wme] = S.jt[tid];
-            if (ib < p.it1 || p.tail) {
-                if (cold) {
-                    double *dst = p.am + (size_t)am_slot * d * W + wme;
-#pragma unroll
-                    for (int k = 0; k < DP; ++k)
-                        if (k < d) dst[(size_t)k * W] = S.xs[k * NC + tid];
-                }
-                if (recorded && thin_ctr == 0 && row >= 0 && row < p.rec_cap) {
-                    const size_t r = ((size_t)row * p.ntr + tme) * W + wme;
-                    double *dst = p.rec_x + r * d;
-#pragma unroll
-                    for (int k = 0; k < DP; ++k)
-                        if (k < d) dst[k] = S.xs[k * NC + tid];
-                    p.rec_lnl[r] = S.lnl[tid];
-                    p.rec_lnp[r] = S.beta[tid] * S.lnl[tid] + S.lp[tid];
-                }
-            }
-        }
-        if (it > p.it0) {  // advance the ring slot / thinning counters from iteration it-1 to it
-            if (++am_slot == p.cov_update) am_slot = 0;
-            if (++thin_ctr == p.thin) { thin_ctr = 0; ++row; }
-        }
-        if (it > p.it1) break;
-        int *count = S.count + 4 * (int)(it & 1);
+    // jump kind of iteration `it` for the owned chain (ref :1058) into the lists of buffer (lb, cb)
+    auto draw_kind = [&](long long it, int lb, int cb) {
         int kind = 3;  // none
         if (have) {
-            Stream st(p.seed, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + wme),
+            Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + wme),
                       (uint32_t)(p.temp_offset + tme));
             const int jump = pick_jump(p, st);
-            S.jt[tid] = (unsigned char)jump;
             kind = (jump == JUMP_AM) ? 0 : (jump == JUMP_SCAM) ? 1 : 2;
         }
 #pragma unroll
@@ -141,27 +151,37 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const DevParams p)
             if (m) {
                 int base = 0;
                 const int leader = __ffs(m) - 1;
-                if (lane == leader) base = atomicAdd(&count[kk], __popc(m));
+                if (lane == leader) base = atomicAdd(&S.count[cb][kk], __popc(m));
                 base = __shfl_sync(0xffffffffu, base, leader);
-                if (kind == kk) S.list[kk * NC + base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)tid;
+                if (kind == kk) S.list[lb][kk * NC + base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)tid;
             }
         }
-        __syncthreads();
-        // ---- phase B: thread r processes the r-th chain of (AM | SCAM | DE)
-        const int nA = count[0], nS = count[1], nD = count[2];
-        if (tid < 4) S.count[4 * (int)((it + 1) & 1) + tid] = 0;  // next iteration's counters
+    };
+    draw_kind(p.it0, 0, 0);
+    __syncthreads();
+
+    int lb = 0, cb = 0;  // list / count buffers of the current iteration
+    for (long long it = p.it0; it <= p.it1; ++it) {
+        // buffer / record positions of iteration it (ref :327-335)
+        if (++am_slot == cov_update) am_slot = 0;
+        if (++thin_ctr == thin) { thin_ctr = 0; ++row; }
+        const bool keep = it < p.it1 || p.tail;  // the swap kernel does the last iteration's bookkeeping otherwise
+        const int cb2 = (cb == 0) ? 2 : cb - 1;  // buffer of iteration it+2 == it-1: everyone has read it
+        if (tid < 4) S.count[cb2][tid] = 0;
+        const int nA = S.count[cb][0], nS = S.count[cb][1], nD = S.count[cb][2];
+        const unsigned short *list = S.list[lb];
+        // ---- phase B: thread r steps the r-th chain of (AM | SCAM | DE)
         if (tid < nA + nS + nD) {
             const int kindr = (tid < nA) ? 0 : (tid < nA + nS) ? 1 : 2;
-            const int cl = (kindr == 0) ? S.list[tid] : (kindr == 1) ? S.list[NC + tid - nA] : S.list[2 * NC + tid - nA - nS];
+            const int cl = (kindr == 0) ? list[tid] : (kindr == 1) ? list[NC + tid - nA] : list[2 * NC + tid - nA - nS];
             const int t = S.ct[cl], w = S.cw[cl];
-            const double temp = S.temp[cl], beta = S.beta[cl];
-            Stream st(p.seed, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + w),
-                      (uint32_t)(p.temp_offset + t));
+            const double beta = S.beta[cl];
+            Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + w), (uint32_t)(p.temp_offset + t));
             st.j = 2;  // words 0 (jump index) and 1 (group index of the single group) are spent
             double q[DP];
             if (kindr == 0) {  // AM (ref :879-933)
                 const double prob = word_to_unit(st.next());
-                const double cd = 2.4 / sqrt(2.0 * d) * cov_jump_scale(prob, temp);
+                const double cd = c_am * (((prob > 0.97) ? 10.0 : (prob > 0.9) ? 0.2 : 1.0) * S.sct[cl]);
                 // q = x + U delta accumulated column pair by column pair as the normals are drawn (same
                 // j order per row as a row-wise dot product, so the same bits): no delta array stays live
                 // and the draw of pair j+1 overlaps the 2 d FMAs of pair j
@@ -181,8 +201,8 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const DevParams p)
                 }
             } else if (kindr == 1) {  // SCAM (ref :820-876)
                 const double prob = word_to_unit(st.next());
-                const double scale = cov_jump_scale(prob, temp);
-                const int k = (int)word_to_int(st.next(), (unsigned long long)d);
+                const double scale = ((prob > 0.97) ? 10.0 : (prob > 0.9) ? 0.2 : 1.0) * S.sct[cl];
+                const int k = (int)word_to_int32(st.next(), (uint32_t)d);
                 const double cd = 2.4 / sqrt(2.0) * scale;
                 double z0, z1;
                 word_to_normals(st.next(), z0, z1);
@@ -190,15 +210,22 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const DevParams p)
 #pragma unroll
                 for (int i = 0; i < DP; ++i) q[i] = fma(coef, S.Us[i * DP + k], S.xs[i * NC + cl]);
             } else {  // DE (ref :936-985)
-                const unsigned long long bufsize = (unsigned long long)p.burn * (unsigned long long)W;
-                const unsigned long long mm = word_to_int(st.next(), bufsize);
-                unsigned long long nn = word_to_int(st.next(), bufsize);
-                while (mm == nn) nn = word_to_int(st.next(), bufsize);
-                const double prob = word_to_unit(st.next());
-                double scale = 1.0;
-                if (!(prob > 0.5)) scale = word_to_unit(st.next()) * 2.4 / sqrt(2.0 * d) * sqrt(1.0 / beta);
+                unsigned long long mm, nn;
+                if (small_buf) {
+                    const uint32_t bs = (uint32_t)bufsize;
+                    mm = word_to_int32(st.next(), bs);
+                    nn = word_to_int32(st.next(), bs);
+                    while (mm == nn) nn = word_to_int32(st.next(), bs);
+                } else {
+                    mm = word_to_int(st.next(), bufsize);
+                    nn = word_to_int(st.next(), bufsize);
+                    while (mm == nn) nn = word_to_int(st.next(), bufsize);
+                }
                 const double *bm = p.de + de_row_offset(mm, bufsize, W, p.burn, p.de_head) * d;
                 const double *bn = p.de + de_row_offset(nn, bufsize, W, p.burn, p.de_head) * d;
+                const double prob = word_to_unit(st.next());
+                double scale = 1.0;
+                if (!(prob > 0.5)) scale = word_to_unit(st.next()) * S.dsc[cl];  // ref :969-976
                 if ((d & 1) == 0) {  // rows are 16-byte aligned: half as many load instructions
 #pragma unroll
                     for (int i = 0; i < DP; i += 2) {
@@ -220,59 +247,60 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const DevParams p)
             }
             bool inside = true;
 #pragma unroll
-            for (int k = 0; k < DP; ++k) inside = inside && in_box(q[k], S.los[k], S.his[k], inclusive);
-            const double lpn = inside ? p.p_inside : neg_inf();
+            for (int k = 0; k < DP; ++k) inside = inside & (q[k] >= tb.lo[k]) & (q[k] <= tb.hi[k]);
+            double lpn = inside ? p.p_inside : neg_inf();
             double lnln = 0.0, lnpn = neg_inf();
             if (inside) {
-                if (p.logl_kind == LOGL_GAUSSIAN) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int i = 0; i < DP; ++i) {
-                        double row = 0.0;
-#pragma unroll
-                        for (int j = i; j < DP; ++j) row = fma(S.Ps[i * DP + j], q[j] - S.mus[j], row);
-                        acc = fma(q[i] - S.mus[i], row, acc);
-                    }
-                    lnln = acc + p.g_offset;
-                } else if (p.logl_kind == LOGL_CURVED) {
-                    double tot = 0.0;
-#pragma unroll
-                    for (int b = 0; b + 1 < DP; b += 2) {
-                        if (b + 1 < d) {
-                            const double a = q[b], y = q[b + 1];
-                            const double t0 = 9.0 + 4.0 * a * a + 9.0 * y;
-                            tot += log(exp(-a * a - t0 * t0) + 0.5 * exp(-8.0 * a * a - 8.0 * (y - 2.0) * (y - 2.0)));
-                        }
-                    }
-                    lnln = tot;
-                } else {
-                    double tot = 0.0;
-#pragma unroll
-                    for (int i = 0; i + 1 < DP; ++i) {
-                        if (i + 1 < d) {
-                            const double a = q[i + 1] - q[i] * q[i], b = 1.0 - q[i];
-                            tot -= 100.0 * a * a + b * b;
-                        }
-                    }
-                    lnln = tot / 20.0;
-                }
+                lnln = logl_builtin<DP>(p, tb, q);
                 lnpn = beta * lnln + lpn;
             }
-            const double lnp0 = beta * S.lnl[cl] + S.lp[cl];
-            const double diff = lnpn - lnp0;
-            const double u = word_to_unit(st.next());
-            const bool accept = diff > log(u);
+            const double lnl0 = S.lnl[cl], lp0 = S.lp[cl];
+            const bool accept = hastings_accept(lnpn - (beta * lnl0 + lp0), st.next());
             const int jump = (kindr == 0) ? JUMP_AM : (kindr == 1) ? JUMP_SCAM : JUMP_DE;
-            S.cnt[jump * NC + cl] += 1;
+            S.cnt[jump * NC + cl] += accept ? 0x100000001ull : 1ull;
             if (accept) {
 #pragma unroll
                 for (int k = 0; k < DP; ++k) S.xs[k * NC + cl] = q[k];
                 S.lnl[cl] = lnln;
                 S.lp[cl] = lpn;
-                S.cnt[(3 + jump) * NC + cl] += 1;
-                S.jt[cl] = (unsigned char)(jump | 0x80);
+            } else {
+                lnln = lnl0;
+                lpn = lp0;
+            }
+            // ---- updateChains of this iteration for the chain just stepped (ref :627, :321-335)
+            if (p.trace && it - 1 < p.trace_cap)
+                p.trace[((size_t)(it - 1) * T + t) * W + w] = (unsigned char)(jump | ((int)accept << 7));
+            if (keep) {
+                const bool cold = ring && t == 0;
+                const bool rec = t < p.ntr && thin_ctr == 0 && row >= 0 && row < p.rec_cap;
+                if (cold || rec) {
+                    if (!accept) {
+#pragma unroll
+                        for (int k = 0; k < DP; ++k) q[k] = S.xs[k * NC + cl];
+                    }
+                    if (cold) {
+                        double *dst = p.am + (size_t)am_slot * d * W + w;
+#pragma unroll
+                        for (int k = 0; k < DP; ++k)
+                            if (k < d) dst[(size_t)k * W] = q[k];
+                    }
+                    if (rec) {
+                        const size_t r = ((size_t)row * p.ntr + t) * W + w;
+                        double *dst = p.rec_x + r * d;
+#pragma unroll
+                        for (int k = 0; k < DP; ++k)
+                            if (k < d) dst[k] = q[k];
+                        p.rec_lnl[r] = lnln;
+                        p.rec_lnp[r] = beta * lnln + lpn;
+                    }
+                }
             }
         }
+        // ---- phase A of the next iteration, in the shadow of the longer warps of phase B
+        const int lb1 = lb ^ 1, cb1 = (cb == 2) ? 0 : cb + 1;
+        if (it < p.it1) draw_kind(it + 1, lb1, cb1);
+        lb = lb1;
+        cb = cb1;
         __syncthreads();
     }
     if (have) {
@@ -284,8 +312,9 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const DevParams p)
         p.lp[cme] = S.lp[tid];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            p.prop[(size_t)j * TW + cme] += S.cnt[j * NC + tid];
-            p.acc[(size_t)j * TW + cme] += S.cnt[(3 + j) * NC + tid];
+            const unsigned long long c = S.cnt[j * NC + tid];
+            p.prop[(size_t)j * TW + cme] += c & 0xFFFFFFFFull;
+            p.acc[(size_t)j * TW + cme] += c >> 32;
         }
     }
 }

@@ -5,7 +5,7 @@
 namespace ptm {
 
 constexpr int MAX_CYCLE = 16;
-constexpr int MAX_REG_DIM = 32;       // register-resident kernel covers ndim <= 32
+constexpr int MAX_REG_DIM = 32;       // shared-memory (sorted) kernel covers ndim <= 32
 constexpr int MAX_GENERIC_DIM = 128;  // local-memory kernel covers ndim <= 128
 constexpr int MH_THREADS = 128;
 
@@ -19,6 +19,7 @@ struct DevParams {
     int walker_offset, temp_offset;
     int ngroups, identity_group, njumps;
     unsigned long long seed;
+    uint32_t rk[20];  // Philox round keys of the seed (philox_round_keys), read as constant-bank operands
     // chain state, SoA with the walker index fastest: x[T][d][W], lnl/lp[T][W]
     double *x, *lnl, *lp;
     const double *mh_temp, *ladder;  // [T]
@@ -50,5 +51,17 @@ struct DevParams {
     long long it0, it1;
     int tail, pad2;
 };
+
+// round r of Philox4x32-10 uses the key (k0 + r W0, k1 + r W1), Weyl constants of Salmon et al.
+inline void philox_round_keys(unsigned long long seed, uint32_t *rk)
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        rk[2 * r] = k0;
+        rk[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
 
 }  // namespace ptm

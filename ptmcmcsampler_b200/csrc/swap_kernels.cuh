@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(128) swap_decide_kernel(const DevParams p, lon
     const int W = p.W, T = p.T;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
-    Stream st(p.seed, PURPOSE_SWAP, (unsigned long long)it, (uint32_t)(p.walker_offset + w), 0u);
+    Stream st(p, PURPOSE_SWAP, (unsigned long long)it, (uint32_t)(p.walker_offset + w), 0u);
     int carry = T - 1;
     double Lcarry = p.lnl[(size_t)(T - 1) * W + w];
     for (int sc = T - 2; sc >= 0; --sc) {
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) swap_sweep_kernel(const DevParams p, long
     const int d = p.d, W = p.W, T = p.T;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
-    Stream st(p.seed, PURPOSE_SWAP, (unsigned long long)it, (uint32_t)(p.walker_offset + w), 0u);
+    Stream st(p, PURPOSE_SWAP, (unsigned long long)it, (uint32_t)(p.walker_offset + w), 0u);
     int carry = T - 1;
     double Lcarry = p.lnl[(size_t)(T - 1) * W + w];
     if (carry_in) {
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(MH_THREADS) swap_finish_kernel(const DevParams
     if (t == 0) {
         code = carry_code[w];
         if (below_top) {
-            Stream st(p.seed, PURPOSE_SWAP, (unsigned long long)it, (uint32_t)(p.walker_offset + w), 0u);
+            Stream st(p, PURPOSE_SWAP, (unsigned long long)it, (uint32_t)(p.walker_offset + w), 0u);
             st.seek((uint32_t)(Tg - 2 - (p.temp_offset - 1)));
             if (swap_accept(below_top[(size_t)d * W + w], carry_L[w], ladder_below, p.ladder[0], word_to_unit(st.next())))
                 code = T + 1;

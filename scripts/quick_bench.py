@@ -22,6 +22,7 @@ def main(d=20, W=8192, T=32, niter=1000, reps=3):
                      logl_params=lpar, logp_params=ppar, record_rows=niter * (reps + 2) // 10 + 2, timing=False)
     x0 = np.random.default_rng(1).uniform(0, 10, (T, W, d))
     e.set_state(x0)
+    print("kernel:", e.mh_kernel_name, flush=True)
     e.run(niter)
     e.sync()
     for r in range(reps):
@@ -33,7 +34,14 @@ def main(d=20, W=8192, T=32, niter=1000, reps=3):
     prop, acc, sw, nsw = e.counters()
     print("acceptance per jump (cold):", acc[0].sum(0) / np.maximum(1, prop[0].sum(0)))
     print("swap acc (first rungs):", sw[:4].mean(1) / max(1, nsw))
-    print(e.timing())
+    e.set_timing(True)
+    e.reset_timing()
+    e.run(niter)
+    e.sync()
+    tm = e.timing()
+    print("mh kernel: %.3f ms / launch over %d launches -> %.3e chain-steps/s in-kernel; class ms %s" % (
+        tm["ms"]["mh"] / tm["launches"]["mh"], tm["launches"]["mh"], W * T * niter / (tm["ms"]["mh"] * 1e-3),
+        {k: round(v, 2) for k, v in tm["ms"].items() if v}))
     x, lnl, lp, lnp = e.state()
     print("cold mean", x[0].mean(0)[:4], "cold var/target", (x[0].var(0) / np.diag(cov))[:4])
 

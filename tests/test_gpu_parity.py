@@ -19,27 +19,31 @@ FTOL = 1e-9
 
 
 def make_pair(d, W, T, cov0, seed, target, groups=None, cycle=((0, 20), (1, 20)), de_weight=20, cov_update=50,
-              burn=100, tskip=10, thin=5, niter=300, ladder=None, record_hot=True, mh_temp=None, variant=None):
+              burn=100, tskip=10, thin=5, niter=300, ladder=None, record_hot=True, mh_temp=None, variant=None,
+              sort_cfg=None, nthreads=4):
     lk, lpar, pk, ppar = target
     ladder = orc.temperature_ladder(d, T) if ladder is None else np.asarray(ladder, float)
     rows = niter // thin + 1
     o = orc.Oracle(d, W, T, cov0, seed=seed, ladder=ladder, mh_temp=mh_temp, groups=groups, cycle=cycle,
                    de_weight=de_weight, cov_update=cov_update, burn=burn, tskip=tskip, thin=thin, logl_kind=lk,
-                   logl_params=lpar, logp_kind=pk, logp_params=ppar, record_hot=record_hot, max_rows=rows, nthreads=4)
-    old = os.environ.get("PTMCMC_MH_VARIANT")
-    if variant is not None:
-        os.environ["PTMCMC_MH_VARIANT"] = str(variant)  # read when the engine is created
+                   logl_params=lpar, logp_kind=pk, logp_params=ppar, record_hot=record_hot, max_rows=rows, nthreads=nthreads)
+    env = {"PTMCMC_MH_VARIANT": variant, "PTMCMC_SORT_CFG": sort_cfg}  # read when the engine is created
+    old = {k: os.environ.get(k) for k in env}
+    for k, v in env.items():
+        if v is not None:
+            os.environ[k] = str(v)
     try:
         g = _cabi.Engine(d, W, T, cov0, ladder, mh_temp=mh_temp, seed=seed, groups=groups, cycle=cycle,
                          de_weight=de_weight, cov_update=cov_update, burn=burn, tskip=tskip, thin=thin, logl_kind=lk,
                          logl_params=lpar, logp_kind=pk, logp_params=ppar, record_hot=record_hot, record_rows=rows,
                          trace_iters=niter)
     finally:
-        if variant is not None:
-            if old is None:
-                del os.environ["PTMCMC_MH_VARIANT"]
-            else:
-                os.environ["PTMCMC_MH_VARIANT"] = old
+        for k, v in env.items():
+            if v is not None:
+                if old[k] is None:
+                    del os.environ[k]
+                else:
+                    os.environ[k] = old[k]
     return o, g
 
 
@@ -92,14 +96,46 @@ def gaussian_target(d, seed, lo=-50.0, hi=60.0):
             orc.uniform_params(lo * np.ones(d), hi * np.ones(d)))
 
 
+def test_device_normals_equal_oracle_bits():
+    """word_to_normals on the device (round-toward-zero conversion + fma, integer split of the float, sign-bit
+    quadrant logic) returns the oracle's doubles bit for bit: 10^7 random words plus the edges of every branch."""
+    rng = np.random.default_rng(5)
+    words = rng.integers(0, 2**64, 10_000_000, dtype=np.uint64)
+    his = np.array([0, 1, 2, 3, 2**23 - 1, 2**23, 2**23 + 1, 2**24 - 1, 2**24, 2**24 + 1, 2**25 + 3, 2**31, 2**32 - 129,
+                    2**32 - 128, 2**32 - 1, 0xB504F300, 0xB504F3FF, 0xB504F400, 0x5A827980, 0x5A827A00], dtype=np.uint64)
+    los = np.array([0, 1, 63, 64, 2**29, 2**29 + 64, 2**30 - 1, 2**30, 2**31 - 64, 2**31, 2**31 + 2**29, 3 * 2**30,
+                    2**32 - 1, 0x20000000, 0x20000040, 0x1FFFFFC0], dtype=np.uint64)
+    edge = ((his[:, None] << np.uint64(32)) | los[None, :]).ravel()
+    words = np.concatenate([words, edge])
+    d0, d1 = _cabi.device_normals(words)
+    o0, o1 = orc.word_to_normals_many(words)
+    assert np.array_equal(d0.view(np.uint64), o0.view(np.uint64))
+    assert np.array_equal(d1.view(np.uint64), o1.view(np.uint64))
+
+
+@pytest.mark.parametrize("sort_cfg", [None, 0])
 @pytest.mark.parametrize("d,W,T", [(20, 64, 4), (5, 33, 3), (8, 128, 1), (12, 7, 5), (32, 16, 2), (3, 1, 1), (1, 5, 2),
-                                   (2, 9, 1)])
-def test_register_kernel_matches_oracle(d, W, T):
+                                   (2, 9, 1), (20, 300, 2), (18, 33, 3), (17, 5, 1), (16, 200, 2), (24, 150, 2), (10, 400, 1)])
+def test_sorted_kernel_matches_oracle(d, W, T, sort_cfg):
+    """mh_sorted_kernel, default geometry (AM chains on lane pairs) and one task per chain (cfg 0): same draws,
+    same decisions; widths with odd and even numbers of normal pairs per lane, padded and unpadded ndim."""
     niter, tskip = 320, 10
     cov0 = np.diag(0.01 * (1.0 + np.arange(d)))
-    o, g = make_pair(d, W, T, cov0, seed=11 + d, target=gaussian_target(d, d), niter=niter, tskip=tskip)
+    o, g = make_pair(d, W, T, cov0, seed=11 + d, target=gaussian_target(d, d), niter=niter, tskip=tskip, sort_cfg=sort_cfg,
+                     variant=6)
+    assert "mh_sorted_kernel" in g.mh_kernel_name
     x0 = np.random.default_rng(d).uniform(0, 10, (T, W, d))
     compare(o, g, x0, niter, tskip, T, chunks=(0.33, 0.7, 1.0))
+
+
+@pytest.mark.parametrize("cycle,dew", [(((0, 5), (1, 40)), 5), (((1, 20),), 0), (((0, 20),), 0)])
+def test_sorted_kernel_am_heavy_cycle_overflows_task_list(cycle, dew):
+    """More AM chains in a block than its spare threads cover: the task loop takes a second pass."""
+    d, W, T, niter, tskip = 20, 256, 2, 240, 10
+    cov0 = np.diag(0.01 * (1.0 + np.arange(d)))
+    o, g = make_pair(d, W, T, cov0, seed=3, target=gaussian_target(d, d), niter=niter, tskip=tskip, cycle=cycle, de_weight=dew)
+    x0 = np.random.default_rng(d).uniform(0, 10, (T, W, d))
+    compare(o, g, x0, niter, tskip, T, chunks=(0.5, 1.0))
 
 
 @pytest.mark.parametrize("d,W,T", [(20, 64, 4), (5, 33, 3), (8, 128, 1), (12, 7, 5), (32, 16, 2), (3, 1, 1),
@@ -113,29 +149,6 @@ def test_tensor_core_kernel_matches_oracle(d, W, T):
     compare(o, g, x0, niter, tskip, T, chunks=(0.33, 0.7, 1.0), ftol=1e-8 if d > 32 else FTOL)
 
 
-@pytest.mark.parametrize("d,W,T", [(20, 64, 4), (20, 300, 2), (18, 33, 3), (17, 5, 1)])
-def test_warp_specialised_kernel_matches_oracle(d, W, T):
-    """mh_pipe_kernel: draw warps one iteration ahead of the step warps; same draws, same decisions."""
-    niter, tskip = 320, 10
-    cov0 = np.diag(0.01 * (1.0 + np.arange(d)))
-    o, g = make_pair(d, W, T, cov0, seed=11 + d, target=gaussian_target(d, d), niter=niter, tskip=tskip, variant=4)
-    x0 = np.random.default_rng(d).uniform(0, 10, (T, W, d))
-    compare(o, g, x0, niter, tskip, T, chunks=(0.33, 0.7, 1.0))
-
-
-@pytest.mark.parametrize("d,W,T,cycle,dew", [(20, 64, 4, ((0, 20), (1, 20)), 20), (20, 300, 2, ((0, 20), (1, 20)), 20),
-                                             (18, 33, 3, ((0, 5), (1, 40)), 5), (20, 256, 1, ((1, 20),), 0)])
-def test_shadow_kernel_matches_oracle(d, W, T, cycle, dew):
-    """mh_shadow_kernel: AM draws of iteration it+1 made during iteration it; same draws, same decisions.
-    The AM-heavy cycles overflow the draw queue (more than 128 AM chains of a block in one iteration)."""
-    niter, tskip = 320, 10
-    cov0 = np.diag(0.01 * (1.0 + np.arange(d)))
-    o, g = make_pair(d, W, T, cov0, seed=11 + d, target=gaussian_target(d, d), niter=niter, tskip=tskip, variant=5,
-                     cycle=cycle, de_weight=dew)
-    x0 = np.random.default_rng(d).uniform(0, 10, (T, W, d))
-    compare(o, g, x0, niter, tskip, T, chunks=(0.33, 0.7, 1.0))
-
-
 def test_tensor_core_kernel_truncated_box_and_outside_start():
     d, W, T, niter = 6, 40, 3, 250
     tgt = gaussian_target(d, 3, lo=3.0, hi=7.0)
@@ -146,7 +159,7 @@ def test_tensor_core_kernel_truncated_box_and_outside_start():
 
 def test_sorted_kernel_widest_instance_matches_oracle():
     """ndim in (24, 32] defaults to the tensor-core kernel; variant 6 keeps the sorted kernel's DP=32 instance covered."""
-    d, W, T, niter = 30, 40, 2, 200
+    d, W, T, niter = 30, 140, 2, 200
     o, g = make_pair(d, W, T, np.diag(0.01 * (1.0 + np.arange(d))), seed=41, target=gaussian_target(d, d), niter=niter,
                      variant=6)
     x0 = np.random.default_rng(d).uniform(0, 10, (T, W, d))

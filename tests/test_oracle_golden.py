@@ -43,6 +43,37 @@ def test_draw_primitives():
     assert a == -c and b == -d
 
 
+def test_normals_distribution_ks_and_tails():
+    """10^7 Box-Muller pairs of the engine's single-precision generator (word_to_normals, the same bits on the
+    device: tests/test_gpu_parity.py::test_device_normals_equal_oracle_bits) against N(0, 1): Kolmogorov-Smirnov
+    distance, tail masses out to 5 sigma within Poisson error, moments, independence of the pair."""
+    from scipy import special
+
+    n = 10_000_000
+    words = np.random.default_rng(2024).integers(0, 2**64, n, dtype=np.uint64)
+    z0, z1 = orc.word_to_normals_many(words)
+    for z in (z0, z1):
+        zs = np.sort(z)
+        cdf = 0.5 * special.erfc(-zs / np.sqrt(2.0))
+        i = np.arange(1, n + 1)
+        ks = max(np.max(i / n - cdf), np.max(cdf - (i - 1) / n))
+        assert ks < 1.63 / np.sqrt(n)  # 1 % critical value of the KS statistic
+        assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1.0) < 5 * np.sqrt(2.0 / n)
+        assert abs(np.mean(z**4) - 3.0) < 5 * np.sqrt(96.0 / n)
+        for k in (2.0, 3.0, 4.0, 5.0):
+            expect = n * special.erfc(k / np.sqrt(2.0))  # two-sided tail mass
+            got = np.count_nonzero(np.abs(z) > k)
+            assert abs(got - expect) < 5 * np.sqrt(expect) + 1, (k, got, expect)
+        assert np.abs(z).max() < 6.77  # the radius comes from 33 bits: |z| <= sqrt(66 ln 2)
+    assert abs(np.mean(z0 * z1)) < 5 / np.sqrt(n)
+    assert abs(np.mean(z0 * z0 * z1 * z1) - 1.0) < 5 * np.sqrt(8.0 / n)
+    # the far tail keeps its resolution: radius from the smallest words
+    tiny = (np.arange(1, 2000, dtype=np.uint64) << np.uint64(32))
+    r = np.hypot(*orc.word_to_normals_many(tiny))
+    expect = np.sqrt(-2.0 * np.log((2.0 * np.arange(1, 2000) + 1.0) * 2.0**-33))
+    assert np.allclose(r, expect, rtol=3e-7)
+
+
 def test_temperature_ladder_matches_reference_formula():
     # ref PTMCMCSampler.py:709-718
     lad = orc.temperature_ladder(20, 5)
