@@ -20,12 +20,12 @@ constexpr Cfg CFGS[] = {
 constexpr int NCFG = sizeof(CFGS) / sizeof(CFGS[0]);
 constexpr int DEFAULT_CFG = 0;
 
-template <int DP, int C>
-cudaError_t launch_one(const DevParams &p, const SortedHostTables &ht, const SortedGeom &g, int device, cudaStream_t stream)
+template <int DP, int C, int LK>
+cudaError_t launch_lk(const DevParams &p, const SortedHostTables &ht, const SortedGeom &g, int device, cudaStream_t stream)
 {
     constexpr Cfg c = CFGS[C];
     using Smem = SortedSmem<DP, c.nc>;
-    auto kern = mh_sorted_kernel<DP, c.nc, c.minb>;
+    auto kern = mh_sorted_kernel<DP, c.nc, c.minb, LK>;
     static bool attr_dev[64] = {};
     bool &attr_done = attr_dev[device & 63];  // function attributes are per device
     if (!attr_done) {
@@ -45,6 +45,16 @@ cudaError_t launch_one(const DevParams &p, const SortedHostTables &ht, const Sor
     }
     kern<<<g.blocks, c.nc, sizeof(Smem), stream>>>(p, tb, g.nc);
     return cudaGetLastError();
+}
+
+template <int DP, int C>
+cudaError_t launch_one(const DevParams &p, const SortedHostTables &ht, const SortedGeom &g, int device, cudaStream_t stream)
+{
+    switch (p.logl_kind) {
+    case LOGL_GAUSSIAN: return launch_lk<DP, C, LOGL_GAUSSIAN>(p, ht, g, device, stream);
+    case LOGL_CURVED: return launch_lk<DP, C, LOGL_CURVED>(p, ht, g, device, stream);
+    default: return launch_lk<DP, C, LOGL_ROSENBROCK>(p, ht, g, device, stream);
+    }
 }
 
 template <int DP>

@@ -48,11 +48,11 @@ template <int DP>
 __device__ __forceinline__ constexpr int tri_index(int i, int j) { return i * DP - (i * (i - 1)) / 2 + (j - i); }
 
 // log-likelihood of the built-in targets from a full proposal in registers
-template <int DP>
+template <int DP, int LK>
 __device__ __forceinline__ double logl_builtin(const DevParams &p, const SortedTables<DP> &tb, const double (&q)[DP])
 {
     const int d = p.d;
-    if (p.logl_kind == LOGL_GAUSSIAN) {
+    if (LK == LOGL_GAUSSIAN) {
         double dv[DP];
 #pragma unroll
         for (int j = 0; j < DP; ++j) dv[j] = q[j] - tb.mu[j];
@@ -66,7 +66,7 @@ __device__ __forceinline__ double logl_builtin(const DevParams &p, const SortedT
         }
         return acc + p.g_offset;
     }
-    if (p.logl_kind == LOGL_CURVED) {
+    if (LK == LOGL_CURVED) {
         double tot = 0.0;
 #pragma unroll
         for (int b = 0; b + 1 < DP; b += 2) {
@@ -89,7 +89,35 @@ __device__ __forceinline__ double logl_builtin(const DevParams &p, const SortedT
     return tot / 20.0;
 }
 
-template <int DP, int NC, int MINB>
+// jump kind of iteration `it` for the chain this thread owns (ref :1058), appended to that kind's list
+template <int NC>
+__device__ __noinline__ void draw_kind(const DevParams &p, long long it, bool have, uint32_t gw, uint32_t gt, unsigned short *list,
+                                       int *count)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    int kind = 3;  // none
+    if (have) {
+        Stream st(p, PURPOSE_MH, (unsigned long long)it, gw, gt);
+        const int jump = pick_jump(p, st);
+        kind = (jump == JUMP_AM) ? 0 : (jump == JUMP_SCAM) ? 1 : 2;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+        const unsigned m = __ballot_sync(0xffffffffu, kind == kk);
+        if (m) {
+            int base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(&count[kk], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (kind == kk) list[kk * NC + base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)tid;
+        }
+    }
+}
+
+// LK: the built-in log-likelihood this instance evaluates (one instance per target keeps the code resident in the
+// instruction cache: the round-2 capture of a single kernel for all targets showed 130 KB of code and 11 % of the
+// stall samples waiting for instructions)
+template <int DP, int NC, int MINB, int LK>
 __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const __grid_constant__ DevParams p,
                                                              const __grid_constant__ SortedTables<DP> tb, const int nc)
 {
@@ -134,30 +162,11 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const __grid_consta
     const bool ring = p.temp_offset == 0 && p.am != nullptr;
     const unsigned long long bufsize = (unsigned long long)p.burn * (unsigned long long)W;
     const bool small_buf = bufsize <= 0xFFFFFFFFull;
+    const uint32_t npairs = (uint32_t)((d + 1) >> 1);
     __syncthreads();
 
-    // jump kind of iteration `it` for the owned chain (ref :1058) into the lists of buffer (lb, cb)
-    auto draw_kind = [&](long long it, int lb, int cb) {
-        int kind = 3;  // none
-        if (have) {
-            Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + wme),
-                      (uint32_t)(p.temp_offset + tme));
-            const int jump = pick_jump(p, st);
-            kind = (jump == JUMP_AM) ? 0 : (jump == JUMP_SCAM) ? 1 : 2;
-        }
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-            const unsigned m = __ballot_sync(0xffffffffu, kind == kk);
-            if (m) {
-                int base = 0;
-                const int leader = __ffs(m) - 1;
-                if (lane == leader) base = atomicAdd(&S.count[cb][kk], __popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (kind == kk) S.list[lb][kk * NC + base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)tid;
-            }
-        }
-    };
-    draw_kind(p.it0, 0, 0);
+    const uint32_t gwme = (uint32_t)(p.walker_offset + wme), gtme = (uint32_t)(p.temp_offset + tme);
+    draw_kind<NC>(p, p.it0, have, gwme, gtme, S.list[0], S.count[0]);
     __syncthreads();
 
     int lb = 0, cb = 0;  // list / count buffers of the current iteration
@@ -176,72 +185,101 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const __grid_consta
             const int cl = (kindr == 0) ? list[tid] : (kindr == 1) ? list[NC + tid - nA] : list[2 * NC + tid - nA - nS];
             const int t = S.ct[cl], w = S.cw[cl];
             const double beta = S.beta[cl];
-            Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + w), (uint32_t)(p.temp_offset + t));
-            st.j = 2;  // words 0 (jump index) and 1 (group index of the single group) are spent
+            // Words of this chain's stream: 0 = jump index, 1 = group index (both spent), then the proposal's draws
+            // and the accept uniform.  The generator is inlined at four places only (code size): block 1 here,
+            // block 2 for SCAM / DE, block 3 for DE, and the block loop of AM; rare paths call stream_word.
+            const Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + w), (uint32_t)(p.temp_offset + t));
+            const uint4 b1 = st.block(1);  // words 2, 3
+            uint64_t wacc;                 // word of the accept uniform (ref :616)
             double q[DP];
-            if (kindr == 0) {  // AM (ref :879-933)
-                const double prob = word_to_unit(st.next());
+            if (kindr == 0) {  // AM (ref :879-933): word 2 = prob, word 3 + m = normal pair m, then the accept uniform
+                const double prob = word_to_unit(lo_word(b1));
                 const double cd = c_am * (((prob > 0.97) ? 10.0 : (prob > 0.9) ? 0.2 : 1.0) * S.sct[cl]);
-                // q = x + U delta accumulated column pair by column pair as the normals are drawn (same
-                // j order per row as a row-wise dot product, so the same bits): no delta array stays live
-                // and the draw of pair j+1 overlaps the 2 d FMAs of pair j
+                // q = x + U delta accumulated column pair by column pair as the normals are drawn (same j order per
+                // row as a row-wise dot product, so the same bits).  One trip per Philox block, the next block
+                // generated ahead of the normals and FMAs of the current one.
 #pragma unroll
                 for (int i = 0; i < DP; ++i) q[i] = S.xs[i * NC + cl];
+                const uint32_t ja = 3u + npairs, jb = ja >> 1;  // accept word and its block
+                uint4 cur = b1;
+#pragma unroll 1
+                for (uint32_t b = 1; b <= jb; ++b) {
+                    uint4 nxt = cur;
+                    if (b < jb) nxt = st.block(b + 1);
+                    // word 2b -> pair 2b - 3 (word 2 is prob), word 2b + 1 -> pair 2b - 2
 #pragma unroll
-                for (int j = 0; j < DP; j += 2) {
-                    double z0 = 0.0, z1 = 0.0;
-                    if (j < d) word_to_normals(st.next(), z0, z1);
-                    const double d0 = z0 * cd * S.sS[j];
-                    const double d1 = (j + 1 < DP) ? z1 * cd * S.sS[j + 1] : 0.0;
+                    for (int half = 0; half < 2; ++half) {
+                        const int m = 2 * (int)b - 3 + half;
+                        if (m >= 0 && m < (int)npairs) {
+                            double z0, z1;
+                            word_to_normals(half ? cur.w : cur.y, half ? cur.z : cur.x, z0, z1);
+                            const int j = 2 * m;
+                            const double d0 = z0 * cd * S.sS[j], d1 = z1 * cd * S.sS[j + 1];  // sS is zero padded
+                            const double *Uj = S.Us + j;
 #pragma unroll
-                    for (int i = 0; i < DP; ++i) {
-                        q[i] = fma(S.Us[i * DP + j], d0, q[i]);
-                        if (j + 1 < DP) q[i] = fma(S.Us[i * DP + j + 1], d1, q[i]);
-                    }
-                }
-            } else if (kindr == 1) {  // SCAM (ref :820-876)
-                const double prob = word_to_unit(st.next());
-                const double scale = ((prob > 0.97) ? 10.0 : (prob > 0.9) ? 0.2 : 1.0) * S.sct[cl];
-                const int k = (int)word_to_int32(st.next(), (uint32_t)d);
-                const double cd = 2.4 / sqrt(2.0) * scale;
-                double z0, z1;
-                word_to_normals(st.next(), z0, z1);
-                const double coef = z0 * cd * S.sS[k];
-#pragma unroll
-                for (int i = 0; i < DP; ++i) q[i] = fma(coef, S.Us[i * DP + k], S.xs[i * NC + cl]);
-            } else {  // DE (ref :936-985)
-                unsigned long long mm, nn;
-                if (small_buf) {
-                    const uint32_t bs = (uint32_t)bufsize;
-                    mm = word_to_int32(st.next(), bs);
-                    nn = word_to_int32(st.next(), bs);
-                    while (mm == nn) nn = word_to_int32(st.next(), bs);
-                } else {
-                    mm = word_to_int(st.next(), bufsize);
-                    nn = word_to_int(st.next(), bufsize);
-                    while (mm == nn) nn = word_to_int(st.next(), bufsize);
-                }
-                const double *bm = p.de + de_row_offset(mm, bufsize, W, p.burn, p.de_head) * d;
-                const double *bn = p.de + de_row_offset(nn, bufsize, W, p.burn, p.de_head) * d;
-                const double prob = word_to_unit(st.next());
-                double scale = 1.0;
-                if (!(prob > 0.5)) scale = word_to_unit(st.next()) * S.dsc[cl];  // ref :969-976
-                if ((d & 1) == 0) {  // rows are 16-byte aligned: half as many load instructions
-#pragma unroll
-                    for (int i = 0; i < DP; i += 2) {
-                        double2 vm = make_double2(0.0, 0.0), vn = vm;
-                        if (i < d) {
-                            vm = __ldg(reinterpret_cast<const double2 *>(bm + i));
-                            vn = __ldg(reinterpret_cast<const double2 *>(bn + i));
+                            for (int i = 0; i < DP; ++i) {
+                                q[i] = fma(Uj[i * DP], d0, q[i]);
+                                q[i] = fma(Uj[i * DP + 1], d1, q[i]);
+                            }
                         }
-                        q[i] = fma(scale, vm.x - vn.x, S.xs[i * NC + cl]);
-                        if (i + 1 < DP) q[i + 1] = fma(scale, vm.y - vn.y, S.xs[(i + 1) * NC + cl]);
                     }
-                } else {
+                    cur = nxt;
+                }
+                wacc = (ja & 1u) ? hi_word(cur) : lo_word(cur);
+            } else {
+                const uint4 b2 = st.block(2);  // words 4, 5
+                if (kindr == 1) {  // SCAM (ref :820-876): prob, k, normal, accept
+                    const double prob = word_to_unit(lo_word(b1));
+                    const double scale = ((prob > 0.97) ? 10.0 : (prob > 0.9) ? 0.2 : 1.0) * S.sct[cl];
+                    const int k = (int)word_to_int32(hi_word(b1), (uint32_t)d);
+                    const double cd = 2.4 / sqrt(2.0) * scale;
+                    double z0, z1;
+                    word_to_normals(b2.y, b2.x, z0, z1);
+                    const double coef = z0 * cd * S.sS[k];
 #pragma unroll
-                    for (int i = 0; i < DP; ++i) {
-                        const double sigma = (i < d) ? (__ldg(bm + i) - __ldg(bn + i)) : 0.0;
-                        q[i] = fma(scale, sigma, S.xs[i * NC + cl]);
+                    for (int i = 0; i < DP; ++i) q[i] = fma(coef, S.Us[i * DP + k], S.xs[i * NC + cl]);
+                    wacc = hi_word(b2);
+                } else {  // DE (ref :936-985): mm, nn (redrawn while equal), prob, [scale uniform], accept
+                    unsigned long long mm, nn;
+                    if (small_buf) {
+                        mm = word_to_int32(lo_word(b1), (uint32_t)bufsize);
+                        nn = word_to_int32(hi_word(b1), (uint32_t)bufsize);
+                    } else {
+                        mm = word_to_int(lo_word(b1), bufsize);
+                        nn = word_to_int(hi_word(b1), bufsize);
+                    }
+                    double scale = 1.0;
+                    if (mm != nn) {
+                        wacc = hi_word(b2);
+                        if (!(word_to_unit(lo_word(b2)) > 0.5)) {  // ref :969-976
+                            scale = word_to_unit(wacc) * S.dsc[cl];
+                            wacc = lo_word(st.block(3));
+                        }
+                    } else {  // one draw in bufsize: the sequential form through the out-of-line generator
+                        uint32_t j = 4;
+                        while (mm == nn) nn = word_to_int(stream_word(st, j++), bufsize);
+                        if (!(word_to_unit(stream_word(st, j++)) > 0.5)) scale = word_to_unit(stream_word(st, j++)) * S.dsc[cl];
+                        wacc = stream_word(st, j);
+                    }
+                    const double *bm = p.de + de_row_offset(mm, bufsize, W, p.burn, p.de_head) * d;
+                    const double *bn = p.de + de_row_offset(nn, bufsize, W, p.burn, p.de_head) * d;
+                    if ((d & 1) == 0) {  // rows are 16-byte aligned: half as many load instructions
+#pragma unroll
+                        for (int i = 0; i < DP; i += 2) {
+                            double2 vm = make_double2(0.0, 0.0), vn = vm;
+                            if (i < d) {
+                                vm = __ldg(reinterpret_cast<const double2 *>(bm + i));
+                                vn = __ldg(reinterpret_cast<const double2 *>(bn + i));
+                            }
+                            q[i] = fma(scale, vm.x - vn.x, S.xs[i * NC + cl]);
+                            if (i + 1 < DP) q[i + 1] = fma(scale, vm.y - vn.y, S.xs[(i + 1) * NC + cl]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < DP; ++i) {
+                            const double sigma = (i < d) ? (__ldg(bm + i) - __ldg(bn + i)) : 0.0;
+                            q[i] = fma(scale, sigma, S.xs[i * NC + cl]);
+                        }
                     }
                 }
             }
@@ -251,11 +289,11 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const __grid_consta
             double lpn = inside ? p.p_inside : neg_inf();
             double lnln = 0.0, lnpn = neg_inf();
             if (inside) {
-                lnln = logl_builtin<DP>(p, tb, q);
+                lnln = logl_builtin<DP, LK>(p, tb, q);
                 lnpn = beta * lnln + lpn;
             }
             const double lnl0 = S.lnl[cl], lp0 = S.lp[cl];
-            const bool accept = hastings_accept(lnpn - (beta * lnl0 + lp0), st.next());
+            const bool accept = hastings_accept(lnpn - (beta * lnl0 + lp0), wacc);
             const int jump = (kindr == 0) ? JUMP_AM : (kindr == 1) ? JUMP_SCAM : JUMP_DE;
             S.cnt[jump * NC + cl] += accept ? 0x100000001ull : 1ull;
             if (accept) {
@@ -298,7 +336,7 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const __grid_consta
         }
         // ---- phase A of the next iteration, in the shadow of the longer warps of phase B
         const int lb1 = lb ^ 1, cb1 = (cb == 2) ? 0 : cb + 1;
-        if (it < p.it1) draw_kind(it + 1, lb1, cb1);
+        if (it < p.it1) draw_kind<NC>(p, it + 1, have, gwme, gtme, S.list[lb1], S.count[cb1]);
         lb = lb1;
         cb = cb1;
         __syncthreads();

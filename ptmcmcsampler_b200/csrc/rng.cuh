@@ -57,6 +57,15 @@ struct Stream {
     __device__ __forceinline__ uint4 block(uint32_t b) const { return philox4x32_10(p, c0, c1b | b, c2, c3); }
 };
 
+__device__ __forceinline__ uint64_t lo_word(const uint4 &b) { return (uint64_t)b.x | ((uint64_t)b.y << 32); }
+__device__ __forceinline__ uint64_t hi_word(const uint4 &b) { return (uint64_t)b.z | ((uint64_t)b.w << 32); }
+// word j of a stream through ONE out-of-line copy of the generator (rare paths of the unrolled kernels)
+static __device__ __noinline__ uint64_t stream_word(const Stream &st, uint32_t j)
+{
+    const uint4 b = st.block(j >> 1);
+    return (j & 1u) ? hi_word(b) : lo_word(b);
+}
+
 // integer in [0, n): high 64 bits of word*n (stands in for Generator.integers)
 __device__ __forceinline__ uint64_t word_to_int(uint64_t w, uint64_t n) { return __umul64hi(w, n); }
 // the same value for n < 2^32 with two 32 x 32 -> 64 multiplies
