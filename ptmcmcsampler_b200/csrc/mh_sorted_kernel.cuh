@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const __grid_consta
     const double c_am = 2.4 / sqrt(2.0 * d);
     if (have) {
         const double *xg = p.x + (size_t)tme * d * W + wme;
-#pragma unroll
         for (int k = 0; k < DP; ++k) S.xs[k * NC + tid] = (k < d) ? xg[(size_t)k * W] : 0.0;
         S.lnl[tid] = p.lnl[cme];
         S.lp[tid] = p.lp[cme];
@@ -308,29 +307,17 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const __grid_consta
             // ---- updateChains of this iteration for the chain just stepped (ref :627, :321-335)
             if (p.trace && it - 1 < p.trace_cap)
                 p.trace[((size_t)(it - 1) * T + t) * W + w] = (unsigned char)(jump | ((int)accept << 7));
-            if (keep) {
-                const bool cold = ring && t == 0;
-                const bool rec = t < p.ntr && thin_ctr == 0 && row >= 0 && row < p.rec_cap;
-                if (cold || rec) {
-                    if (!accept) {
-#pragma unroll
-                        for (int k = 0; k < DP; ++k) q[k] = S.xs[k * NC + cl];
-                    }
-                    if (cold) {
-                        double *dst = p.am + (size_t)am_slot * d * W + w;
-#pragma unroll
-                        for (int k = 0; k < DP; ++k)
-                            if (k < d) dst[(size_t)k * W] = q[k];
-                    }
-                    if (rec) {
-                        const size_t r = ((size_t)row * p.ntr + t) * W + w;
-                        double *dst = p.rec_x + r * d;
-#pragma unroll
-                        for (int k = 0; k < DP; ++k)
-                            if (k < d) dst[k] = q[k];
-                        p.rec_lnl[r] = lnln;
-                        p.rec_lnp[r] = beta * lnln + lpn;
-                    }
+            if (keep) {  // (from shared memory, after the accept store, in rolled loops: cold rung / thinned rows only)
+                if (ring && t == 0) {
+                    double *dst = p.am + (size_t)am_slot * d * W + w;
+                    for (int k = 0; k < d; ++k) dst[(size_t)k * W] = S.xs[k * NC + cl];
+                }
+                if (t < p.ntr && thin_ctr == 0 && row >= 0 && row < p.rec_cap) {
+                    const size_t r = ((size_t)row * p.ntr + t) * W + w;
+                    double *dst = p.rec_x + r * d;
+                    for (int k = 0; k < d; ++k) dst[k] = S.xs[k * NC + cl];
+                    p.rec_lnl[r] = lnln;
+                    p.rec_lnp[r] = beta * lnln + lpn;
                 }
             }
         }
@@ -343,9 +330,7 @@ __global__ void __launch_bounds__(NC, MINB) mh_sorted_kernel(const __grid_consta
     }
     if (have) {
         double *xo = p.x + (size_t)tme * d * W + wme;
-#pragma unroll
-        for (int k = 0; k < DP; ++k)
-            if (k < d) xo[(size_t)k * W] = S.xs[k * NC + tid];
+        for (int k = 0; k < d; ++k) xo[(size_t)k * W] = S.xs[k * NC + tid];
         p.lnl[cme] = S.lnl[tid];
         p.lp[cme] = S.lp[tid];
 #pragma unroll

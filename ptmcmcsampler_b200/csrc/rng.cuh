@@ -85,6 +85,8 @@ __device__ __forceinline__ double word_to_unit(uint64_t w)
 // logarithm is evaluated: the decision is exactly that of the double-precision comparison, at a fifth of
 // its instructions.  Error budget of the filter: MUFU.LG2 2^-22 absolute on [1/2, 2], 2 ulp elsewhere,
 // the float conversion of u and the product with ln 2 2^-24 relative each; the margin is > 6x that.
+static __device__ __noinline__ bool hastings_exact(double diff, double u) { return diff > log(u); }
+
 __device__ __forceinline__ bool hastings_accept(double diff, uint64_t w)
 {
     const double u = word_to_unit(w);
@@ -92,7 +94,7 @@ __device__ __forceinline__ bool hastings_accept(double diff, uint64_t w)
     const double margin = fma(fabs(la), 2e-6, 2e-6);
     if (diff > la + margin) return true;
     if (diff < la - margin) return false;
-    return diff > log(u);  // also u = 0 (la = -inf) and NaN differences (compare false, ref :616)
+    return hastings_exact(diff, u);  // also u = 0 (la = -inf) and NaN differences (compare false, ref :616)
 }
 
 // Box-Muller pair (stands in for standard_normal): radius from the high 32 bits, angle from the low 32
