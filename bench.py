@@ -1,14 +1,19 @@
 #!/usr/bin/env python
-"""Benchmark of the PT-MCMC hot path (BASELINE.json metric and config).
+"""Benchmark of the PT-MCMC hot path (BASELINE.json metric and configs).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--shard walkers|ladder]
 
-Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): 20-dim correlated Gaussian target,
+Headline workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): 20-dim correlated Gaussian target,
 8192 walkers x 32 temperatures per GPU, SCAM/AM/DE = 20/20/20, covUpdate = burn = 1000, Tskip = 100,
 thin = 10, default geometric ladder.  One bench "step" = 1000 MH iterations of all 262 144 chains
 (10 swap sweeps, one pooled covariance update + eigen-factorisation and one DE-history update
 included).  N > 1: every rank runs its own 8192 x 32 shard (weak scaling); the only collective is the
 pooled-covariance all-gather at every covariance boundary.
+
+The same JSON line also carries the other BASELINE configurations, each measured in this run with its own
+`value`, `ms_per_step`, `roofline` and `e2e`: `configs.C3` (100-dim dense Gaussian, 4096 x 64, tensor-core
+kernel) and `configs.C4` (curved 10-dim, 16384 x 128, DE-dominant) at N = 1, and `c5_ladder` (one ladder of
+32 N rungs split 32 per GPU, neighbour exchange of the boundary rung over NCCL) at N > 1.
 
 One JSON line on stdout (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes
 through the public PTSampler.sample() call with host buffers.
@@ -19,7 +24,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -27,37 +31,102 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-D, W, T = 20, 8192, 32
 ITERS = 1000          # MH iterations per bench step
 COV_UPDATE = BURN = 1000
 TSKIP, THIN = 100, 10
-WEIGHTS = (20, 20, 20)
 METRIC = "walker-steps/sec (20-dim Gaussian, 8192 walkers x 32 temps)"
 UNIT = "chain-steps/s"
 
 
-def algorithmic_bytes_per_chain_step(d=D, t=T, thin=THIN, p_de=1.0 / 3.0):
+# ------------------------------------------------------------------------------------------ workloads
+def algorithmic_bytes_per_chain_step(d, t, thin=THIN, p_de=1.0 / 3.0):
     """state read+write (x, lnL, lnP, 16-B RNG counter), two DE rows on DE
     steps, the thinned record and the cold rung's AM-ring write."""
     return 2 * (8 * d + 16 + 16) + p_de * 2 * 8 * d + (8 * d + 16) / thin + 8 * d / t
 
 
-def algorithmic_flops_per_chain_step(d=D, p_am=1.0 / 3.0, p_scam=1.0 / 3.0, p_de=1.0 / 3.0):
-    """dense Gaussian logl 2d^2+3d, box prior 2d, AM mat-vecs 2d^2 (the engine's
-    x + U delta form), SCAM / DE 2d, ~30 for the Hastings test."""
-    return (2 * d * d + 3 * d) + 2 * d + p_am * 2 * d * d + (p_scam + p_de) * 2 * d + 30
+def algorithmic_flops_per_chain_step(d, f_logl, p_am, p_scam, p_de):
+    """logl, box prior 2d, AM mat-vecs 2d^2 (the engine's x + U delta form), SCAM / DE 2d,
+    ~30 for the Hastings test."""
+    return f_logl + 2 * d + p_am * 2 * d * d + (p_scam + p_de) * 2 * d + 30
 
 
-def problem():
-    """C2 target: mu = 5, Sigma = A.A + 0.1 I with A as in examples/simple.py:27-30 from default_rng(20)."""
-    rng = np.random.default_rng(20)
-    A = 0.5 - rng.random(D * D).reshape(D, D)
-    A = np.triu(A)
-    A += A.T - np.diag(A.diagonal())
-    cov = A @ A + 0.1 * np.eye(D)
-    mu = 5.0 * np.ones(D)
-    ladder = (1 + np.sqrt(2.0 / D)) ** np.arange(T)
-    return mu, cov, ladder
+class Workload(object):
+    """One BASELINE configuration: sizes, target, proposal mix, and what the engine / sampler need."""
+
+    def __init__(self, name):
+        from ptmcmcsampler_b200 import _cabi
+
+        self.name = name
+        if name == "C2":
+            d, W, T = 20, 8192, 32
+            rng = np.random.default_rng(20)  # Sigma = A.A + 0.1 I, A as in ref examples/simple.py:27-30
+            A = 0.5 - rng.random(d * d).reshape(d, d)
+            A = np.triu(A)
+            A += A.T - np.diag(A.diagonal())
+            self.cov = A @ A + 0.1 * np.eye(d)
+            self.mu = 5.0 * np.ones(d)
+            self.box, self.inclusive = (-50.0, 60.0), True
+            self.weights = (20, 20, 20)
+            self.cov0 = 0.01 * np.eye(d)
+            self.x0 = lambda seed, T_, W_: np.random.default_rng(seed).uniform(0, 10, (T_, W_, d))
+            self.logl_kind = _cabi.LOGL_GAUSSIAN
+            self.desc = "C2: 20-dim Gaussian, 8192 walkers x 32 temps per GPU, SCAM/AM/DE 20/20/20"
+        elif name == "C3":
+            d, W, T = 100, 4096, 64
+            s = np.logspace(-1, 1, d)
+            idx = np.arange(d)
+            self.cov = 0.9 ** np.abs(idx[:, None] - idx[None, :]) * s[:, None] * s[None, :]
+            self.mu = np.zeros(d)
+            self.box, self.inclusive = (-500.0, 500.0), True
+            self.weights = (20, 20, 20)
+            self.cov0 = np.diag(0.01 * s * s)
+            self.x0 = lambda seed, T_, W_: np.random.default_rng(seed).standard_normal((T_, W_, d)) * s
+            self.logl_kind = _cabi.LOGL_GAUSSIAN
+            self.desc = "C3: 100-dim correlated Gaussian (dense cov 0.9^|i-j| s_i s_j), 4096 walkers x 64 temps, SCAM/AM/DE 20/20/20"
+        elif name == "C4":
+            d, W, T = 10, 16384, 128
+            self.cov, self.mu = None, None
+            self.box, self.inclusive = (-10.0, 10.0), False
+            self.weights = (10, 10, 60)
+            self.cov0 = 0.1 * np.eye(d)
+            self.x0 = lambda seed, T_, W_: np.random.default_rng(seed).uniform(-1, 1, (T_, W_, d))
+            self.logl_kind = _cabi.LOGL_CURVED
+            self.desc = ("C4: curved 10-dim (five copies of the reference's 2-D curved density), 16384 walkers x 128 temps, "
+                         "SCAM/AM/DE 10/10/60")
+        else:
+            raise ValueError(name)
+        self.d, self.W, self.T = d, W, T
+        self.ladder = np.minimum((1 + np.sqrt(2.0 / d)) ** np.arange(T), 1e30)
+        ws = float(sum(self.weights))
+        self.p_scam, self.p_am, self.p_de = (w / ws for w in self.weights)
+        self.icov = np.linalg.inv(self.cov) if self.cov is not None else None
+        # flops of one log-likelihood: dense Gaussian 2d^2+3d; curved ~ 2 exp + 1 log + 20 flops per pair
+        self.f_logl = (2 * d * d + 3 * d) if self.cov is not None else (d // 2) * 80
+        self.bytes_per_step = algorithmic_bytes_per_chain_step(d, T, THIN, self.p_de)
+        self.flops_per_step = algorithmic_flops_per_chain_step(d, self.f_logl, self.p_am, self.p_scam, self.p_de)
+
+    def engine_kwargs(self):
+        from ptmcmcsampler_b200 import _cabi
+
+        d = self.d
+        kw = dict(cycle=((_cabi.JUMP_SCAM, self.weights[0]), (_cabi.JUMP_AM, self.weights[1])), de_weight=self.weights[2],
+                  cov_update=COV_UPDATE, burn=BURN, tskip=TSKIP, thin=THIN, logl_kind=self.logl_kind,
+                  logp_params=np.concatenate([self.box[0] * np.ones(d), self.box[1] * np.ones(d),
+                                              [0.0, 1.0 if self.inclusive else 0.0]]))
+        if self.icov is not None:
+            kw["logl_params"] = np.concatenate([self.mu, self.icov.ravel(), [0.0]])
+        return kw
+
+    def targets(self):
+        from ptmcmcsampler_b200.likelihoods import CurvedLikelihood, GaussianLikelihood, UniformPrior
+
+        lk = GaussianLikelihood(self.mu, icov=self.icov) if self.icov is not None else CurvedLikelihood()
+        return lk, UniformPrior(self.box[0], self.box[1], inclusive=self.inclusive)
+
+    def sample_kwargs(self):
+        return dict(burn=BURN, covUpdate=COV_UPDATE, Tskip=TSKIP, thin=THIN, isave=ITERS, SCAMweight=self.weights[0],
+                    AMweight=self.weights[1], DEweight=self.weights[2])
 
 
 class ClockSampler(object):
@@ -120,19 +189,21 @@ class ClockSampler(object):
         return out
 
 
+# ------------------------------------------------------------------------------------------ CPU arms
 def cpu_port_rate(walkers, iters, threads, seed=3):
     """Time the CPU oracle (plain-C port of the reference algorithm) on a bounded sample of the
-    same workload: `walkers` x 32 temperatures x `iters` iterations."""
+    C2 workload: `walkers` x 32 temperatures x `iters` iterations."""
     from oracle import oracle as orc
 
-    mu, cov, ladder = problem()
-    o = orc.Oracle(D, walkers, T, 0.01 * np.eye(D), seed=seed, ladder=ladder,
-                   cycle=((orc.JUMP_SCAM, WEIGHTS[0]), (orc.JUMP_AM, WEIGHTS[1])), de_weight=WEIGHTS[2],
+    wl = Workload("C2")
+    D, T = wl.d, wl.T
+    o = orc.Oracle(D, walkers, T, wl.cov0, seed=seed, ladder=wl.ladder,
+                   cycle=((orc.JUMP_SCAM, wl.weights[0]), (orc.JUMP_AM, wl.weights[1])), de_weight=wl.weights[2],
                    cov_update=COV_UPDATE, burn=BURN, tskip=TSKIP, thin=THIN,
-                   logl_params=orc.gaussian_params(mu, np.linalg.inv(cov)),
+                   logl_params=orc.gaussian_params(wl.mu, wl.icov),
                    logp_params=orc.uniform_params(-50 * np.ones(D), 60 * np.ones(D)),
                    max_rows=(2 * iters) // THIN + 2, nthreads=threads)
-    o.set_state(np.random.default_rng(1).uniform(0, 10, (T, walkers, D)))
+    o.set_state(wl.x0(1, T, walkers))
     o.run(BURN + 1)          # DE joins the cycle, covariance adapted once: the steady-state mix
     t0 = time.perf_counter()
     o.run(iters)
@@ -140,20 +211,44 @@ def cpu_port_rate(walkers, iters, threads, seed=3):
     return walkers * T * iters / dt, dt
 
 
+def reference_python_rates(threads):
+    """The unmodified reference on this host (baseline/_ref, scripts/install_reference.sh): config 1 verbatim on
+    one core, and one process per core on the C2 target.  None when the install is absent."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import ref_worker
+    except Exception as exc:  # pragma: no cover
+        return {"unavailable": "baseline/ref_worker.py failed to import: %s" % exc}
+    if not ref_worker.available():
+        return {"unavailable": "baseline/_ref is absent (run scripts/install_reference.sh where /root/reference exists); "
+                               "the CPU arm is the C port alone"}
+    c1_rate, c1_dt = ref_worker.run_config1()
+    niter = 30000
+    all_rate, all_wall = ref_worker.run_c2_all_cores(threads, niter)
+    return {"config1": {"value": c1_rate, "unit": UNIT, "cores": 1, "seconds": c1_dt,
+                        "workload": "examples/simple.py verbatim: 20-dim Gaussian in a [0,10] box, 1 chain, 10000 iterations, "
+                                    "burn=covUpdate=500, thin=1"},
+            "value": all_rate, "unit": UNIT, "cores": threads, "seconds": all_wall,
+            "workload": "C2 target, one reference process per core, %d iterations each, thin=10, isave=Niter; independent "
+                        "chains (mpi4py is not in the image, so the reference's PTswap cannot run)" % niter,
+            "per_core": all_rate / threads}
+
+
 def run_reference(args, rank, world):
-    """Reference arm: the reference is pure Python and cannot travel to the GPU box, so this times
-    its plain-C restatement (oracle/, kind "port") on all host cores, same config and metric."""
+    """Reference arm: the path's CPU implementation on all host cores, same config and metric.  The ratio uses the
+    plain-C restatement of the reference algorithm (oracle/, kind "port": OpenMP over walkers, the strongest CPU
+    baseline available); the unmodified Python reference is timed beside it (`reference_python`)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     walkers, iters = 128 * threads, 1000
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_port_rate(walkers, 100, threads)
-    rates, times = [], []
+    times = []
     for _ in range(args.steps):
         r, dt = cpu_port_rate(walkers, iters, threads)
-        rates.append(r)
         times.append(dt)
+    T = 32
     value = float(walkers * T * iters * len(times) / sum(times))
     sample = "%d walkers x %d temps x %d iterations per step, OpenMP over walkers" % (walkers, T, iters)
     line = {
@@ -161,59 +256,76 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C2: 20-dim Gaussian, SCAM/AM/DE 20/20/20, covUpdate=burn=1000, Tskip=100, thin=10; "
-                               "CPU sample " + sample},
+                               "CPU sample " + sample,
+                   "cpu_sample_walkers": walkers,
+                   "note": "per-chain-step rate of a bounded sample (the full 8192 walkers would take minutes); the C port, "
+                           "not the Python reference, is the denominator of the driver's ratio"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ladder_steps_per_s": value / T,
+        "reference_python": reference_python_rates(threads),
     }
     print(json.dumps(line), flush=True)
 
 
-def run_engine(args, rank, world, local_rank):
+# ------------------------------------------------------------------------------------------ engine arm
+def peaks(local_rank):
+    from ptmcmcsampler_b200 import _cabi
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm, src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        hbm, src = 6650.0, "fallback (B200_PROFILING.md)"
+    fp64 = _cabi.measure_fp64_peak(local_rank)
+    return hbm, src, fp64
+
+
+def traffic_of(kernel_name):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json); null when the
+    capture is of another kernel."""
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(prof))
+        for rec in t.get("kernels", []):
+            if rec["kernel"].split("(")[0].strip() == kernel_name.split("(")[0].strip():
+                return rec["dram_bytes_per_launch"], rec.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
+def device_run(wl, args_steps, args_warmup, rank, world, local_rank, group=None, ladder_mode=False):
+    """Device-timed K steps of one workload with the state resident in HBM, then the same K steps with every
+    launch bracketed by CUDA events (per-class durations).  Returns a dict of raw measurements."""
     import torch
     import torch.distributed as dist
 
-    from ptmcmcsampler_b200 import PTMCMCSampler, _cabi, distributed
-    from ptmcmcsampler_b200.likelihoods import GaussianLikelihood, UniformPrior
+    from ptmcmcsampler_b200 import _cabi, distributed
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    group = None
-
-    mu, cov, ladder = problem()
-    icov = np.linalg.inv(cov)
-    lpar = np.concatenate([mu, icov.ravel(), [0.0]])
-    ppar = np.concatenate([-50 * np.ones(D), 60 * np.ones(D), [0.0, 1.0]])
-    total_iters = ITERS * (2 * args.steps + args.warmup)
-    ladder_mode = args.shard == "ladder" and world > 1
+    d, W, T = wl.d, wl.W, wl.T
+    kw = wl.engine_kwargs()
+    total_iters = ITERS * (2 * args_steps + args_warmup) + BURN + 100
+    ladder = wl.ladder
     shard_kw, Tg = dict(ntemps=T, ladder=ladder, walker_offset=rank * W), T
     if ladder_mode:  # BASELINE config 5: T rungs per GPU of one ladder of T * N rungs, same walkers everywhere
         Tg = T * world
-        ladder = np.minimum((1 + np.sqrt(2.0 / D)) ** np.arange(Tg), 1e30)
+        ladder = np.minimum((1 + np.sqrt(2.0 / d)) ** np.arange(Tg), 1e30)
         shard_kw = distributed.ladder_shard_kwargs(ladder, world, rank)
-    eng = _cabi.Engine(D, W, shard_kw.pop("ntemps"), 0.01 * np.eye(D), shard_kw.pop("ladder"), seed=42,
-                       cycle=((0, WEIGHTS[0]), (1, WEIGHTS[1])), de_weight=WEIGHTS[2], cov_update=COV_UPDATE, burn=BURN,
-                       tskip=TSKIP, thin=THIN, logl_params=lpar, logp_params=ppar, record_rows=total_iters // THIN + 2,
-                       device=local_rank, timing=False, **shard_kw)
-    x0 = np.random.default_rng(1 + rank).uniform(0, 10, (T, W, D))
-    eng.set_state(x0)
+    eng = _cabi.Engine(d, W, shard_kw.pop("ntemps"), wl.cov0, shard_kw.pop("ladder"), seed=42,
+                       record_rows=total_iters // THIN + 2, device=local_rank, timing=False, **kw, **shard_kw)
+    eng.set_state(wl.x0(1 + rank, T, W))
     comm = distributed.LadderComm(eng) if ladder_mode else None
 
-    def step():
+    def step(n=ITERS):
         if ladder_mode:
-            distributed.run_ladder(eng, ITERS, comm, TSKIP)
+            distributed.run_ladder(eng, n, comm, TSKIP)
         elif world > 1:
-            distributed.run(eng, ITERS, group)
+            distributed.run(eng, n, group)
         else:
-            eng.run(ITERS)
+            eng.run(n)
 
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    for _ in range(args.warmup):
+    for _ in range(args_warmup):
         step()
     eng.sync()
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
@@ -225,7 +337,7 @@ def run_engine(args, rank, world, local_rank):
     t_wall0 = time.time()
     # timed region: exactly K steps, nothing but the engine's own launches on its stream
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(args_steps):
         step()
     ev1.record(stream)
     eng.sync()
@@ -234,115 +346,178 @@ def run_engine(args, rank, world, local_rank):
         dist.barrier()
     t_wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
-    gpu_launches = int(sum(eng.timing()["launches"].values()))
+    launches = int(sum(eng.timing()["launches"].values()))
     # same K steps again with every launch bracketed by CUDA events on the engine's stream: the
     # per-kernel-class durations behind `roofline` (the bracketing serialises host and device, so this
     # pass is not the one `value` is taken from)
     eng.reset_timing()
     eng.set_timing(True)
-    for _ in range(args.steps):
+    for _ in range(args_steps):
         step()
     eng.sync()
-    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
     tm = eng.timing()
     eng.set_timing(False)
+    kernel = eng.mh_kernel_name
+    eng.close()
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    chain_steps_rank = W * T * ITERS * args.steps
-    value = world * chain_steps_rank / (ms * 1e-3)
+    return dict(ms=ms, steps=args_steps, launches=launches, tm=tm, kernel=kernel, wall=(t_wall0, t_wall1), Tg=Tg,
+                value=world * W * T * ITERS * args_steps / (ms * 1e-3))
 
-    # roofline of the dominant kernel (fused MH segment): algorithmic bytes per launch / mean duration
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+
+def roofline_of(wl, run, hbm_peak, hbm_src, fp64_peak):
+    """Roofline of the dominant kernel (the fused MH segment): algorithmic bytes and flops per launch over the
+    kernel's mean launch duration (CUDA events around every launch, measured in this run)."""
+    tm = run["tm"]
+    n_launch, mh_ms = max(1, tm["launches"]["mh"]), tm["ms"]["mh"]
+    steps_per_launch = wl.W * wl.T * ITERS * run["steps"] / n_launch
+    sec = mh_ms / n_launch * 1e-3
+    gbs = wl.bytes_per_step * steps_per_launch / sec / 1e9
+    tfs = wl.flops_per_step * steps_per_launch / sec / 1e12
+    traffic, traffic_src = traffic_of(run["kernel"])
+    total_ms = sum(tm["ms"].values())
+    common = {"kernel": run["kernel"], "launches": n_launch, "avg_launch_ms": mh_ms / n_launch,
+              "kernel_share_of_step": mh_ms / total_ms if total_ms > 0 else None, "class_ms": tm["ms"],
+              "algorithmic_bytes_per_chain_step": wl.bytes_per_step, "algorithmic_flops_per_chain_step": wl.flops_per_step,
+              "traffic": traffic, "traffic_source": traffic_src}
+    hbm = {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src}
+    fp64 = {"achieved": tfs, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfs / fp64_peak,
+            "peak_source": "measured in this run (ptmcmc_measure_fp64_peak: DFMA kernel, 8 chains x 512 threads x 2 blocks per SM)"}
+    # the binding bound is the one with the larger fraction of its peak (SURVEY 8d: HBM for C2 / C4, fp64 for C3)
+    if fp64["frac"] > hbm["frac"]:
+        out = dict(bound="tensor", **fp64)
+        out["note"] = ("fp64 is the binding bound (dense quadratic form and AM mat-vec run as fp64 DMMA on the tensor pipe; "
+                       "tcgen05 has no fp64 kind)")
+        out["hbm"] = hbm
     else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    bpcs = algorithmic_bytes_per_chain_step()
-    mh_launches, mh_ms = tm["launches"]["mh"], tm["ms"]["mh"]
-    steps_per_launch = W * T * ITERS * args.steps / max(1, mh_launches)
-    achieved = bpcs * steps_per_launch / (mh_ms / max(1, mh_launches) * 1e-3) / 1e9
-    fp64_peak = 37.1e12  # measured on this pool's B200: scripts/micro/dmma_rate.cu (DFMA and DMMA alike)
-    flops = algorithmic_flops_per_chain_step()
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "mh_sorted_kernel<20,256,2>", "peak_source": peak_src,
-                "fp64": {"algorithmic_flops_per_chain_step": flops, "peak_tflops": fp64_peak / 1e12,
-                         "achieved_tflops": flops * steps_per_launch / (mh_ms / max(1, mh_launches) * 1e-3) / 1e12,
-                         "frac": flops * steps_per_launch / (mh_ms / max(1, mh_launches) * 1e-3) / fp64_peak,
-                         "note": "the launch keeps chain state on chip for Tskip iterations, so fp64 issue, not HBM, "
-                                 "is the binding resource (SURVEY 8d)"},
-                "algorithmic_bytes_per_chain_step": bpcs, "launches": mh_launches,
-                "avg_launch_ms": mh_ms / max(1, mh_launches),
-                "kernel_share_of_step": mh_ms / sum(tm["ms"].values()) if sum(tm["ms"].values()) > 0 else None,
-                "class_ms": tm["ms"]}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("mh_kernel_dram_bytes_per_launch")
-        except Exception:
-            pass
-    eng.close()
+        out = dict(bound="hbm", **hbm)
+        out["note"] = ("algorithmic stream-in/stream-out bytes per chain-step over the launch time; a launch keeps chain state "
+                       "on chip for Tskip iterations, so real DRAM traffic (`traffic`) is far below the algorithmic bytes")
+        out["fp64"] = fp64
+    out.update(common)
+    return out
 
-    # end to end through the public API: host p0 in, recorded chain out, every step
-    lk, pr = GaussianLikelihood(mu, icov=icov), UniformPrior(-50.0, 60.0)
-    p0 = _cabi.pinned_empty((T, W, D))
-    p0[...] = np.random.default_rng(7 + rank).uniform(0, 10, (T, W, D))
+
+def e2e_run(wl, rank, world, local_rank, nrep, ladder_mode=False, Tg=None):
+    """End to end through the public API: host p0 in, recorded chain out, every step."""
+    import torch
+    import torch.distributed as dist
+
+    from ptmcmcsampler_b200 import PTMCMCSampler, _cabi
+
+    d, W, T = wl.d, wl.W, wl.T
+    Tg = Tg or T
+    ladder = np.minimum((1 + np.sqrt(2.0 / d)) ** np.arange(Tg), 1e30) if ladder_mode else None
+    lk, pr = wl.targets()
+    p0 = _cabi.pinned_empty((T, W, d))
+    p0[...] = wl.x0(7 + rank, T, W)
     outdir = tempfile.mkdtemp(prefix="ptmcmc_bench_")
 
-    def e2e_step(seed):
-        s = PTMCMCSampler.PTSampler(D, lk, pr, 0.01 * np.eye(D), outDir=outdir, verbose=False, seed=seed, ntemps=Tg,
+    def once(seed):
+        s = PTMCMCSampler.PTSampler(d, lk, pr, wl.cov0.copy(), outDir=outdir, verbose=False, seed=seed, ntemps=Tg,
                                     nwalkers=W, device=local_rank, walker_offset=0 if ladder_mode else rank * W,
                                     dist_group=True if world > 1 else None, shard="ladder" if ladder_mode else "walkers")
-        s.sample(p0, ITERS, burn=BURN, covUpdate=COV_UPDATE, Tskip=TSKIP, thin=THIN, isave=ITERS,
-                 SCAMweight=WEIGHTS[0], AMweight=WEIGHTS[1], DEweight=WEIGHTS[2],
-                 ladder=ladder if ladder_mode else None)
+        s.sample(p0, ITERS, ladder=ladder, **wl.sample_kwargs())
         loss = float(s._lnlike_all[-1].mean())   # the step's result read on the host
         d2h = s._chain_all.nbytes + s._lnlike_all.nbytes + s._lnprob_all.nbytes
-        s.engine.close()
+        s.close()
         return loss, d2h
 
-    e2e_step(100)
-    nrep = max(1, min(args.steps, 3))
+    once(100)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for r in range(nrep):
-        _, d2h = e2e_step(101 + r)
+        _, d2h = once(101 + r)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    e2e = {"value": world * W * T * ITERS * nrep / dt, "unit": UNIT, "h2d_bytes_per_step": int(p0.nbytes),
-           "d2h_bytes_per_step": int(d2h), "steps": nrep,
-           "note": "PTSampler(...).sample(p0_host, 1000): engine build, H2D of p0, 1000 iterations, D2H of the "
-                   "thinned T=1 record of all walkers, chain file of walker 0"}
+    return {"value": world * W * T * ITERS * nrep / dt, "unit": UNIT, "h2d_bytes_per_step": int(p0.nbytes),
+            "d2h_bytes_per_step": int(d2h), "steps": nrep,
+            "note": "PTSampler(...).sample(p0_host, 1000): engine build, H2D of p0, 1000 iterations, D2H of the "
+                    "thinned T=1 record of all walkers (overlapped with the run), chain file of walker 0"}
+
+
+def side_config(name, local_rank, hbm_peak, hbm_src, fp64_peak, steps=3, warmup=2):
+    """One of the other BASELINE configurations on this GPU (bounded: `steps` timed steps)."""
+    wl = Workload(name)
+    run = device_run(wl, steps, warmup, 0, 1, local_rank)
+    out = {"workload": wl.desc + ", covUpdate=burn=1000, Tskip=100, thin=10; step = 1000 MH iterations of all chains",
+           "value": run["value"], "unit": UNIT, "ms_per_step": run["ms"] / steps, "steps": steps, "warmup": warmup,
+           "ladder_steps_per_s": run["value"] / wl.T, "gpu_launches": run["launches"],
+           "roofline": roofline_of(wl, run, hbm_peak, hbm_src, fp64_peak)}
+    out["e2e"] = e2e_run(wl, 0, 1, local_rank, 2)
+    return out
+
+
+def run_engine(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    wl = Workload("C2")
+    ladder_mode = args.shard == "ladder" and world > 1
+    hbm_peak, hbm_src, fp64_peak = peaks(local_rank)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    run = device_run(wl, args.steps, args.warmup, rank, world, local_rank, ladder_mode=ladder_mode)
+    clk = clocks.stop(*run["wall"]) if rank == 0 else None
+    roofline = roofline_of(wl, run, hbm_peak, hbm_src, fp64_peak)
+    e2e = e2e_run(wl, rank, world, local_rank, max(1, min(args.steps, 3)), ladder_mode=ladder_mode, Tg=run["Tg"])
+
+    extra = {}
+    if world == 1 and not args.no_side:
+        extra["configs"] = {name: side_config(name, local_rank, hbm_peak, hbm_src, fp64_peak) for name in ("C3", "C4")}
+    if world > 1 and not ladder_mode and not args.no_side:
+        # BASELINE config 5: the same GPUs as ONE ladder of 32 N rungs, 32 per GPU, nearest-neighbour swap exchange
+        k = max(2, min(args.steps, 5))
+        r5 = device_run(wl, k, 2, rank, world, local_rank, ladder_mode=True)
+        extra["c5_ladder"] = {
+            "workload": "C5: %d-rung ladder as 32 rungs per GPU x %d GPUs, 8192 walkers, 20-dim Gaussian, NCCL nearest-neighbour "
+                        "exchange of the boundary rung at every swap; factor and AM ring broadcast from the T=1 shard" % (run["Tg"] * world, world),
+            "value": r5["value"], "unit": UNIT, "ms_per_step": r5["ms"] / k, "steps": k, "warmup": 2,
+            "fraction_of_walker_sharded": r5["value"] / run["value"], "gpu_launches": r5["launches"],
+            "roofline": roofline_of(wl, r5, hbm_peak, hbm_src, fp64_peak),
+            "e2e": e2e_run(wl, rank, world, local_rank, 2, ladder_mode=True, Tg=r5["Tg"])}
 
     cpu = None
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
         walkers = 128 * threads
         rate, dtc = cpu_port_rate(walkers, 1000, threads)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d walkers x %d temps x 1000 iterations (%.1f s)" % (walkers, T, dtc)}
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "cpu_sample_walkers": walkers,
+               "sample": "%d walkers x %d temps x 1000 iterations (%.1f s)" % (walkers, wl.T, dtc)}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: 20-dim Gaussian, 8192 walkers x 32 temps per GPU, SCAM/AM/DE 20/20/20, "
-                                   "covUpdate=burn=1000, Tskip=100, thin=10; step = 1000 MH iterations of all chains",
+            "metric": METRIC, "value": run["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": run["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64",
+            "dtype_note": "state, proposals, likelihood and the Hastings test are f64; the Box-Muller normals of the AM / SCAM "
+                          "proposals are generated in f32 with individually rounded operations (24-bit mantissa, |z| <= 6.76, "
+                          "bit-identical on the CPU oracle; KS / tail tests in tests/test_oracle_golden.py)",
+            "data": "synthetic",
+            "config": {"workload": wl.desc + ", covUpdate=burn=1000, Tskip=100, thin=10; step = 1000 MH iterations of all chains",
                        "l2": "no flush needed: each step streams the 1.3 GB AM ring and gathers from the 1.3 GB DE "
                              "history (inputs >> 126 MB L2)",
-                       "parallelism": ("ladder-sharded x%d (%d rungs, neighbour exchange of the boundary rung)" % (world, Tg)
+                       "parallelism": ("ladder-sharded x%d (%d rungs, neighbour exchange of the boundary rung)" % (world, run["Tg"])
                                        if ladder_mode else "walker-sharded x%d" % world)},
-            "ladder_steps_per_s": value / T,
-            "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
+            "ladder_steps_per_s": run["value"] / wl.T,
+            "clocks": clk, "e2e": e2e, "gpu_launches": run["launches"], "roofline": roofline, "cpu_baseline": cpu,
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -356,7 +531,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--shard", default="walkers", choices=["walkers", "ladder"],
                     help="N > 1: independent walkers per GPU (default, the contract's weak scaling) or one ladder of "
-                         "32 N rungs split over the GPUs (BASELINE config 5)")
+                         "32 N rungs split over the GPUs (BASELINE config 5; also measured as `c5_ladder` in the default run)")
+    ap.add_argument("--no-side", action="store_true", help="skip the C3 / C4 / C5 side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -229,6 +229,27 @@ int32_t ptmcmc_get_counters(ptmcmc_engine *e, int64_t *prop, int64_t *acc, int64
 int32_t ptmcmc_get_trace(ptmcmc_engine *e, uint8_t *trace, int64_t iters, int16_t *swapmaps,
                          int64_t events);
 
+/* Record sink: overlaps the device->host copy of the thinned record with sampling.  The reference stores every
+ * thinned sample into _chain / _lnlike / _lnprob as it goes (ref :331-335); with a sink registered the engine does
+ * the same: after every enqueued segment the rows it completed are copied, on a second stream ordered by events,
+ * to the caller's arrays chain [row_capacity][ntr][W][d], lnl / lnprob [row_capacity][ntr][W] at their absolute
+ * row positions (rows >= row_capacity are dropped).  EXCEPTION to the "no host pointer is kept" rule: the three
+ * arrays (page-locked memory, e.g. ptmcmc_host_alloc) must stay valid until ptmcmc_set_sink(e, NULL, ...) or
+ * ptmcmc_destroy.  With a sink the device window needs no ptmcmc_release_rows: it is reused as soon as its rows
+ * have landed, and ptmcmc_run never fails with PTMCMC_ERR_CAPACITY. */
+int32_t ptmcmc_set_sink(ptmcmc_engine *e, double *chain, double *lnl, double *lnprob, int64_t row_capacity);
+/* block until every row recorded by the calls made so far has landed in the sink */
+int32_t ptmcmc_sink_wait(ptmcmc_engine *e);
+/* Asynchronous snapshot of what the reference's writeOutput needs (ref :341-372, :722-766), ordered after the
+ * work enqueued so far and before anything enqueued later: host (page-locked, ptmcmc_snapshot_bytes() bytes)
+ * receives  int64 {iteration, swapProposed, nsamp, njumps}, int64 prop_sum[nj][T], acc_sum[nj][T] (summed over
+ * walkers), prop_w0[nj][T], acc_w0[nj][T] (walker 0), swap_sum[T], swap_w0[T], then doubles cov[d*d], mu[d],
+ * M2[d*d], U, S.  Two slots so that the host can write files for one boundary while the next segment runs;
+ * ptmcmc_snapshot_wait(slot) blocks until that snapshot (and every sink row before it) has landed. */
+int64_t ptmcmc_snapshot_bytes(const ptmcmc_engine *e);
+int32_t ptmcmc_snapshot(ptmcmc_engine *e, void *host, int64_t nbytes, int32_t slot);
+int32_t ptmcmc_snapshot_wait(ptmcmc_engine *e, int32_t slot);
+
 int32_t ptmcmc_get_timing(ptmcmc_engine *e, ptmcmc_timing *out);
 int32_t ptmcmc_reset_timing(ptmcmc_engine *e);
 /* switch the per-launch CUDA-event bracketing on or off (same as cfg.timing) */

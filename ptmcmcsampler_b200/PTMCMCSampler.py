@@ -123,6 +123,12 @@ class PTSampler(object):
 
             self._shard_rank, self._shard_world = dist.get_rank(self._group), dist.get_world_size(self._group)
             self.MPIrank = self._shard_rank  # rank g holds rungs [g*T/G, (g+1)*T/G), ref :94-97, :278
+        if dist_group is not None and shard == "walkers":
+            import torch.distributed as dist
+
+            r = dist.get_rank(self._group)
+            if r > 0:  # every rank holds its own walkers: its files must not collide with another rank's
+                outDir = os.path.join(outDir, "rank%d" % r)
         self._lo, self._Tloc = 0, self.nchain
         self._comm = None
         if seed is None:
@@ -262,6 +268,11 @@ class PTSampler(object):
             if self._external:
                 raise NotImplementedError("ladder sharding needs device targets and the built-in proposals")
             self._comm = distributed.LadderComm(self._engine, self._group)
+        # the thinned T=1 record streams into the result arrays while the engine runs (hot-rung records and
+        # engine checkpoints are taken synchronously at every write instead)
+        self._async = self._engine.ntr == 1 and not self._external and not self.checkpoint
+        if self._engine.ntr == 1:
+            self._engine.set_sink(self._chain_all, self._lnlike_all, self._lnprob_all)
         self._pull_factor()
 
     def _default_groups(self):
@@ -310,6 +321,9 @@ class PTSampler(object):
         self.ind_next_write = 0
         self._rows_pulled = 0
         self._counters_at = None
+        self._acc_offset = 0.0
+        self._full_counters = None
+        self._acc_w0 = self._swap_w0 = None
         self.naccepted = 0
         self.swapProposed = 0
         self.nswap_accepted = 0
@@ -345,6 +359,7 @@ class PTSampler(object):
         # resume (ref :289-319): an engine checkpoint if there is one, else the reference's replay of the chain file
         self.resumeLength = 0
         self.resumechain = None
+        self._resumed_at = 0
         self._state_file = os.path.join(self.outDir, "engine_state.npy" if self._shard_world == 1
                                         else "engine_state_%d.npy" % self._shard_rank)
         self._resume_state = self.resume and os.path.isfile(self._state_file)
@@ -385,9 +400,10 @@ class PTSampler(object):
         r0 = self._rows_pulled
         n = min(rows - r0, self._chain_all.shape[0] - r0)
         if eng.ntr == 1:
-            # T=1 rung only: the device rows land directly in the (pinned) result arrays
-            eng.chain(r0, n, out=(self._chain_all[r0:r0 + n], self._lnlike_all[r0:r0 + n],
-                                  self._lnprob_all[r0:r0 + n]))
+            # T=1 rung only: the device rows stream straight into the (pinned) result arrays (record sink)
+            eng.sink_wait()
+            self._rows_pulled = min(rows, self._chain_all.shape[0])
+            return
         else:
             ch, lnl, lnp = eng.chain(r0, n)
             self._chain_all[r0:r0 + n] = ch[:, 0]
@@ -399,9 +415,31 @@ class PTSampler(object):
         self._rows_pulled = rows
         eng.release_rows(rows)
 
+    _JUMP_NAMES = {_cabi.JUMP_SCAM: "covarianceJumpProposalSCAM", _cabi.JUMP_AM: "covarianceJumpProposalAM",
+                   _cabi.JUMP_DE: "DEJump", _cabi.JUMP_PRIOR: "priorDrawJump"}
+
+    def _jump_names(self):
+        names = dict(self._JUMP_NAMES)
+        for k, f in enumerate(self._ext_jumps):
+            names[_cabi.JUMP_EXT0 + k] = f.__name__
+        return names
+
+    def _set_counter_summary(self, prop_sum, acc_sum, acc_w0, swap_sum, swap_w0, nsw):
+        """jumpDict / naccepted / swap statistics from per-rung sums over walkers ([njumps][T]) and walker 0's values."""
+        for jid, name in self._jump_names().items():
+            if jid < prop_sum.shape[0] and (name in self.jumpDict or prop_sum[jid, 0] > 0):
+                # T=1 rung, summed over walkers (one walker: the reference's rank-0 jumpDict)
+                self.jumpDict[name] = [int(prop_sum[jid, 0]), int(acc_sum[jid, 0])]
+        self._acc_w0 = acc_w0.sum(axis=0)        # walker 0, per local rung
+        self._swap_w0 = np.asarray(swap_w0)
+        self.naccepted = acc_sum[:, 0].sum() / float(self.nwalkers) + self._acc_offset
+        self.swapProposed = nsw
+        self.nswap_accepted = swap_sum[0] / float(self.nwalkers)
+
     def _pull_counters(self):
+        """Synchronous pull of every per-chain counter (the asynchronous path uses ptmcmc_snapshot's summary)."""
         it = self._engine.iteration
-        if getattr(self, "_counters_at", None) == it:
+        if getattr(self, "_counters_at", None) == it and self._full_counters is not None:
             return
         self._counters_at = it
         if it == 0:  # nothing proposed yet: no device round trip
@@ -410,21 +448,23 @@ class PTSampler(object):
             sw, nsw = np.zeros(shp[:2], dtype=np.int64), 0
         else:
             prop, acc, sw, nsw = self._engine.counters()
+        self._full_counters = (prop, acc, sw)
         self._prop, self._acc, self._swap_acc = prop, acc, sw
-        names = {_cabi.JUMP_SCAM: "covarianceJumpProposalSCAM", _cabi.JUMP_AM: "covarianceJumpProposalAM",
-                 _cabi.JUMP_DE: "DEJump", _cabi.JUMP_PRIOR: "priorDrawJump"}
-        for k, f in enumerate(self._ext_jumps):
-            names[_cabi.JUMP_EXT0 + k] = f.__name__
-        for jid, name in names.items():
-            if jid < prop.shape[2] and (name in self.jumpDict or prop[0, :, jid].sum() > 0):
-                # T=1 rung, summed over walkers (one walker: the reference's rank-0 jumpDict)
-                self.jumpDict[name] = [int(prop[0, :, jid].sum()), int(acc[0, :, jid].sum())]
-        # acc is a [T][W][njumps] view of the engine's [njumps][T][W] array: reduce along the contiguous layout
-        self.naccepted_all = np.add.reduce(acc.transpose(2, 0, 1), axis=0)  # [T][W]
-        self.naccepted = self.naccepted_all[0].sum() / float(self.nwalkers) + getattr(self, "_acc_offset", 0.0)
-        self.swapProposed = nsw
-        self.nswap_accepted = sw[0].sum() / float(self.nwalkers)
-        self.nswap_accepted_all = sw
+        # prop / acc are [T][W][njumps] views of the engine's [njumps][T][W] arrays: reduce along the contiguous layout
+        pj, aj = prop.transpose(2, 0, 1), acc.transpose(2, 0, 1)
+        self._set_counter_summary(pj.sum(axis=2), aj.sum(axis=2), aj[:, :, 0], sw.sum(axis=1), sw[:, 0], nsw)
+
+    @property
+    def naccepted_all(self):
+        """Accepted MH steps of every chain, [T][W] (fetched from the device on access)."""
+        self._pull_counters()
+        return np.add.reduce(self._full_counters[1].transpose(2, 0, 1), axis=0)
+
+    @property
+    def nswap_accepted_all(self):
+        """Accepted swaps with the next-hotter rung of every chain, [T][W] (fetched from the device on access)."""
+        self._pull_counters()
+        return self._full_counters[2]
 
     def updateChains(self, p0, lnlike0, lnprob0, iter):
         """The reference's per-iteration buffer/record hook (ref :321-339) is fused into the kernels;
@@ -433,6 +473,10 @@ class PTSampler(object):
 
     def writeOutput(self, iter):
         """Write chain rows, covariance and jump statistics (ref :341-372)."""
+        if self._async:
+            self._engine.snapshot(0)
+            self._write_boundary(iter, 0)
+            return
         self._pull_rows()
         self._pull_counters()
         if iter // self.thin >= self.ind_next_write:
@@ -444,14 +488,51 @@ class PTSampler(object):
                 tmp = self._state_file + ".tmp.npy"
                 np.save(tmp, self._engine.save_state())
                 os.replace(tmp, self._state_file)
-            if self.verbose:
-                if iter > 0:
-                    sys.stdout.write("\r")
-                percent = iter / self.Niter * 100
-                acceptance = self.naccepted / iter if iter > 0 else 0
-                sys.stdout.write("Finished %2.2f percent in %f s Acceptance rate = %g"
-                                 % (percent, time.time() - self.tstart, acceptance))
-                sys.stdout.flush()
+            self._progress(iter)
+
+    def _progress(self, iter):
+        """Progress line (ref :353-372); on resume the percentage is of the new work, as in the reference (:359-367)."""
+        if not self.verbose:
+            return
+        if iter > 0:
+            sys.stdout.write("\r")
+        done0 = getattr(self, "_resumed_at", 0)
+        if done0 and self.Niter > done0:
+            percent = (iter - done0) / (self.Niter - done0) * 100
+        else:
+            percent = iter / self.Niter * 100
+        acceptance = self.naccepted / iter if iter > 0 else 0
+        sys.stdout.write("Finished %2.2f percent in %f s Acceptance rate = %g" % (percent, time.time() - self.tstart, acceptance))
+        sys.stdout.flush()
+
+    def _write_boundary(self, iter, slot):
+        """Finish the write of iteration ``iter`` from snapshot ``slot`` (taken on the engine's stream right after that
+        iteration): the engine may already be running the next segment."""
+        snap = self._engine.snapshot_result(slot)   # waits for the snapshot and every record row before it
+        self._rows_pulled = min(iter // self.thin + 1, self._chain_all.shape[0])
+        self._full_counters = None
+        self._counters_at = None
+        self._set_counter_summary(snap["prop_sum"], snap["acc_sum"], snap["acc_w0"], snap["swap_sum"], snap["swap_w0"],
+                                  snap["swap_proposed"])
+        if iter // self.thin >= self.ind_next_write:
+            self._writeToFile(iter)
+            if iter > 0:
+                self._apply_adapt(snap["cov"], snap["mu"], snap["m2"], snap["U"], snap["S"])
+                if self.MPIrank == 0:
+                    np.save(self.outDir + "/cov.npy", np.asarray(self.cov))
+            self._progress(iter)
+
+    def _apply_adapt(self, cov, mu, m2, U, S):
+        if self.MPIrank == 0:
+            np.asarray(self.cov)[:, :] = cov  # in place, like the reference (:794)
+            self.mu, self.M2 = mu, m2
+        uo = so = 0
+        for g, grp in enumerate(self.groups):
+            n = len(grp)
+            self.U[g] = U[uo:uo + n * n].reshape(n, n).copy()
+            self.S[g] = S[so:so + n].copy()
+            uo += n * n
+            so += n
 
     def _writeToFile(self, iter):
         """Chain file: ndim columns ``%22.22f`` then lnprob, lnlike, acceptance rate, PT swap
@@ -459,21 +540,22 @@ class PTSampler(object):
         reference's layout; all walkers stay available in ``_chain_all``."""
         write_end = iter // self.thin + 1
         rows = range(self.ind_next_write, min(write_end, self._rows_pulled))
-        acc_rate = (self.naccepted_all[0, 0] + getattr(self, "_acc_offset", 0.0)) / iter if iter > 0 else 0
+        acc_rate = (self._acc_w0[0] + self._acc_offset) / iter if iter > 0 else 0
         pt_acc = 1  # the hottest chain has no hotter partner (ref :737-739)
         if self._lo < self.nchain - 1 and self.swapProposed != 0:
-            pt_acc = self.nswap_accepted_all[0, 0] / self.swapProposed
+            pt_acc = self._swap_w0[0] / self.swapProposed
         if self._writes_primary:
+            tail = "\t%f\t%f\t%f\t%f\n"
+            fmt = "\t".join(["%22.22f"] * self.ndim) + tail
             with open(self.fname, "a+") as fh:
-                for ind in rows:
-                    fh.write("\t".join(["%22.22f" % v for v in self._chain[ind]]))
-                    fh.write("\t%f\t%f\t%f\t%f\n" % (self._lnprob[ind], self._lnlike[ind], acc_rate, pt_acc))
+                fh.write("".join([fmt % (tuple(self._chain[ind]) + (self._lnprob[ind], self._lnlike[ind], acc_rate, pt_acc))
+                                  for ind in rows]))
         if self.writeHotChains and self._hot_rows:
             for t in range(1, self._Tloc):
-                a_t = self.naccepted_all[t, 0] / iter if iter > 0 else 0
+                a_t = self._acc_w0[t] / iter if iter > 0 else 0
                 p_t = 1
                 if self._lo + t < self.nchain - 1 and self.swapProposed != 0:
-                    p_t = self.nswap_accepted_all[t, 0] / self.swapProposed
+                    p_t = self._swap_w0[t] / self.swapProposed
                 with open(self._hot_fnames[t], "a+") as fh:
                     for r0, ch, lnl, lnp in self._hot_rows:
                         for i in range(ch.shape[0]):
@@ -656,13 +738,24 @@ class PTSampler(object):
             self.writeOutput(i0)  # row 0 (ref :491 -> updateChains -> writeOutput at iter 0)
 
         iter = i0
+        pending, slot = None, 0
         while iter < self.Niter:
             # advance to the next multiple of isave, the reference's write cadence (ref :338-339)
             nxt = min(self.Niter, (iter // self.isave + 1) * self.isave)
             self._advance(nxt - iter, iter)
             iter = nxt
             if iter % self.isave == 0 or iter >= self.Niter:
-                self.writeOutput(iter)
+                if self._async:
+                    # the engine returns as soon as the segment is enqueued: snapshot what this write needs in stream
+                    # order, and write the PREVIOUS boundary's files while the device works on
+                    self._engine.snapshot(slot)
+                    if pending is not None:
+                        self._write_boundary(*pending)
+                    pending, slot = (iter, slot), slot ^ 1
+                else:
+                    self.writeOutput(iter)
+        if pending is not None:
+            self._write_boundary(*pending)
         self._finish()
         if self.verbose:
             print("\nRun Complete")
@@ -678,6 +771,20 @@ class PTSampler(object):
             if self.verbose:
                 print("Resuming from engine checkpoint {0} at iteration {1}".format(self._state_file, it))
             self._rows_pulled = self.ind_next_write = it // self.thin + 1
+            self._resumed_at = it
+            # rows before the checkpoint: walker 0's come back from its chain file (as the reference refills its arrays
+            # on resume, ref :291-299); the other walkers' rows are not stored anywhere and read as zeros
+            n0 = min(self._rows_pulled, self._chain_all.shape[0])
+            for a in (self._chain_all, self._lnlike_all, self._lnprob_all):
+                a[:n0] = 0.0
+            if os.path.isfile(self.fname):
+                try:
+                    old = np.loadtxt(self.fname, ndmin=2)[:n0]
+                    self._chain_all[:len(old), 0] = old[:, :self.ndim]
+                    self._lnprob_all[:len(old), 0] = old[:, -4]
+                    self._lnlike_all[:len(old), 0] = old[:, -3]
+                except ValueError:
+                    pass
             return it
         # the reference's replay (ref :474-476, :591-599): row 0 is the initial point, every stored row is
         # used for `thin` iterations; buffers, covariance and DE history are rebuilt through the normal
@@ -707,18 +814,30 @@ class PTSampler(object):
             self._pull_rows()
         self.ind_next_write = R                                # these rows are already in the file (ref :476)
         self._acc_offset = total * float(rc[-1, -2])           # ref :599
+        self._resumed_at = total
         return total
 
     def _finish(self):
-        self._pull_rows()
-        self._pull_counters()
+        if not self._async:
+            self._pull_rows()
+            self._pull_counters()
+            if self.MPIrank == 0:
+                self._pull_adapt()
+            else:
+                self._pull_factor()
+        elif self._engine.iteration == 0:
+            self._pull_counters()
         for a in (self._chain_all, self._lnlike_all, self._lnprob_all):
             a[self._rows_pulled:] = 0.0  # rows never reached (the reference's arrays start as zeros, :208-212)
-        if self.MPIrank == 0:
-            self._pull_adapt()
-        else:
-            self._pull_factor()
         self._buffers = None
+
+    def close(self):
+        """Release the device engine (the result arrays stay valid)."""
+        if self._engine is not None:
+            self._engine.sync()
+            self._engine.clear_sink()
+            self._engine.close()
+            self._engine = None
 
     def _fetch_buffers(self):
         if self._buffers is None:
@@ -750,6 +869,8 @@ class PTSampler(object):
         rates, as in a file written in one block."""
         if fname is None:
             fname = os.path.join(self.outDir, "chain_1_walker%d.txt" % walker)
+        if getattr(self, "_resumed_at", 0) and walker != 0:
+            raise ValueError("rows before the checkpoint exist for walker 0 only (its chain file); walker %d's are not stored" % walker)
         it = self._engine.iteration
         acc = (self.naccepted_all[0, walker] / it) if it > 0 else 0
         pt_acc = 1

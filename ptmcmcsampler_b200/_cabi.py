@@ -60,7 +60,8 @@ SYMBOLS = [
     "ptmcmc_host_alloc", "ptmcmc_host_free", "ptmcmc_swap_msg_doubles", "ptmcmc_swap_pending",
     "ptmcmc_swap_pack_top", "ptmcmc_swap_sweep", "ptmcmc_swap_finish", "ptmcmc_am_ring", "ptmcmc_maintain",
     "ptmcmc_state_bytes", "ptmcmc_save_state", "ptmcmc_load_state", "ptmcmc_replay", "ptmcmc_mh_kernel_name",
-    "ptmcmc_test_normals", "ptmcmc_measure_fp64_peak",
+    "ptmcmc_test_normals", "ptmcmc_measure_fp64_peak", "ptmcmc_set_sink", "ptmcmc_sink_wait", "ptmcmc_snapshot_bytes",
+    "ptmcmc_snapshot", "ptmcmc_snapshot_wait",
 ]
 
 _lib = None
@@ -135,6 +136,12 @@ def load():
     L.ptmcmc_mh_kernel_name.restype = C.c_char_p
     L.ptmcmc_mh_kernel_name.argtypes = [h]
     L.ptmcmc_measure_fp64_peak.argtypes = [C.c_int32, _dp]
+    L.ptmcmc_set_sink.argtypes = [h, _dp, _dp, _dp, C.c_int64]
+    L.ptmcmc_sink_wait.argtypes = [h]
+    L.ptmcmc_snapshot_bytes.restype = C.c_int64
+    L.ptmcmc_snapshot_bytes.argtypes = [h]
+    L.ptmcmc_snapshot.argtypes = [h, C.c_void_p, C.c_int64, C.c_int32]
+    L.ptmcmc_snapshot_wait.argtypes = [h, C.c_int32]
     L.ptmcmc_test_normals.argtypes = [C.c_int32, C.POINTER(C.c_uint64), C.c_int64, _dp, _dp]
     for name in SYMBOLS:
         getattr(L, name)
@@ -275,6 +282,8 @@ class Engine(object):
         if getattr(self, "_h", None):
             self._L.ptmcmc_destroy(self._h)
             self._h = None
+        self._sink = None
+        self._snap = None
 
     __del__ = close
 
@@ -448,6 +457,52 @@ class Engine(object):
         lnl = np.ascontiguousarray(np.broadcast_to(lnl, (nrows, self.T, self.W)), dtype=np.float64)
         lnprior = np.ascontiguousarray(np.broadcast_to(lnprior, (nrows, self.T, self.W)), dtype=np.float64)
         self._check(self._L.ptmcmc_replay(self._h, int(niter), int(repeat), nrows, _d(x), _d(lnl), _d(lnprior)))
+
+    # ---- asynchronous record sink and write-time snapshots --------------------------------------------
+    def set_sink(self, chain, lnl, lnprob):
+        """Stream recorded rows into the page-locked arrays chain [rows][ntr][W][d], lnl / lnprob [rows][ntr][W]
+        (kept alive by this object until ``clear_sink`` / ``close``)."""
+        for a in (chain, lnl, lnprob):
+            assert a.flags["C_CONTIGUOUS"] and a.dtype == np.float64
+        rows = chain.shape[0]
+        assert chain.size == rows * self.ntr * self.W * self.d and lnl.size == rows * self.ntr * self.W == lnprob.size
+        self._sink = (chain, lnl, lnprob)
+        self._check(self._L.ptmcmc_set_sink(self._h, _d(chain), _d(lnl), _d(lnprob), rows))
+
+    def clear_sink(self):
+        if getattr(self, "_h", None):
+            self._L.ptmcmc_set_sink(self._h, None, None, None, 0)
+        self._sink = None
+
+    def sink_wait(self):
+        self._check(self._L.ptmcmc_sink_wait(self._h))
+
+    def snapshot(self, slot):
+        """Enqueue a snapshot into slot 0 / 1; ``snapshot_result(slot)`` waits for it and decodes it."""
+        if getattr(self, "_snap", None) is None:
+            n = int(self._L.ptmcmc_snapshot_bytes(self._h))
+            self._snap = [pinned_empty((n // 8,), dtype=np.int64) for _ in range(2)]
+        buf = self._snap[slot]
+        self._check(self._L.ptmcmc_snapshot(self._h, buf.ctypes.data, buf.nbytes, slot))
+
+    def snapshot_result(self, slot):
+        self._check(self._L.ptmcmc_snapshot_wait(self._h, slot))
+        buf = self._snap[slot]
+        nj, T, d = self.njumps, self.T, self.d
+        it, nsw, nsamp = int(buf[0]), int(buf[1]), int(buf[2])
+        n = nj * T
+        summ = buf[4:4 + 4 * n + 2 * T]
+        out = dict(iteration=it, swap_proposed=nsw, nsamp=nsamp,
+                   prop_sum=summ[0:n].reshape(nj, T).copy(), acc_sum=summ[n:2 * n].reshape(nj, T).copy(),
+                   prop_w0=summ[2 * n:3 * n].reshape(nj, T).copy(), acc_w0=summ[3 * n:4 * n].reshape(nj, T).copy(),
+                   swap_sum=summ[4 * n:4 * n + T].copy(), swap_w0=summ[4 * n + T:4 * n + 2 * T].copy())
+        dbl = buf[4 + 4 * n + 2 * T:].view(np.float64)
+        o = 0
+        for name, cnt, shp in (("cov", d * d, (d, d)), ("mu", d, (d,)), ("m2", d * d, (d, d)), ("U", self.usize, (-1,)),
+                               ("S", self.ssize, (-1,))):
+            out[name] = dbl[o:o + cnt].reshape(shp).copy()
+            o += cnt
+        return out
 
     def timing(self):
         t = Timing()

@@ -119,6 +119,12 @@ struct Engine {
     double *d_q = nullptr, *d_qxy = nullptr, *d_lnl_new = nullptr, *d_lp_new = nullptr;
     int *d_jump = nullptr;
     unsigned *d_wordpos = nullptr;
+    // record sink: rows stream to caller-owned page-locked arrays on a copy stream as segments complete
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_rows = nullptr, ev_copied = nullptr, ev_snap[2] = {nullptr, nullptr};
+    double *sink_x = nullptr, *sink_lnl = nullptr, *sink_lnp = nullptr;
+    long long sink_cap = 0, copied = 0;
+    long long *d_snap[2] = {nullptr, nullptr};  // device staging of ptmcmc_snapshot, one per slot
     // timing
     ptmcmc_timing tm{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -392,6 +398,71 @@ int check_rows(Engine *e, long long end_iter)
     return 0;
 }
 
+// counter summary for the host's write cadence (ref jumpDict :602, :622, naccepted :620, nswap_accepted :691):
+// out = prop_sum[nj][T] | acc_sum[nj][T] | prop_w0[nj][T] | acc_w0[nj][T] | swap_sum[T] | swap_w0[T]; one block per (j, t)
+__global__ void __launch_bounds__(256) counter_summary_kernel(const unsigned long long *prop, const unsigned long long *acc,
+                                                              const unsigned long long *swap_acc, int nj, int T, int W,
+                                                              long long *out)
+{
+    __shared__ unsigned long long sh[3][8];
+    const int jt = blockIdx.x, j = jt / T, t = jt % T;
+    const size_t base = (size_t)jt * W;
+    unsigned long long a = 0, b = 0, c = 0;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        a += prop[base + w];
+        b += acc[base + w];
+        if (j == 0) c += swap_acc[(size_t)t * W + w];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; sh[2][threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = b = c = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh[0][i]; b += sh[1][i]; c += sh[2][i]; }
+        const int n = nj * T;
+        out[jt] = (long long)a;
+        out[n + jt] = (long long)b;
+        out[2 * n + jt] = (long long)prop[base];
+        out[3 * n + jt] = (long long)acc[base];
+        if (j == 0) {
+            out[4 * n + t] = (long long)c;
+            out[4 * n + T + t] = (long long)swap_acc[(size_t)t * W];
+        }
+    }
+}
+
+// rows whose record is complete in stream order -> the sink's host arrays (absolute row positions)
+cudaError_t sink_flush(Engine *e)
+{
+    if (!e->sink_x || e->rows <= e->copied) return cudaSuccess;
+    const long long r0 = std::max(e->copied, e->rec_base), r1 = std::min(e->rows, e->sink_cap);
+    e->copied = e->rows;
+    if (r1 <= r0) return cudaSuccess;
+    cudaError_t st = cudaEventRecord(e->ev_rows, e->stream);
+    if (st == cudaSuccess) st = cudaStreamWaitEvent(e->copy_stream, e->ev_rows, 0);
+    const size_t per_row = (size_t)e->ntr * e->W, off = (size_t)(r0 - e->rec_base) * per_row, dst = (size_t)r0 * per_row;
+    const size_t n = (size_t)(r1 - r0) * per_row;
+    if (st == cudaSuccess)
+        st = cudaMemcpyAsync(e->sink_x + dst * e->d, e->d_rec_x + off * e->d, sizeof(double) * n * e->d, cudaMemcpyDeviceToHost, e->copy_stream);
+    if (st == cudaSuccess) st = cudaMemcpyAsync(e->sink_lnl + dst, e->d_rec_lnl + off, sizeof(double) * n, cudaMemcpyDeviceToHost, e->copy_stream);
+    if (st == cudaSuccess) st = cudaMemcpyAsync(e->sink_lnp + dst, e->d_rec_lnp + off, sizeof(double) * n, cudaMemcpyDeviceToHost, e->copy_stream);
+    if (st == cudaSuccess) st = cudaEventRecord(e->ev_copied, e->copy_stream);
+    return st;
+}
+
+// with a sink the window is reused once its rows are on the host: no compaction, no host synchronisation
+cudaError_t sink_recycle(Engine *e)
+{
+    cudaError_t st = sink_flush(e);
+    if (st == cudaSuccess) st = cudaStreamWaitEvent(e->stream, e->ev_copied, 0);
+    e->rec_base = e->rows;
+    return st;
+}
+
 }  // namespace
 
 extern "C" {
@@ -437,6 +508,9 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     g_alloc_stream = e->stream;  // allocations, fills and uploads below are ordered on the engine's stream
     CUDA_TRY(nullptr, cudaEventCreate(&e->ev0));
     CUDA_TRY(nullptr, cudaEventCreate(&e->ev1));
+    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t *ev : {&e->ev_rows, &e->ev_copied, &e->ev_snap[0], &e->ev_snap[1]})
+        CUDA_TRY(nullptr, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     e->ladder.assign(cfg->ladder, cfg->ladder + T);
     e->mh_temp.assign(cfg->mh_temp ? cfg->mh_temp : cfg->ladder, (cfg->mh_temp ? cfg->mh_temp : cfg->ladder) + T);
     // groups (ref :129-131)
@@ -694,12 +768,16 @@ void ptmcmc_destroy(ptmcmc_engine *h)
                     e->d_plo, e->d_phi, e->d_rec_x, e->d_rec_lnl, e->d_rec_lnp, e->d_prop, e->d_acc,
                     e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_part2, e->d_batch, e->d_gram,
                     e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos, e->d_stage,
-                    e->d_carry_code, e->d_carry_L, e->d_Uf, e->d_Pf, e->d_gPfull, e->d_Ut};
+                    e->d_carry_code, e->d_carry_L, e->d_Uf, e->d_Pf, e->d_gPfull, e->d_Ut, e->d_snap[0], e->d_snap[1]};
     for (void *p : ptrs)
         if (p) cudaFreeAsync(p, e->stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    for (cudaEvent_t ev : {e->ev_rows, e->ev_copied, e->ev_snap[0], e->ev_snap[1]})
+        if (ev) cudaEventDestroy(ev);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -723,6 +801,7 @@ static int finish_set_state(Engine *e)
     e->iter = 0;
     e->rows = 1;
     e->rec_base = 0;
+    e->copied = 0;
     e->has_state = true;
     e->pending_swap = e->swept = false;
     DevParams p = make_params(e);
@@ -731,6 +810,7 @@ static int finish_set_state(Engine *e)
         bookkeep_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, 0);  // ref :491
     }
     CUDA_TRY(e, cudaGetLastError());
+    CUDA_TRY(e, sink_flush(e));
     return 0;
 }
 
@@ -780,8 +860,9 @@ int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
         return fail(e, PTMCMC_ERR_STATE,
                     "ladder-sharded engine: ptmcmc_run must stop at the swap iteration %lld (asked to reach %lld)",
                     next_multiple(e->iter + 1, tskip), end);
-    int rc = check_rows(e, end);
+    int rc = e->sink_x ? 0 : check_rows(e, end);
     if (rc) return rc;
+    const long long thin = e->cfg.thin, cap = e->cfg.record_rows;
     while (e->iter < end) {
         const long long it0 = e->iter + 1;
         rc = maintenance(e, it0);
@@ -791,6 +872,12 @@ int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
         seg_end = std::min(seg_end, next_multiple(it0, burn));
         const bool swaps = e->Tg > 1;
         if (swaps) seg_end = std::min(seg_end, next_multiple(it0, tskip));
+        if (e->sink_x && seg_end / thin - e->rec_base >= cap) {
+            // the window is full: its rows are on their way to the host; reuse it from slot 0 once they have landed
+            cudaError_t st = sink_recycle(e);
+            if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "record sink: %s", cudaGetErrorString(st));
+            seg_end = std::min(seg_end, (e->rec_base + cap) * thin - 1);
+        }
         const bool swap_now = swaps && (seg_end % tskip == 0);
         cudaError_t st = launch_mh(e, it0, seg_end, !swap_now);
         if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "MH kernel: %s", cudaGetErrorString(st));
@@ -802,9 +889,13 @@ int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
             if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "swap kernels: %s", cudaGetErrorString(st));
         }
         e->iter = seg_end;
+        // a pending sharded swap writes the record of its iteration in ptmcmc_swap_finish
+        e->rows = std::max(e->rows, (long long)((e->iter - (e->pending_swap ? 1 : 0)) / e->cfg.thin + 1));
+        if (e->sink_x) {
+            st = sink_flush(e);
+            if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "record sink: %s", cudaGetErrorString(st));
+        }
     }
-    // a pending sharded swap writes the record of its iteration in ptmcmc_swap_finish
-    e->rows = std::max(e->rows, (long long)((e->iter - (e->pending_swap ? 1 : 0)) / e->cfg.thin + 1));
     return 0;
 }
 
@@ -877,6 +968,7 @@ int32_t ptmcmc_accept(ptmcmc_engine *h, const double *q, const double *qxy, cons
     e->iter = it;
     e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
     e->pending_propose = false;
+    CUDA_TRY(e, sink_flush(e));
     return 0;
 }
 
@@ -887,6 +979,7 @@ int32_t ptmcmc_sync(ptmcmc_engine *h)
     Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->copy_stream));
     return 0;
 }
 
@@ -1142,6 +1235,7 @@ int32_t ptmcmc_swap_finish(ptmcmc_engine *h, const double *dev_below_top)
     e->swept = false;
     e->carry_in = nullptr;
     e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
+    CUDA_TRY(e, sink_flush(e));
     return 0;
 }
 
@@ -1256,6 +1350,7 @@ int32_t ptmcmc_load_state(ptmcmc_engine *h, const void *buf, int64_t nbytes)
     }
     e->rows = e->iter / e->cfg.thin + 1;
     e->rec_base = e->rows;  // the record window restarts empty after the checkpointed iteration
+    e->copied = e->rows;
     e->has_state = true;
     e->pending_swap = e->swept = e->pending_propose = false;
     cudaError_t st = build_u_frags(e);
@@ -1306,6 +1401,7 @@ int32_t ptmcmc_replay(ptmcmc_engine *h, int64_t niter, int64_t repeat, int64_t n
     CUDA_TRY(e, cudaGetLastError());
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
+    CUDA_TRY(e, sink_flush(e));
     return 0;
 }
 
@@ -1335,6 +1431,84 @@ int32_t ptmcmc_get_trace(ptmcmc_engine *h, uint8_t *trace, int64_t iters, int16_
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     if (trace) CUDA_TRY(e, cudaMemcpy(trace, e->d_trace, (size_t)iters * C, cudaMemcpyDeviceToHost));
     if (swapmaps) CUDA_TRY(e, cudaMemcpy(swapmaps, e->d_swapmaps, sizeof(short) * (size_t)events * C, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t ptmcmc_set_sink(ptmcmc_engine *h, double *chain, double *lnl, double *lnprob, int64_t row_capacity)
+{
+    Engine *e = engine_of(h);
+    if (!e) return PTMCMC_ERR_ARG;
+    if (e->copy_stream) CUDA_TRY(e, cudaStreamSynchronize(e->copy_stream));
+    if (!chain) {
+        e->sink_x = e->sink_lnl = e->sink_lnp = nullptr;
+        e->sink_cap = 0;
+        return 0;
+    }
+    if (!lnl || !lnprob || row_capacity < 1) return fail(e, PTMCMC_ERR_ARG, "ptmcmc_set_sink: three arrays and a row capacity");
+    e->sink_x = chain; e->sink_lnl = lnl; e->sink_lnp = lnprob;
+    e->sink_cap = row_capacity;
+    e->copied = e->has_state ? e->rows : 0;
+    return 0;
+}
+
+int64_t ptmcmc_snapshot_bytes(const ptmcmc_engine *h)
+{
+    const Engine *e = (const Engine *)h;
+    if (!e) return -1;
+    const size_t ni = 4 + (size_t)4 * e->njumps * e->T + 2 * (size_t)e->T;
+    const size_t nd = 2 * (size_t)e->d * e->d + e->d + e->uoff[e->ngroups] + e->soff[e->ngroups];
+    return (int64_t)(8 * (ni + nd));
+}
+
+int32_t ptmcmc_snapshot(ptmcmc_engine *h, void *host, int64_t nbytes, int32_t slot)
+{
+    Engine *e = engine_of(h);
+    if (!e || !host || slot < 0 || slot > 1) return PTMCMC_ERR_ARG;
+    if (nbytes < ptmcmc_snapshot_bytes(h)) return fail(e, PTMCMC_ERR_ARG, "snapshot buffer too small");
+    const int nj = e->njumps, T = e->T, d = e->d;
+    const size_t ns = (size_t)4 * nj * T + 2 * (size_t)T;
+    const size_t nd = 2 * (size_t)d * d + d + e->uoff[e->ngroups] + e->soff[e->ngroups];
+    if (!e->d_snap[slot]) {
+        g_alloc_stream = e->stream;
+        CUDA_TRY(e, dalloc(&e->d_snap[slot], ns + nd));
+    }
+    // staged on the compute stream (the next covariance update may rewrite cov / factor right away), copied out on the
+    // copy stream: the compute stream never waits for the host transfer
+    long long *stage = e->d_snap[slot];
+    counter_summary_kernel<<<nj * T, 256, 0, e->stream>>>(e->d_prop, e->d_acc, e->d_swap_acc, nj, T, e->W, stage);
+    e->tm.launches[PTMCMC_K_INIT] += 1;
+    CUDA_TRY(e, cudaGetLastError());
+    double *sd = (double *)(stage + ns);
+    struct { const double *src; size_t n; } parts[] = {{e->d_cov, (size_t)d * d}, {e->d_mu, (size_t)d}, {e->d_m2, (size_t)d * d},
+                                                       {e->d_U, (size_t)e->uoff[e->ngroups]}, {e->d_S, (size_t)e->soff[e->ngroups]}};
+    for (auto &pt : parts) {
+        CUDA_TRY(e, cudaMemcpyAsync(sd, pt.src, 8 * pt.n, cudaMemcpyDeviceToDevice, e->stream));
+        sd += pt.n;
+    }
+    CUDA_TRY(e, sink_flush(e));
+    CUDA_TRY(e, cudaEventRecord(e->ev_rows, e->stream));
+    CUDA_TRY(e, cudaStreamWaitEvent(e->copy_stream, e->ev_rows, 0));
+    long long *hi = (long long *)host;
+    hi[0] = e->iter; hi[1] = e->swap_proposed; hi[2] = e->nsamp; hi[3] = nj;
+    CUDA_TRY(e, cudaMemcpyAsync(hi + 4, stage, 8 * (ns + nd), cudaMemcpyDeviceToHost, e->copy_stream));
+    CUDA_TRY(e, cudaEventRecord(e->ev_snap[slot], e->copy_stream));
+    return 0;
+}
+
+int32_t ptmcmc_snapshot_wait(ptmcmc_engine *h, int32_t slot)
+{
+    Engine *e = engine_of(h);
+    if (!e || slot < 0 || slot > 1) return PTMCMC_ERR_ARG;
+    CUDA_TRY(e, cudaEventSynchronize(e->ev_snap[slot]));
+    return 0;
+}
+
+int32_t ptmcmc_sink_wait(ptmcmc_engine *h)
+{
+    Engine *e = engine_of(h);
+    if (!e) return PTMCMC_ERR_ARG;
+    CUDA_TRY(e, sink_flush(e));
+    CUDA_TRY(e, cudaStreamSynchronize(e->copy_stream));
     return 0;
 }
 

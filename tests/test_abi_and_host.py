@@ -127,10 +127,14 @@ def test_bench_accounting_and_clock_parsing(tmp_path):
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    assert abs(bench.algorithmic_bytes_per_chain_step() - 513.2667) < 1e-3          # C2: 513 B
-    assert abs(bench.algorithmic_flops_per_chain_step() - (860 + 40 + 800 / 3 + 80 / 3 + 30)) < 1e-9
-    mu, cov, ladder = bench.problem()
-    assert cov.shape == (20, 20) and np.all(np.linalg.eigvalsh(cov) > 0) and len(ladder) == 32
+    c2, c3, c4 = bench.Workload("C2"), bench.Workload("C3"), bench.Workload("C4")
+    assert abs(c2.bytes_per_step - 513.2667) < 1e-3 and abs(c3.bytes_per_step - 2291.2) < 0.5   # 513 B, 2 291 B
+    assert abs(c4.bytes_per_step - 354.2) < 0.5                                                    # 354 B
+    assert abs(c2.flops_per_step - (860 + 40 + 800 / 3 + 80 / 3 + 30)) < 1e-9
+    assert 2.6e4 < c3.flops_per_step < 2.8e4                                                       # ~2.7e4
+    assert c2.cov.shape == (20, 20) and np.all(np.linalg.eigvalsh(c2.cov) > 0) and len(c2.ladder) == 32
+    assert (c3.d, c3.W, c3.T) == (100, 4096, 64) and (c4.d, c4.W, c4.T, c4.weights) == (10, 16384, 128, (10, 10, 60))
+    assert set(c3.engine_kwargs()) >= {"cycle", "de_weight", "logl_params", "logp_params"}
     cs = bench.ClockSampler(0)
     cs.proc = type("P", (), {"terminate": lambda s: None, "wait": lambda s, timeout=None: 0, "kill": lambda s: None})()
     cs.path = str(tmp_path / "clk.csv")
