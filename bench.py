@@ -32,6 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ITERS = 1000          # MH iterations per bench step
+E2E_ITERS = 2000      # iterations of one end-to-end sample() call
 COV_UPDATE = BURN = 1000
 TSKIP, THIN = 100, 10
 METRIC = "walker-steps/sec (20-dim Gaussian, 8192 walkers x 32 temps)"
@@ -125,7 +126,7 @@ class Workload(object):
         return lk, UniformPrior(self.box[0], self.box[1], inclusive=self.inclusive)
 
     def sample_kwargs(self):
-        return dict(burn=BURN, covUpdate=COV_UPDATE, Tskip=TSKIP, thin=THIN, isave=ITERS, SCAMweight=self.weights[0],
+        return dict(burn=BURN, covUpdate=COV_UPDATE, Tskip=TSKIP, thin=THIN, isave=E2E_ITERS, SCAMweight=self.weights[0],
                     AMweight=self.weights[1], DEweight=self.weights[2])
 
 
@@ -419,7 +420,7 @@ def e2e_run(wl, rank, world, local_rank, nrep, ladder_mode=False, Tg=None):
         s = PTMCMCSampler.PTSampler(d, lk, pr, wl.cov0.copy(), outDir=outdir, verbose=False, seed=seed, ntemps=Tg,
                                     nwalkers=W, device=local_rank, walker_offset=0 if ladder_mode else rank * W,
                                     dist_group=True if world > 1 else None, shard="ladder" if ladder_mode else "walkers")
-        s.sample(p0, ITERS, ladder=ladder, **wl.sample_kwargs())
+        s.sample(p0, E2E_ITERS, ladder=ladder, **wl.sample_kwargs())
         loss = float(s._lnlike_all[-1].mean())   # the step's result read on the host
         d2h = s._chain_all.nbytes + s._lnlike_all.nbytes + s._lnprob_all.nbytes
         s.close()
@@ -438,10 +439,12 @@ def e2e_run(wl, rank, world, local_rank, nrep, ladder_mode=False, Tg=None):
         t = torch.tensor([dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    return {"value": world * W * T * ITERS * nrep / dt, "unit": UNIT, "h2d_bytes_per_step": int(p0.nbytes),
-            "d2h_bytes_per_step": int(d2h), "steps": nrep,
-            "note": "PTSampler(...).sample(p0_host, 1000): engine build, H2D of p0, 1000 iterations, D2H of the "
-                    "thinned T=1 record of all walkers (overlapped with the run), chain file of walker 0"}
+    return {"value": world * W * T * E2E_ITERS * nrep / dt, "unit": UNIT, "h2d_bytes_per_step": int(p0.nbytes),
+            "d2h_bytes_per_step": int(d2h), "steps": nrep, "iterations_per_step": E2E_ITERS,
+            "note": "one step = a fresh PTSampler(...).sample(p0_host, 2000): engine build, H2D of p0, 2000 iterations (DE joins "
+                    "the cycle at burn + 1 = 1001, so the second half runs the steady-state mix), D2H of the thinned T=1 "
+                    "record of all walkers streamed while the engine runs, covariance / counters snapshot, chain file of "
+                    "walker 0"}
 
 
 def side_config(name, local_rank, hbm_peak, hbm_src, fp64_peak, steps=3, warmup=2):

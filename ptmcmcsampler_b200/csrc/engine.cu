@@ -389,12 +389,20 @@ int maintenance(Engine *e, long long it0)
 
 long long next_multiple(long long it, long long m) { return ((it + m - 1) / m) * m; }
 
+cudaError_t sink_recycle(Engine *e);
+
 int check_rows(Engine *e, long long end_iter)
 {
     const long long last_row = end_iter / e->cfg.thin;
-    if (last_row - e->rec_base >= e->cfg.record_rows)
+    if (last_row - e->rec_base >= e->cfg.record_rows) {
+        if (e->sink_x) {  // rows stream to the host: reuse the window once they have landed
+            cudaError_t st = sink_recycle(e);
+            if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "record sink: %s", cudaGetErrorString(st));
+            if (last_row - e->rec_base < e->cfg.record_rows) return 0;
+        }
         return fail(e, PTMCMC_ERR_CAPACITY, "record window holds rows [%lld, %lld); iteration %lld needs row %lld",
                     e->rec_base, e->rec_base + e->cfg.record_rows, end_iter, last_row);
+    }
     return 0;
 }
 

@@ -83,7 +83,14 @@ def test_c3_full_size_matches_oracle():
 
 
 def test_c4_full_size_matches_oracle():
-    """BASELINE config 4: curved 10-dim density, 16384 walkers x 128 temperatures, SCAM/AM/DE = 10/10/60."""
+    """BASELINE config 4: curved 10-dim density, 16384 walkers x 128 temperatures, SCAM/AM/DE = 10/10/60.
+
+    The curved density  log(exp(A) + exp(B) / 2)  (ref examples/curved_likelihood.ipynb) underflows over most of the box; in the
+    narrow band where the exponentials are subnormal, one ulp of difference between CUDA's and glibc's exp is a relative
+    error of up to 1e-3 in the log-likelihood, so about one chain-step in 10^7 takes the other side of the Hastings test
+    and that chain's trajectory is a different (equally valid) one from there on.  Jump ids do not depend on floating
+    point and must agree everywhere; accept flags must agree on all but a handful of walkers until the first DE-history
+    update (iteration 100) couples the walkers through the pooled history."""
     d, W, T, niter = 10, 16384, 128, 220
     tgt = (orc.LOGL_CURVED, None, orc.LOGP_UNIFORM, orc.uniform_params(-10 * np.ones(d), 10 * np.ones(d), 0.0, False))
     ladder = np.minimum((1 + np.sqrt(2.0 / d)) ** np.arange(T), 1e30)
@@ -91,4 +98,54 @@ def test_c4_full_size_matches_oracle():
                      burn=100, tskip=50, thin=10, niter=niter, record_hot=False, ladder=ladder, nthreads=os.cpu_count() or 4)
     assert "mh_sorted_kernel" in g.mh_kernel_name
     x0 = np.random.default_rng(2).uniform(-1, 1, (T, W, d))
-    compare_full(o, g, x0, niter, 50, T, 1e-8)
+    nsw = niter // 50
+    otrace, oswap = o.set_trace(niter, nsw)
+    o.set_state(x0)
+    g.set_state(x0)
+    o.run(niter)
+    g.run(niter)
+    gtrace, gswap = g.trace(niter, nsw)
+    assert np.array_equal(gtrace & 0x7F, otrace & 0x7F), "jump ids differ"
+    diff = (gtrace >> 7) != (otrace >> 7)
+    bad_walkers = diff[:100].any(axis=(0, 1))          # a walker's rungs exchange states at every swap
+    assert bad_walkers.mean() < 0.01, "%d of %d walkers diverged before the first DE update" % (bad_walkers.sum(), W)
+    assert diff.mean() < 1e-3
+    good = ~bad_walkers
+    assert np.array_equal(gswap[:2, good], oswap[:2, good]), "swap maps of the unaffected walkers differ"
+    # the sampled distribution is unaffected: acceptance per jump and rung agrees far inside its Monte-Carlo error
+    (op, oa, _, _), (gp, ga, _, _) = o.counters(), g.counters()
+    assert np.array_equal(op, gp)
+    ra, rg = oa.sum(axis=1) / np.maximum(1, op.sum(axis=1)), ga.sum(axis=1) / np.maximum(1, gp.sum(axis=1))
+    assert np.allclose(ra, rg, atol=2e-3)
+
+
+def test_d100_reaches_target_covariance():
+    """Known answer at ndim 100 on the tensor-core kernel: an untruncated Gaussian target sampled at temperature T has
+    covariance T Sigma (SURVEY 8c KAT 1).  256 walkers x 4 rungs, 20 000 iterations, second half of the thinned record:
+    marginal variances within 3 % on average, every entry of the whitened covariance within 0.1 of the identity
+    (measured 0.045-0.05; at 2 000 iterations the adaptive proposal has not converged yet and the ratio is ~0.5)."""
+    from ptmcmcsampler_b200 import _cabi
+
+    d, W, T, niter = 100, 256, 4, 20000
+    s = np.logspace(-1, 1, d)
+    idx = np.arange(d)
+    cov = 0.9 ** np.abs(idx[:, None] - idx[None, :]) * s[:, None] * s[None, :]
+    ladder = (1 + np.sqrt(2.0 / d)) ** np.arange(T)
+    e = _cabi.Engine(d, W, T, np.diag(0.01 * s * s), ladder, seed=3, cov_update=1000, burn=1000, tskip=100, thin=10,
+                     logl_params=np.concatenate([np.zeros(d), np.linalg.inv(cov).ravel(), [0.0]]),
+                     logp_params=np.concatenate([-500 * np.ones(d), 500 * np.ones(d), [0.0, 1.0]]),
+                     record_rows=niter // 10 + 2, record_hot=True)
+    assert "mh_mma_kernel" in e.mh_kernel_name
+    e.set_state(np.random.default_rng(1).standard_normal((T, W, d)) * s)
+    e.run(niter)
+    ch = e.chain()[0]
+    half = ch[len(ch) // 2:]
+    L = np.linalg.cholesky(np.linalg.inv(cov))
+    for t in range(T):
+        x = half[:, t].reshape(-1, d)
+        ratio = x.var(0) / np.diag(cov) / ladder[t]
+        assert abs(ratio.mean() - 1.0) < 0.03, (t, ratio.mean())
+        assert 0.85 < ratio.min() and ratio.max() < 1.15, (t, ratio.min(), ratio.max())
+        wc = np.cov((x @ L).T) / ladder[t]
+        assert np.abs(wc - np.eye(d)).max() < 0.1, (t, np.abs(wc - np.eye(d)).max())
+        assert np.abs(x.mean(0) / np.sqrt(np.diag(cov) * ladder[t])).max() < 0.05
