@@ -179,6 +179,19 @@ int32_t ptmcmc_get_buffers(ptmcmc_engine *e, double *am, double *de);
 int32_t ptmcmc_adapt_begin(ptmcmc_engine *e, double *batch_out);
 int32_t ptmcmc_adapt_finish(ptmcmc_engine *e, const double *batch_in);
 
+/* The same without a host round trip (the collective runs on device memory, e.g. NCCL all-gather on the engine's
+ * stream).  begin_dev: dev_batch receives the device address of this engine's batch buffer (ndoubles doubles), filled
+ * in stream order when an update is due (returns 1, else 0).  finish_dev: dev_parts holds nparts such batches back to
+ * back in DEVICE memory; they are merged in part order by a kernel (Chan's formula, as the host path) and applied;
+ * nsamples = the samples all parts hold together (known to the host: covUpdate x walkers per part). */
+int32_t ptmcmc_adapt_begin_dev(ptmcmc_engine *e, void **dev_batch, int64_t *ndoubles);
+int32_t ptmcmc_adapt_finish_dev(ptmcmc_engine *e, const double *dev_parts, int32_t nparts, int64_t nsamples);
+/* device addresses of the eigen-factor (U concatenated per group, S) so that the shard holding T=1 can broadcast it in
+ * place (the multi-device form of the reference's send(cov) + per-rank SVD, ref :545-560); ptmcmc_factor_refresh
+ * re-derives sqrt(S) and the tensor-core operand images after the buffers were written from outside */
+int32_t ptmcmc_factor_dev(ptmcmc_engine *e, void **dev_U, int64_t *usize, void **dev_S, int64_t *ssize);
+int32_t ptmcmc_factor_refresh(ptmcmc_engine *e);
+
 /* Ladder sharding (ntemps_global > ntemps): the swap sweep (ref PTswap :631-697) cut at the shard
  * boundaries; replaces the reference's gather / scatter to rank 0 (ref :660-661, :689-691) by a
  * nearest-neighbour exchange of one rung.  ptmcmc_run stops at every swap iteration (it refuses to

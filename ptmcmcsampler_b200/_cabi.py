@@ -61,7 +61,8 @@ SYMBOLS = [
     "ptmcmc_swap_pack_top", "ptmcmc_swap_sweep", "ptmcmc_swap_finish", "ptmcmc_am_ring", "ptmcmc_maintain",
     "ptmcmc_state_bytes", "ptmcmc_save_state", "ptmcmc_load_state", "ptmcmc_replay", "ptmcmc_mh_kernel_name",
     "ptmcmc_test_normals", "ptmcmc_measure_fp64_peak", "ptmcmc_set_sink", "ptmcmc_sink_wait", "ptmcmc_snapshot_bytes",
-    "ptmcmc_snapshot", "ptmcmc_snapshot_wait",
+    "ptmcmc_snapshot", "ptmcmc_snapshot_wait", "ptmcmc_adapt_begin_dev", "ptmcmc_adapt_finish_dev", "ptmcmc_factor_dev",
+    "ptmcmc_factor_refresh",
 ]
 
 _lib = None
@@ -136,6 +137,10 @@ def load():
     L.ptmcmc_mh_kernel_name.restype = C.c_char_p
     L.ptmcmc_mh_kernel_name.argtypes = [h]
     L.ptmcmc_measure_fp64_peak.argtypes = [C.c_int32, _dp]
+    L.ptmcmc_adapt_begin_dev.argtypes = [h, C.POINTER(C.c_void_p), _i64p]
+    L.ptmcmc_adapt_finish_dev.argtypes = [h, C.c_void_p, C.c_int32, C.c_int64]
+    L.ptmcmc_factor_dev.argtypes = [h, C.POINTER(C.c_void_p), _i64p, C.POINTER(C.c_void_p), _i64p]
+    L.ptmcmc_factor_refresh.argtypes = [h]
     L.ptmcmc_set_sink.argtypes = [h, _dp, _dp, _dp, C.c_int64]
     L.ptmcmc_sink_wait.argtypes = [h]
     L.ptmcmc_snapshot_bytes.restype = C.c_int64
@@ -390,6 +395,25 @@ class Engine(object):
     def adapt_finish(self, batch):
         batch = np.ascontiguousarray(batch, dtype=np.float64)
         self._check(self._L.ptmcmc_adapt_finish(self._h, _d(batch)))
+
+    # ---- device-resident forms (collectives on device memory, no host synchronisation) ------------------
+    def adapt_begin_dev(self):
+        """(due, device address, doubles) of this engine's batch moments; filled in stream order when due."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        rc = self._check(self._L.ptmcmc_adapt_begin_dev(self._h, C.byref(ptr), C.byref(n)))
+        return rc == 1, int(ptr.value), int(n.value)
+
+    def adapt_finish_dev(self, parts_ptr, nparts, nsamples):
+        self._check(self._L.ptmcmc_adapt_finish_dev(self._h, parts_ptr, int(nparts), int(nsamples)))
+
+    def factor_dev(self):
+        """((U device address, doubles), (S device address, doubles))."""
+        pu, ps, nu, ns = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        self._check(self._L.ptmcmc_factor_dev(self._h, C.byref(pu), C.byref(nu), C.byref(ps), C.byref(ns)))
+        return (int(pu.value), int(nu.value)), (int(ps.value), int(ns.value))
+
+    def factor_refresh(self):
+        self._check(self._L.ptmcmc_factor_refresh(self._h))
 
     def counters(self):
         """(proposed[T][W][njumps], accepted[T][W][njumps], swap_accepted[T][W], swapProposed); the first

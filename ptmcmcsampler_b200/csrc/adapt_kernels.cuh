@@ -299,6 +299,30 @@ __global__ void __launch_bounds__(JAC_THREADS) adapt_finalize_kernel(const Facto
     }
 }
 
+// Chan merge of nparts batches {n, mean[d], M2c[d*d]} in part order (the same recurrence, in the same order, as
+// distributed.merge_batches on the host), result into out.  One block; thread per matrix entry.
+__global__ void __launch_bounds__(256) merge_batches_kernel(const double *parts, int nparts, int d, double *out)
+{
+    const int len = 1 + d + d * d;
+    for (int idx = threadIdx.x; idx < d * d; idx += blockDim.x) {
+        const int i = idx / d, j = idx % d;
+        double n = 0.0, mi = 0.0, mj = 0.0, m2 = 0.0;
+        for (int b = 0; b < nparts; ++b) {
+            const double *pb = parts + (size_t)b * len;
+            const double nb = pb[0];
+            if (nb == 0.0) continue;
+            const double di = pb[1 + i] - mi, dj = pb[1 + j] - mj, tot = n + nb;
+            m2 = m2 + pb[1 + d + idx] + (di * dj) * (n * nb / tot);
+            mi = mi + di * (nb / tot);
+            mj = mj + dj * (nb / tot);
+            n = tot;
+        }
+        out[1 + d + idx] = m2;
+        if (j == 0) out[1 + i] = mi;
+        if (idx == 0) out[0] = n;
+    }
+}
+
 // sqrtS = sqrt(S) after a host-supplied factor (ptmcmc_set_factor)
 __global__ void sqrt_kernel(const double *S, double *sqrtS, int n)
 {

@@ -1173,6 +1173,62 @@ int32_t ptmcmc_adapt_finish(ptmcmc_engine *h, const double *batch_in)
     return 0;
 }
 
+int32_t ptmcmc_adapt_begin_dev(ptmcmc_engine *h, void **dev_batch, int64_t *ndoubles)
+{
+    Engine *e = engine_of(h);
+    if (!e || !dev_batch || !ndoubles) return PTMCMC_ERR_ARG;
+    *dev_batch = e->d_batch;
+    *ndoubles = (int64_t)1 + e->d + (int64_t)e->d * e->d;
+    const long long b = e->iter;
+    if (b == 0 || b % e->cfg.cov_update != 0 || e->adapt_done_iter == b) return 0;
+    LaunchTimer lt(e, PTMCMC_K_ADAPT, 3);
+    cudaError_t st = launch_batch_moments(e);
+    if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "batch moments: %s", cudaGetErrorString(st));
+    return 1;
+}
+
+int32_t ptmcmc_adapt_finish_dev(ptmcmc_engine *h, const double *dev_parts, int32_t nparts, int64_t nsamples)
+{
+    Engine *e = engine_of(h);
+    if (!e || !dev_parts || nparts < 1) return PTMCMC_ERR_ARG;
+    const long long b = e->iter;
+    if (b == 0 || b % e->cfg.cov_update != 0 || e->adapt_done_iter == b)
+        return fail(e, PTMCMC_ERR_STATE, "no covariance update is due at iteration %lld", b);
+    const long long it = b - e->cfg.cov_update;
+    const double n_prev = (it == 0) ? 0.0 : (double)e->nsamp;
+    {
+        LaunchTimer lt(e, PTMCMC_K_ADAPT, 2);
+        merge_batches_kernel<<<1, 256, 0, e->stream>>>(dev_parts, nparts, e->d, e->d_batch);
+        cudaError_t st = cudaGetLastError();
+        if (st == cudaSuccess) st = launch_factor(e, e->d_batch, n_prev, it == 0);
+        if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "pooled factor: %s", cudaGetErrorString(st));
+    }
+    e->nsamp = (long long)n_prev + nsamples;
+    e->adapt_done_iter = b;
+    return 0;
+}
+
+int32_t ptmcmc_factor_dev(ptmcmc_engine *h, void **dev_U, int64_t *usize, void **dev_S, int64_t *ssize)
+{
+    Engine *e = engine_of(h);
+    if (!e || !dev_U || !dev_S || !usize || !ssize) return PTMCMC_ERR_ARG;
+    *dev_U = e->d_U; *usize = e->uoff[e->ngroups];
+    *dev_S = e->d_S; *ssize = e->soff[e->ngroups];
+    return 0;
+}
+
+int32_t ptmcmc_factor_refresh(ptmcmc_engine *h)
+{
+    Engine *e = engine_of(h);
+    if (!e) return PTMCMC_ERR_ARG;
+    const int n = e->soff[e->ngroups];
+    sqrt_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(e->d_S, e->d_sqrtS, n);
+    e->tm.launches[PTMCMC_K_ADAPT] += 1;
+    CUDA_TRY(e, cudaGetLastError());
+    CUDA_TRY(e, build_u_frags(e));
+    return 0;
+}
+
 int64_t ptmcmc_swap_msg_doubles(const ptmcmc_engine *h)
 {
     const Engine *e = (const Engine *)h;

@@ -43,16 +43,53 @@ def merge_batches(batches):
     return np.concatenate([[n], mean, m2.ravel()])
 
 
+class _CudaAlias(object):
+    """Exposes a raw device allocation through ``__cuda_array_interface__`` (zero-copy torch view)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def _device_view(engine, ptr, n):
+    import torch
+
+    return torch.as_tensor(_CudaAlias(ptr, n), device=torch.device("cuda", engine.device))
+
+
 def pooled_adapt(engine, group=None):
     """If a covariance update is due, pool the batch moments over the ranks of ``group`` and apply.
-    Collective: every rank must call it at the same iteration.  Returns True if an update ran."""
+    Collective: every rank must call it at the same iteration.  Returns True if an update ran.
+
+    With a CUDA engine over NCCL nothing leaves the device and the host does not wait: the batch moments are
+    all-gathered from the engine's own buffer on the engine's stream and merged by a kernel
+    (``ptmcmc_adapt_begin_dev`` / ``ptmcmc_adapt_finish_dev``).  Host engines (the test oracle over gloo) exchange the
+    same batches through numpy and merge them with :func:`merge_batches`, the same recurrence in the same order."""
     import torch
     import torch.distributed as dist
 
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if multi and hasattr(engine, "adapt_begin_dev") and dist.get_backend(group) == "nccl":
+        due, ptr, n = engine.adapt_begin_dev()
+        if not due:
+            return False
+        world = dist.get_world_size(group)
+        st = getattr(engine, "_adapt_comm", None)
+        if st is None:
+            dev = torch.device("cuda", engine.device)
+            stream = torch.cuda.ExternalStream(engine.stream, device=dev)
+            with torch.cuda.stream(stream):
+                parts = torch.empty(world * n, dtype=torch.float64, device=dev)
+            st = engine._adapt_comm = (stream, _device_view(engine, ptr, n), parts)
+        stream, mine, parts = st
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(parts, mine, group=group)
+        engine.adapt_finish_dev(parts.data_ptr(), world, world * engine.cov_update * engine.W)
+        return True
     batch = engine.adapt_begin()
     if batch is None:
         return False
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if multi:
         backend = dist.get_backend(group)
         dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
         mine = torch.from_numpy(batch).to(dev)
@@ -77,14 +114,6 @@ def run(engine, niter, group=None):
 
 
 # ------------------------------------------------------------------ ladder sharding ------------
-class _CudaAlias(object):
-    """Exposes a raw device allocation through ``__cuda_array_interface__`` (zero-copy torch view)."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
-                                         "version": 3, "strides": None}
-
-
 def ladder_slice(ntemps_global, world, rank):
     """Contiguous rungs ``[lo, hi)`` of shard ``rank``; the ladder must divide evenly."""
     if ntemps_global % world != 0:
@@ -130,6 +159,7 @@ class LadderComm(object):
         self.am_sent = -1      # last iteration whose AM-ring slot has been broadcast from the cold shard
         self.am_works = []     # broadcasts in flight
         self._ring = None
+        self._factor = None    # device views of the engine's eigen-factor
 
     def _on_stream(self):
         import contextlib
@@ -156,10 +186,15 @@ class LadderComm(object):
         return self.dist.batch_isend_irecv(ops) if ops else []
 
     def recv_carry(self):
-        self.dist.recv(self.carry_in, self._peer(self.rank + 1), group=self.group)
+        # (batched like the top-rung exchange: unbatched send / recv would be serialised with every other operation of
+        # the process group)
+        for r in self.dist.batch_isend_irecv([self.dist.P2POp(self.dist.irecv, self.carry_in, self._peer(self.rank + 1),
+                                                              self.group)]):
+            r.wait()
 
     def send_carry(self):
-        self.dist.send(self.carry_out, self._peer(self.rank - 1), group=self.group)
+        return self.dist.batch_isend_irecv([self.dist.P2POp(self.dist.isend, self.carry_out, self._peer(self.rank - 1),
+                                                            self.group)])
 
     def bcast(self, tensor):
         self.dist.broadcast(tensor, self._peer(0), group=self.group)
@@ -176,7 +211,7 @@ def ladder_swap(engine, comm):
         engine.swap_sweep(None if comm.hottest else comm.carry_in.data_ptr(),
                           None if comm.coldest else comm.carry_out.data_ptr())
         if not comm.coldest:
-            comm.send_carry()
+            reqs = list(reqs) + list(comm.send_carry())
         for r in reqs:
             r.wait()
         engine.swap_finish(None if comm.coldest else comm.below_in.data_ptr())
@@ -223,16 +258,32 @@ def ladder_maintenance(engine, comm):
             comm.am_works = []
         engine.maintain()
         if due_cov and comm.world > 1:
-            if comm.coldest:
-                U, S = engine.factor()
-                t = torch.from_numpy(np.concatenate([U, S])).to(comm.device)
+            if hasattr(engine, "factor_dev") and comm.device.type == "cuda":
+                # in place, device to device: no host copy, the host does not wait
+                if comm._factor is None:
+                    (pu, nu), (ps, ns) = engine.factor_dev()
+                    comm._factor = (comm.alias(pu, nu), comm.alias(ps, ns))
+                for t in comm._factor:
+                    comm.bcast(t)
+                if not comm.coldest:
+                    engine.factor_refresh()
             else:
-                t = torch.empty(engine.usize + engine.ssize, dtype=torch.float64, device=comm.device)
-            comm.bcast(t)
-            if not comm.coldest:
-                f = t.cpu().numpy()
-                engine.set_factor(f[:engine.usize], f[engine.usize:])
+                if comm.coldest:
+                    U, S = engine.factor()
+                    t = torch.from_numpy(np.concatenate([U, S])).to(comm.device)
+                else:
+                    t = torch.empty(engine.usize + engine.ssize, dtype=torch.float64, device=comm.device)
+                comm.bcast(t)
+                if not comm.coldest:
+                    f = t.cpu().numpy()
+                    engine.set_factor(f[:engine.usize], f[engine.usize:])
     comm.maint_done = it
+
+
+def _next_stop(it, niter_left, tskip, cov_update, burn):
+    """Iterations to the next point a ladder shard must stop at: a swap, or a covariance / DE-history boundary (the
+    factor broadcast and the AM-ring hand-over happen there, whether or not the boundary is a multiple of Tskip)."""
+    return min(niter_left, tskip - it % tskip, cov_update - it % cov_update, burn - it % burn)
 
 
 def run_ladder(engine, niter, comm, tskip):
@@ -241,7 +292,7 @@ def run_ladder(engine, niter, comm, tskip):
     while done < niter:
         it = engine.iteration
         ladder_maintenance(engine, comm)
-        step = min(niter - done, tskip - it % tskip)
+        step = _next_stop(it, niter - done, tskip, engine.cov_update, engine.burn)
         engine.run(step)
         done += step
         if engine.swap_pending:
@@ -312,7 +363,7 @@ def run_ladder_local(engines, niter, tskip, mem):
             U, S = engines[0].factor()
             for e in engines[1:]:
                 e.set_factor(U, S)
-        step = min(niter - done, tskip - it % tskip)
+        step = _next_stop(it, niter - done, tskip, engines[0].cov_update, engines[0].burn)
         for e in engines:
             e.run(step)
         done += step

@@ -15,11 +15,11 @@ from ptmcmcsampler_b200 import distributed as dist_mod
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def problem(d=5, W=7, Tg=6, seed=0):
+def problem(d=5, W=7, Tg=6, seed=0, cov_update=50, burn=100, tskip=10):
     rng = np.random.default_rng(seed)
     A = rng.standard_normal((d, d))
     cov = A @ A.T + 0.5 * np.eye(d)
-    kw = dict(seed=3 + seed, cov_update=50, burn=100, tskip=10, thin=5,
+    kw = dict(seed=3 + seed, cov_update=cov_update, burn=burn, tskip=tskip, thin=5,
               logl_params=orc.gaussian_params(5 * np.ones(d), np.linalg.inv(cov)),
               logp_params=orc.uniform_params(-50 * np.ones(d), 60 * np.ones(d)), record_hot=True)
     return kw, orc.temperature_ladder(d, Tg), rng.uniform(0, 10, (Tg, W, d))
@@ -67,6 +67,22 @@ def test_protocol_in_one_process_matches_unsharded_oracle(Tg, G):
         assert np.array_equal(s.buffers()[1], full.buffers()[1])
 
 
+@pytest.mark.parametrize("cov_update,burn,tskip,first", [(25, 75, 10, 130), (30, 90, 7, 64), (25, 75, 10, 75)])
+def test_covariance_and_de_boundaries_off_the_swap_grid(cov_update, burn, tskip, first):
+    """covUpdate / burn that are not multiples of Tskip (nor of the caller's chunking): the shards must still stop at every
+    boundary for the factor broadcast and the AM-ring hand-over, or the hot shards keep a stale factor and DE history."""
+    d, W, Tg, G, N = 5, 7, 6, 3, 300
+    kw, ladder, x0 = problem(d, W, Tg, cov_update=cov_update, burn=burn, tskip=tskip)
+    full = full_oracle(d, W, Tg, N, kw, ladder, x0)
+    shards = [oracle_shard(d, W, N, kw, ladder, x0, G, g) for g in range(G)]
+    dist_mod.run_ladder_local(shards, first, tskip, dist_mod.HostMem())
+    dist_mod.run_ladder_local(shards, N - first, tskip, dist_mod.HostMem())
+    assert_shards_equal_full(shards, full)
+    for s in shards[1:]:
+        assert np.array_equal(s.factor()[0], full.factor()[0])
+        assert np.array_equal(s.buffers()[1], full.buffers()[1])
+
+
 def test_shard_refuses_to_cross_a_swap_iteration():
     d, W, N = 5, 3, 50
     kw, ladder, x0 = problem(d, W, 4)
@@ -81,7 +97,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _gloo_worker(rank, world, port, Tg, N, out):
+def _gloo_worker(rank, world, port, Tg, N, out, sched=(50, 100, 10)):
     import torch.distributed as dist
 
     sys.path.insert(0, ROOT)
@@ -89,7 +105,7 @@ def _gloo_worker(rank, world, port, Tg, N, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         d, W = 5, 7
-        kw, ladder, x0 = problem(d, W, Tg)
+        kw, ladder, x0 = problem(d, W, Tg, cov_update=sched[0], burn=sched[1], tskip=sched[2])
         shard = oracle_shard(d, W, N, kw, ladder, x0, world, rank)
         comm = dist_mod.LadderComm(shard, device="cpu")
         dist_mod.run_ladder(shard, 130, comm, kw["tskip"])
@@ -100,15 +116,15 @@ def _gloo_worker(rank, world, port, Tg, N, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("Tg,G", [(6, 2), (6, 3)])
-def test_gloo_neighbour_exchange_matches_unsharded_oracle(Tg, G, tmp_path):
+@pytest.mark.parametrize("Tg,G,sched", [(6, 2, (50, 100, 10)), (6, 3, (50, 100, 10)), (6, 3, (25, 75, 10))])
+def test_gloo_neighbour_exchange_matches_unsharded_oracle(Tg, G, sched, tmp_path):
     import torch.multiprocessing as mp
 
     d, W, N = 5, 7, 300
-    kw, ladder, x0 = problem(d, W, Tg)
+    kw, ladder, x0 = problem(d, W, Tg, cov_update=sched[0], burn=sched[1], tskip=sched[2])
     full = full_oracle(d, W, Tg, N, kw, ladder, x0)
     out = str(tmp_path / "shard%d.npz")
-    mp.spawn(_gloo_worker, args=(G, _free_port(), Tg, N, out), nprocs=G, join=True)
+    mp.spawn(_gloo_worker, args=(G, _free_port(), Tg, N, out, sched), nprocs=G, join=True)
     r = [np.load(out % g) for g in range(G)]
     assert np.array_equal(np.concatenate([a["x"] for a in r]), full.state()[0])
     assert np.array_equal(np.concatenate([a["lnl"] for a in r]), full.state()[1])
