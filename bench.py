@@ -414,19 +414,30 @@ def e2e_run(wl, rank, world, local_rank, nrep, ladder_mode=False, Tg=None):
     lk, pr = wl.targets()
     p0 = _cabi.pinned_empty((T, W, d))
     p0[...] = wl.x0(7 + rank, T, W)
-    outdir = tempfile.mkdtemp(prefix="ptmcmc_bench_")
+    # chain / jump files go to memory-backed storage when there is one (a shared box's overlay file system stalls for
+    # tens of ms now and then, which would be timed as if it were the sampler)
+    outdir = tempfile.mkdtemp(prefix="ptmcmc_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+
+    debug = bool(os.environ.get("PTMCMC_E2E_DEBUG"))
 
     def once(seed):
+        t_a = time.perf_counter()
         s = PTMCMCSampler.PTSampler(d, lk, pr, wl.cov0.copy(), outDir=outdir, verbose=False, seed=seed, ntemps=Tg,
                                     nwalkers=W, device=local_rank, walker_offset=0 if ladder_mode else rank * W,
                                     dist_group=True if world > 1 else None, shard="ladder" if ladder_mode else "walkers")
+        t_b = time.perf_counter()
         s.sample(p0, E2E_ITERS, ladder=ladder, **wl.sample_kwargs())
+        t_c = time.perf_counter()
         loss = float(s._lnlike_all[-1].mean())   # the step's result read on the host
         d2h = s._chain_all.nbytes + s._lnlike_all.nbytes + s._lnprob_all.nbytes
         s.close()
+        if debug:
+            sys.stderr.write("e2e rank %d: construct %.1f ms, sample %.1f ms, close %.1f ms\n" % (
+                rank, 1e3 * (t_b - t_a), 1e3 * (t_c - t_b), 1e3 * (time.perf_counter() - t_c)))
         return loss, d2h
 
     once(100)
+    once(99)   # (two warm-up calls: page-locked result arrays and device memory then come from the pools)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -435,6 +446,9 @@ def e2e_run(wl, rank, world, local_rank, nrep, ladder_mode=False, Tg=None):
         _, d2h = once(101 + r)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    import shutil
+
+    shutil.rmtree(outdir, ignore_errors=True)
     if world > 1:
         t = torch.tensor([dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

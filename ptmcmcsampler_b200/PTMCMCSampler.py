@@ -712,6 +712,8 @@ class PTSampler(object):
         if Niter % thin != 0:
             print("Niter = %d is not a multiple of thin = %d.  The last %d samples will be lost"
                   % (Niter, thin, Niter % thin))
+        _dbg = os.environ.get("PTMCMC_E2E_DEBUG")
+        _t = [time.perf_counter()]
         if i0 == 0:
             self.initialize(Niter, ladder=ladder, Tmin=Tmin, Tmax=Tmax, Tskip=Tskip, isave=isave,
                             covUpdate=covUpdate, SCAMweight=SCAMweight, AMweight=AMweight, DEweight=DEweight,
@@ -734,8 +736,10 @@ class PTSampler(object):
         elif self._engine is None:
             raise ValueError("i0 != 0 requires a sampler that has already been initialised")
         self.tstart = time.time()
+        _t.append(time.perf_counter())
         if not (self._resume_state or self.resumeLength > 0):
             self.writeOutput(i0)  # row 0 (ref :491 -> updateChains -> writeOutput at iter 0)
+        _t.append(time.perf_counter())
 
         iter = i0
         pending, slot = None, 0
@@ -754,9 +758,15 @@ class PTSampler(object):
                     pending, slot = (iter, slot), slot ^ 1
                 else:
                     self.writeOutput(iter)
+        _t.append(time.perf_counter())
         if pending is not None:
             self._write_boundary(*pending)
+        _t.append(time.perf_counter())
         self._finish()
+        if _dbg:
+            _t.append(time.perf_counter())
+            sys.stderr.write("sample(): init+set_state %.1f, row0 %.1f, enqueue %.1f, last boundary %.1f, finish %.1f ms\n"
+                             % tuple(1e3 * (b - a) for a, b in zip(_t[:-1], _t[1:])))
         if self.verbose:
             print("\nRun Complete")
 

@@ -23,6 +23,8 @@ The drivers are written against the small engine surface both ``_cabi.Engine`` (
 and the test oracle (host pointers, gloo) expose, so the exchange logic is testable without a GPU.
 """
 import ctypes
+import os
+
 import numpy as np
 
 
@@ -131,6 +133,9 @@ def ladder_shard_kwargs(ladder, world, rank):
                 ladder_below=float(ladder[lo - 1]) if lo > 0 else 0.0)
 
 
+_BULK_GROUPS = {}
+
+
 class LadderComm(object):
     """Neighbour exchange and cold-shard broadcasts of one ladder shard over ``torch.distributed``.
 
@@ -155,6 +160,15 @@ class LadderComm(object):
         with self._on_stream():
             self.up_out, self.below_in, self.carry_in, self.carry_out = (
                 torch.zeros(n, dtype=torch.float64, device=self.device) for _ in range(4))
+        # bulk transfers (the AM ring, 1.3 GB per covUpdate at C5) get their own communicator: operations of one process
+        # group are serialised on one NCCL stream, and a 130 MB broadcast queued ahead of a swap message would stall the
+        # whole ladder for its duration
+        self.bulk_group = group
+        if self.world > 1 and self.device.type == "cuda" and not os.environ.get("PTMCMC_NO_BULK_GROUP"):
+            ranks = tuple(dist.get_process_group_ranks(group) if group is not None else range(dist.get_world_size()))
+            if ranks not in _BULK_GROUPS:  # one extra communicator per set of ranks, for the life of the process
+                _BULK_GROUPS[ranks] = dist.new_group(ranks=list(ranks))
+            self.bulk_group = _BULK_GROUPS[ranks]
         self.maint_done = -1
         self.am_sent = -1      # last iteration whose AM-ring slot has been broadcast from the cold shard
         self.am_works = []     # broadcasts in flight
@@ -234,7 +248,7 @@ def ladder_am_progress(engine, comm, flush=False):
         while lo <= it:
             s0 = lo % cu
             run = min(it - lo + 1, cu - s0)
-            comm.am_works.append(comm.dist.broadcast(ring[s0 * per:(s0 + run) * per], comm._peer(0), group=comm.group,
+            comm.am_works.append(comm.dist.broadcast(ring[s0 * per:(s0 + run) * per], comm._peer(0), group=comm.bulk_group,
                                                      async_op=True))
             lo += run
     comm.am_sent = it
