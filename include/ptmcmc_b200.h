@@ -102,9 +102,9 @@ typedef struct ptmcmc_config {
      * par points at a device copy of user_params. */
     const char *logl_source;
     const char *logp_source;
-    const double *user_params;  /* [n_user_params] */
-    int32_t n_user_params;
-    int32_t reserved3;
+    const double *user_params;  /* [n_logl_user_params + n_logp_user_params]: user_logl gets the first block, user_logp the second */
+    int32_t n_logl_user_params;
+    int32_t n_logp_user_params;
 } ptmcmc_config;
 
 typedef struct ptmcmc_engine ptmcmc_engine;
@@ -132,7 +132,8 @@ void ptmcmc_destroy(ptmcmc_engine *e);
 /* Initial point (ref sample :471-493): evaluate logp/logl on device, record row 0, fill AM slot 0.
  * x0 is [T][W][d]. */
 int32_t ptmcmc_set_state(ptmcmc_engine *e, const double *x0);
-/* Same with host-evaluated values (Python logl/logp): lnl, lnprior are [T][W]. */
+/* Same with host-evaluated values (Python logl/logp): lnl, lnprior are [T][W].  A target the device knows (a built-in or
+ * user source) is evaluated on the device and the host value ignored, so device and host targets can be mixed. */
 int32_t ptmcmc_set_state_external(ptmcmc_engine *e, const double *x0, const double *lnl,
                                   const double *lnprior);
 
@@ -150,6 +151,17 @@ int32_t ptmcmc_run(ptmcmc_engine *e, int64_t niter);
 int32_t ptmcmc_propose(ptmcmc_engine *e, double *q, int32_t *jump);
 int32_t ptmcmc_accept(ptmcmc_engine *e, const double *q, const double *qxy, const double *lnl,
                       const double *lnprior);
+
+/* The same round trip through engine-owned page-locked buffers, with ONE host synchronisation per iteration:
+ * ptmcmc_callback_buffers hands out q [T][W][d], jump [T][W], qxy / lnl / lnprior [T][W] and x [T][W][d] (valid until
+ * ptmcmc_destroy).  ptmcmc_propose_pinned fills q and jump (and x, the current points, when want_x != 0) and returns
+ * once they have landed; the host writes its proposals / qxy / target values in place; ptmcmc_accept_pinned uploads
+ * what the host owns (q only if q_modified; lnl / lnprior only for PTMCMC_LOG*_EXTERNAL targets) and enqueues the rest
+ * of the iteration without waiting for it. */
+int32_t ptmcmc_callback_buffers(ptmcmc_engine *e, double **q, int32_t **jump, double **qxy, double **lnl,
+                                double **lnprior, double **x);
+int32_t ptmcmc_propose_pinned(ptmcmc_engine *e, int32_t want_x);
+int32_t ptmcmc_accept_pinned(ptmcmc_engine *e, int32_t q_modified);
 
 int64_t ptmcmc_iteration(const ptmcmc_engine *e);
 int32_t ptmcmc_sync(ptmcmc_engine *e);
@@ -269,6 +281,10 @@ int32_t ptmcmc_reset_timing(ptmcmc_engine *e);
 int32_t ptmcmc_set_timing(ptmcmc_engine *e, int32_t on);
 /* name of the kernel ptmcmc_run launches for the MH segments of this engine (for profiles and bench records) */
 const char *ptmcmc_mh_kernel_name(ptmcmc_engine *e);
+/* compile-only check of user target sources for compute capability cc_major.cc_minor (no device needed): returns the
+ * cubin size, or < 0 with the NVRTC log in `log` */
+int32_t ptmcmc_user_compile_check(const char *logl_source, const char *logp_source, int32_t cc_major, int32_t cc_minor,
+                                  char *log, int64_t log_capacity);
 /* measured fp64 FMA throughput of `device` in TFLOP/s (a short DFMA kernel; the compute-side roofline denominator) */
 int32_t ptmcmc_measure_fp64_peak(int32_t device, double *tflops);
 /* test hook: the device's Box-Muller pairs of n 64-bit words (word_to_normals) on `device`; host buffers */

@@ -261,6 +261,9 @@ class PTSampler(object):
             logl_params=self._dev_logl.params(d) if self._dev_logl is not None else None,
             logp_kind=self._dev_logp.kind if self._dev_logp is not None else _cabi.LOGP_EXTERNAL,
             logp_params=self._dev_logp.params(d) if self._dev_logp is not None else None,
+            logl_source=getattr(self._dev_logl, "source", None), logp_source=getattr(self._dev_logp, "source", None),
+            logl_user_params=getattr(self._dev_logl, "user_params", None),
+            logp_user_params=getattr(self._dev_logp, "user_params", None),
             record_hot=self.writeHotChains, record_rows=rr, device=self.device, walker_offset=self.walker_offset)
         if self._shard_world > 1:
             from . import distributed
@@ -591,6 +594,16 @@ class PTSampler(object):
             return np.ascontiguousarray(p0)
         raise ValueError("p0 must have shape (ndim,), (nwalkers, ndim) or (ntemps, nwalkers, ndim)")
 
+    def _init_state(self, x0):
+        """Initial point of every chain (ref :471-487): on the device for device targets; Python targets are evaluated
+        here and uploaded (a device prior may be combined with a Python likelihood and vice versa: the engine evaluates
+        what it knows and keeps the host's values for the rest)."""
+        if self._dev_logl is not None and self._dev_logp is not None:
+            self._engine.set_state(x0)
+        else:
+            lnl, lp = self._host_eval(x0)
+            self._engine.set_state_external(x0, lnl, lp)
+
     def _host_eval(self, x):
         """logp / logl of every chain on the host (plain Python callables), ref :478-487, :605-612."""
         T, W = x.shape[:2]
@@ -611,7 +624,9 @@ class PTSampler(object):
         if self._dev_logp is None:
             lp.ravel()[:] = np.asarray(self.logp(X), dtype=np.float64)
         if self._dev_logl is None:
-            ok = np.isfinite(lp.ravel()) | (lp.ravel() == np.inf) if self._dev_logp is None else np.ones(len(X), bool)
+            # (with a device prior the host cannot know which points it rejects: logl is evaluated everywhere and the
+            # device ignores it where its prior returns -inf)
+            ok = (lp.ravel() != -np.inf) if self._dev_logp is None else np.ones(len(X), bool)
             if ok.all():
                 lnl.ravel()[:] = np.asarray(self.logl(X), dtype=np.float64)
             elif ok.any():
@@ -627,14 +642,18 @@ class PTSampler(object):
             self.randomizeProposalCycle()
 
     def _step_external(self, iter):
-        """One iteration with Python callables in the loop (ref :601-612, _jump :1048-1067)."""
+        """One iteration with Python callables in the loop (ref :601-612, _jump :1048-1067).  Proposals, jump ids and
+        (for custom jumps) the current points arrive in the engine's page-locked buffers; the host fills in what it owns
+        -- custom / auxiliary jumps, ``qxy``, Python ``logl`` / ``logp`` -- in place; the rest of the iteration is enqueued
+        without waiting.  One host synchronisation per iteration."""
         eng = self._engine
-        x = eng.state()[0]
-        q, jump = eng.propose()
+        cb = eng.callback_buffers()
+        need_x = bool(self._ext_jumps) or bool(self.aux)
+        eng.propose_pinned(want_x=need_x)
+        q, jump, qxy, lnl, lp, x = cb["q"], cb["jump"], cb["qxy"], cb["lnl"], cb["lp"], cb["x"]
         T, W = jump.shape
-        qxy = np.zeros((T, W))
-        lnl = np.zeros((T, W))
-        lp = np.zeros((T, W))
+        if need_x:
+            qxy[...] = 0.0
         if self.vectorized:
             d = self.ndim
             X, Q, J = x.reshape(T * W, d), q.reshape(T * W, d), jump.ravel()
@@ -657,7 +676,7 @@ class PTSampler(object):
                         Q[i], add = aux(X[i].copy(), Q[i].copy(), iter, betas[i])
                         qxy.ravel()[i] += add
             self._host_eval_vectorized(Q, lnl, lp)
-            eng.accept(q, qxy, lnl, lp)
+            eng.accept_pinned(q_modified=need_x)
             return
         for t in range(T):
             beta = 1 / self._mh_temp[t]
@@ -674,7 +693,7 @@ class PTSampler(object):
                     lp[t, w] = self.logp(q[t, w])
                 if self._dev_logl is None and (self._dev_logp is not None or lp[t, w] != -np.inf):
                     lnl[t, w] = self.logl(q[t, w])
-        eng.accept(q, qxy, lnl, lp)
+        eng.accept_pinned(q_modified=need_x)
 
     def _advance(self, n, iter0):
         """Run ``n`` iterations starting after ``iter0``."""
@@ -722,17 +741,9 @@ class PTSampler(object):
                             neff=neff, writeHotChains=writeHotChains, hotChain=hotChain)
             x0 = self._full_p0(p0)
             if self._resume_state or self.resumeLength > 0:
-                if self._external:
-                    raise NotImplementedError("resume needs device targets and the built-in proposals")
                 i0 = self._resume(x0)
-            elif self._dev_logl is not None and self._dev_logp is not None:
-                self._engine.set_state(x0)
             else:
-                lnl, lp = self._host_eval(x0)
-                if self._dev_logp is not None or self._dev_logl is not None:
-                    raise NotImplementedError("mixing a device target with a Python target is not supported; "
-                                              "pass both as device objects or both as callables")
-                self._engine.set_state_external(x0, lnl, lp)
+                self._init_state(x0)
         elif self._engine is None:
             raise ValueError("i0 != 0 requires a sampler that has already been initialised")
         self.tstart = time.time()
@@ -775,7 +786,10 @@ class PTSampler(object):
         eng = self._engine
         if self._resume_state:
             # exact continuation: the checkpoint holds every array the step reads, the draws are counter-based
-            eng.set_state(x0)
+            if self._dev_logl is not None and self._dev_logp is not None:
+                eng.set_state(x0)
+            else:  # Python targets: the checkpoint replaces every value, nothing needs evaluating
+                eng.set_state_external(x0, np.zeros(x0.shape[:2]), np.zeros(x0.shape[:2]))
             eng.load_state(np.load(self._state_file))
             it = eng.iteration
             if self.verbose:
@@ -805,7 +819,7 @@ class PTSampler(object):
         rows_x[:, 0, 0, :] = rc[:, :d]
         rows_lnl = np.zeros((R, T, 1))
         rows_lp = np.zeros((R, T, 1))
-        eng.set_state(x0)
+        self._init_state(x0)
         st = eng.state()
         rows_lnl[:] = st[1][None]
         rows_lp[:] = st[2][None]

@@ -42,7 +42,7 @@ class Config(C.Structure):
         ("timing", C.c_int32), ("reserved2", C.c_int32),
         ("ladder_above", C.c_double), ("ladder_below", C.c_double),
         ("logl_source", C.c_char_p), ("logp_source", C.c_char_p), ("user_params", _dp),
-        ("n_user_params", C.c_int32), ("reserved3", C.c_int32),
+        ("n_logl_user_params", C.c_int32), ("n_logp_user_params", C.c_int32),
     ]
 
 
@@ -62,7 +62,8 @@ SYMBOLS = [
     "ptmcmc_state_bytes", "ptmcmc_save_state", "ptmcmc_load_state", "ptmcmc_replay", "ptmcmc_mh_kernel_name",
     "ptmcmc_test_normals", "ptmcmc_measure_fp64_peak", "ptmcmc_set_sink", "ptmcmc_sink_wait", "ptmcmc_snapshot_bytes",
     "ptmcmc_snapshot", "ptmcmc_snapshot_wait", "ptmcmc_adapt_begin_dev", "ptmcmc_adapt_finish_dev", "ptmcmc_factor_dev",
-    "ptmcmc_factor_refresh",
+    "ptmcmc_factor_refresh", "ptmcmc_user_compile_check", "ptmcmc_callback_buffers", "ptmcmc_propose_pinned",
+    "ptmcmc_accept_pinned",
 ]
 
 _lib = None
@@ -93,6 +94,10 @@ def load():
     L.ptmcmc_run.argtypes = [h, C.c_int64]
     L.ptmcmc_propose.argtypes = [h, _dp, _ip]
     L.ptmcmc_accept.argtypes = [h, _dp, _dp, _dp, _dp]
+    L.ptmcmc_callback_buffers.argtypes = [h, C.POINTER(_dp), C.POINTER(_ip), C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp),
+                                          C.POINTER(_dp)]
+    L.ptmcmc_propose_pinned.argtypes = [h, C.c_int32]
+    L.ptmcmc_accept_pinned.argtypes = [h, C.c_int32]
     L.ptmcmc_iteration.restype = C.c_int64
     L.ptmcmc_iteration.argtypes = [h]
     L.ptmcmc_sync.argtypes = [h]
@@ -137,6 +142,7 @@ def load():
     L.ptmcmc_mh_kernel_name.restype = C.c_char_p
     L.ptmcmc_mh_kernel_name.argtypes = [h]
     L.ptmcmc_measure_fp64_peak.argtypes = [C.c_int32, _dp]
+    L.ptmcmc_user_compile_check.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]
     L.ptmcmc_adapt_begin_dev.argtypes = [h, C.POINTER(C.c_void_p), _i64p]
     L.ptmcmc_adapt_finish_dev.argtypes = [h, C.c_void_p, C.c_int32, C.c_int64]
     L.ptmcmc_factor_dev.argtypes = [h, C.POINTER(C.c_void_p), _i64p, C.POINTER(C.c_void_p), _i64p]
@@ -221,7 +227,8 @@ class Engine(object):
                  cycle=((JUMP_SCAM, 20), (JUMP_AM, 20)), de_weight=20, cov_update=1000, burn=10000, tskip=100,
                  thin=10, logl_kind=LOGL_GAUSSIAN, logl_params=None, logp_kind=LOGP_UNIFORM, logp_params=None,
                  record_hot=False, record_rows=1024, trace_iters=0, timing=False, device=0, walker_offset=0,
-                 temp_offset=0, ntemps_global=0, ladder_above=0.0, ladder_below=0.0):
+                 temp_offset=0, ntemps_global=0, ladder_above=0.0, ladder_below=0.0, logl_source=None, logp_source=None,
+                 logl_user_params=None, logp_user_params=None):
         L = load()
         self._L = L
         self.d, self.W, self.T = int(ndim), int(nwalkers), int(ntemps)
@@ -266,6 +273,18 @@ class Engine(object):
             ppar = np.ascontiguousarray(logp_params, dtype=np.float64)
             keep.append(ppar)
             cfg.logp_params = _d(ppar)
+        if logl_source is not None:
+            cfg.logl_source = logl_source.encode() if isinstance(logl_source, str) else logl_source
+        if logp_source is not None:
+            cfg.logp_source = logp_source.encode() if isinstance(logp_source, str) else logp_source
+        upar = np.concatenate([np.asarray(a, dtype=np.float64).ravel() if a is not None else np.zeros(0)
+                               for a in (logl_user_params, logp_user_params)])
+        cfg.n_logl_user_params = 0 if logl_user_params is None else int(np.size(logl_user_params))
+        cfg.n_logp_user_params = 0 if logp_user_params is None else int(np.size(logp_user_params))
+        if upar.size:
+            upar = np.ascontiguousarray(upar)
+            keep.append(upar)
+            cfg.user_params = _d(upar)
         cfg.record_hot, cfg.record_rows = int(bool(record_hot)), int(record_rows)
         cfg.trace, cfg.trace_iters = int(trace_iters > 0), int(trace_iters)
         cfg.timing = int(bool(timing))
@@ -278,7 +297,7 @@ class Engine(object):
         self._h = L.ptmcmc_create(C.byref(cfg))
         if not self._h:
             msg = L.ptmcmc_create_error().decode()
-            if "No jump proposals" in msg:
+            if "No jump proposals" in msg or "NVRTC" in msg:
                 raise ValueError(msg)
             raise EngineError(ERR_CUDA, msg)
         self.njumps = L.ptmcmc_njumps(self._h)
@@ -289,6 +308,7 @@ class Engine(object):
             self._h = None
         self._sink = None
         self._snap = None
+        self._cb = None
 
     __del__ = close
 
@@ -326,6 +346,26 @@ class Engine(object):
         lnl = np.ascontiguousarray(lnl, dtype=np.float64)
         lnprior = np.ascontiguousarray(lnprior, dtype=np.float64)
         self._check(self._L.ptmcmc_accept(self._h, _d(q), _d(qxy), _d(lnl), _d(lnprior)))
+
+    def callback_buffers(self):
+        """numpy views of the engine's page-locked round-trip buffers: dict(q, jump, qxy, lnl, lp, x)."""
+        if getattr(self, "_cb", None) is None:
+            q, qxy, lnl, lp, x = _dp(), _dp(), _dp(), _dp(), _dp()
+            jump = _ip()
+            self._check(self._L.ptmcmc_callback_buffers(self._h, C.byref(q), C.byref(jump), C.byref(qxy), C.byref(lnl),
+                                                        C.byref(lp), C.byref(x)))
+            Cn = self.T * self.W
+            as_arr = lambda ptr, n, shp: np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shp)  # noqa: E731
+            self._cb = dict(q=as_arr(q, Cn * self.d, (self.T, self.W, self.d)), x=as_arr(x, Cn * self.d, (self.T, self.W, self.d)),
+                            jump=as_arr(jump, Cn, (self.T, self.W)), qxy=as_arr(qxy, Cn, (self.T, self.W)),
+                            lnl=as_arr(lnl, Cn, (self.T, self.W)), lp=as_arr(lp, Cn, (self.T, self.W)))
+        return self._cb
+
+    def propose_pinned(self, want_x=False):
+        self._check(self._L.ptmcmc_propose_pinned(self._h, int(bool(want_x))))
+
+    def accept_pinned(self, q_modified=True):
+        self._check(self._L.ptmcmc_accept_pinned(self._h, int(bool(q_modified))))
 
     @property
     def iteration(self):
@@ -547,6 +587,17 @@ class Engine(object):
     @property
     def mh_kernel_name(self):
         return self._L.ptmcmc_mh_kernel_name(self._h).decode()
+
+
+def user_compile_check(logl_source=None, logp_source=None, cc=(10, 0)):
+    """Compile user target sources with NVRTC for compute capability ``cc`` (no device needed).  Returns the cubin size;
+    raises ``ValueError`` with the compiler log on failure."""
+    log = C.create_string_buffer(1 << 16)
+    enc = lambda s: None if s is None else (s.encode() if isinstance(s, str) else s)  # noqa: E731
+    rc = load().ptmcmc_user_compile_check(enc(logl_source), enc(logp_source), int(cc[0]), int(cc[1]), log, len(log))
+    if rc < 0:
+        raise ValueError(log.value.decode(errors="replace"))
+    return rc
 
 
 def measure_fp64_peak(device=0):

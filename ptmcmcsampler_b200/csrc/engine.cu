@@ -23,6 +23,7 @@
 #include "mh_kernels.cuh"
 #include "params.h"
 #include "swap_kernels.cuh"
+#include "user_target.h"
 
 using namespace ptm;
 
@@ -115,7 +116,9 @@ struct Engine {
     double *d_part2 = nullptr, *d_batch = nullptr, *d_gram = nullptr;
     double *d_stage = nullptr;  // [T][W][d] staging in the host layout
     int mom_blocks = 0, gram_kp = 0, jac_smem_doubles = 0;
-    // host-callback path staging
+    // host-callback path staging; h_* are engine-owned page-locked host buffers (ptmcmc_callback_buffers)
+    double *h_q = nullptr, *h_qxy = nullptr, *h_lnl = nullptr, *h_lp = nullptr, *h_x = nullptr;
+    int *h_jump = nullptr;
     double *d_q = nullptr, *d_qxy = nullptr, *d_lnl_new = nullptr, *d_lp_new = nullptr;
     int *d_jump = nullptr;
     unsigned *d_wordpos = nullptr;
@@ -131,6 +134,8 @@ struct Engine {
     int sm_count = 148;
     int mh_variant = 0;  // 0: default choice, 2: generic kernel, 3: tensor-core kernel, 6: sorted kernel for any ndim <= 32
     uint32_t rk[20] = {};  // Philox round keys of the seed
+    UserModule *user = nullptr;  // run-time compiled kernels of a user target (NVRTC), owned by the module cache
+    double *d_user_par = nullptr;
     SortedGeom sorted{};   // launch geometry of the sorted shared-memory kernel
     SortedHostTables sorted_tb{};  // its static tables (Gaussian form, mean, prior box)
     // tensor-core (DMMA) kernel: fragment-order matrices and launch geometry
@@ -141,7 +146,7 @@ struct Engine {
 
 int fail(Engine *e, int code, const char *fmt, ...)
 {
-    char buf[512];
+    char buf[8192];
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
@@ -209,6 +214,7 @@ DevParams make_params(const Engine *e)
     p.logl_kind = e->cfg.logl_kind; p.logp_kind = e->cfg.logp_kind; p.p_inclusive = e->p_inclusive;
     p.g_mu = e->d_gmu; p.g_P = e->d_gP; p.g_offset = e->g_offset; p.p_inside = e->p_inside;
     p.p_lo = e->d_plo; p.p_hi = e->d_phi;
+    p.user_par = e->d_user_par; p.n_logl_par = e->cfg.n_logl_user_params; p.n_logp_par = e->cfg.n_logp_user_params;
     p.rec_x = e->d_rec_x; p.rec_lnl = e->d_rec_lnl; p.rec_lnp = e->d_rec_lnp;
     p.rec_base = e->rec_base; p.rec_cap = e->cfg.record_rows; p.thin = e->cfg.thin; p.ntr = e->ntr;
     p.prop = e->d_prop; p.acc = e->d_acc; p.swap_acc = e->d_swap_acc;
@@ -247,7 +253,7 @@ Engine *engine_of(const ptmcmc_engine *h)
 int chain_blocks(const Engine *e) { return (int)(((long long)e->T * e->W + MH_THREADS - 1) / MH_THREADS); }
 
 // the specialised kernels know the three reference proposals; a cycle with the prior-draw jump runs in the generic one
-bool fast_reg_path(const Engine *e) { return e->identity_group && e->d <= MAX_REG_DIM && e->njumps == 3; }
+bool fast_reg_path(const Engine *e) { return e->identity_group && e->d <= MAX_REG_DIM && e->njumps == 3 && !e->user; }
 
 cudaError_t build_u_frags(Engine *e)
 {
@@ -275,6 +281,10 @@ cudaError_t launch_mh(Engine *e, long long it0, long long it1, bool tail)
     e->tm.chain_steps += (it1 - it0 + 1) * (long long)e->T * e->W;
     if (use_mma(e)) return launch_mma(p, e->mma, e->d_Uf, e->d_Pf, e->d_Ut, e->cfg.device, e->stream);
     if (fast_reg_path(e) && e->mh_variant != 2) return launch_sorted(p, e->sorted_tb, e->sorted, e->cfg.device, e->stream);
+    if (e->user) {
+        void *args[] = {&p};
+        return user_launch(e->user->mh, chain_blocks(e), MH_THREADS, e->stream, args);
+    }
     mh_generic_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p);
     return cudaGetLastError();
 }
@@ -617,8 +627,25 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_gP, P.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice, e->stream));
     } else if (cfg->logl_kind == PTMCMC_LOGL_CURVED) {
         if (d % 2) return fail(nullptr, PTMCMC_ERR_ARG, "curved log-likelihood needs an even ndim");
-    } else if (cfg->logl_kind != PTMCMC_LOGL_ROSENBROCK && cfg->logl_kind != PTMCMC_LOGL_EXTERNAL) {
+    } else if (cfg->logl_kind != PTMCMC_LOGL_ROSENBROCK && cfg->logl_kind != PTMCMC_LOGL_EXTERNAL &&
+               cfg->logl_kind != PTMCMC_LOGL_USER) {
         return fail(nullptr, PTMCMC_ERR_ARG, "unknown logl_kind %d", cfg->logl_kind);
+    }
+    if (cfg->logl_kind == PTMCMC_LOGL_USER || cfg->logp_kind == PTMCMC_LOGP_USER) {
+        if (cfg->logl_kind == PTMCMC_LOGL_USER && !(cfg->logl_source && *cfg->logl_source))
+            return fail(nullptr, PTMCMC_ERR_ARG, "PTMCMC_LOGL_USER needs logl_source");
+        if (cfg->logp_kind == PTMCMC_LOGP_USER && !(cfg->logp_source && *cfg->logp_source))
+            return fail(nullptr, PTMCMC_ERR_ARG, "PTMCMC_LOGP_USER needs logp_source");
+        if (cfg->n_logl_user_params < 0 || cfg->n_logp_user_params < 0 ||
+            (cfg->n_logl_user_params + cfg->n_logp_user_params > 0 && !cfg->user_params))
+            return fail(nullptr, PTMCMC_ERR_ARG, "user_params does not match n_logl_user_params + n_logp_user_params");
+        std::string err;
+        e->user = user_module(cfg->logl_kind == PTMCMC_LOGL_USER ? cfg->logl_source : nullptr,
+                              cfg->logp_kind == PTMCMC_LOGP_USER ? cfg->logp_source : nullptr, cfg->device, err);
+        if (!e->user) return fail(nullptr, PTMCMC_ERR_ARG, "%s", err.c_str());
+        const size_t np = (size_t)cfg->n_logl_user_params + cfg->n_logp_user_params;
+        CUDA_TRY(nullptr, dalloc(&e->d_user_par, np));
+        if (np) CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_user_par, cfg->user_params, sizeof(double) * np, cudaMemcpyHostToDevice, e->stream));
     }
     if (cfg->logp_kind == PTMCMC_LOGP_UNIFORM) {
         if (!cfg->logp_params) return fail(nullptr, PTMCMC_ERR_ARG, "uniform log-prior needs parameters");
@@ -628,7 +655,7 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_phi, cfg->logp_params + d, sizeof(double) * d, cudaMemcpyHostToDevice, e->stream));
         e->p_inside = cfg->logp_params[2 * d];
         e->p_inclusive = cfg->logp_params[2 * d + 1] != 0.0;
-    } else if (cfg->logp_kind != PTMCMC_LOGP_FLAT && cfg->logp_kind != PTMCMC_LOGP_EXTERNAL) {
+    } else if (cfg->logp_kind != PTMCMC_LOGP_FLAT && cfg->logp_kind != PTMCMC_LOGP_EXTERNAL && cfg->logp_kind != PTMCMC_LOGP_USER) {
         return fail(nullptr, PTMCMC_ERR_ARG, "unknown logp_kind %d", cfg->logp_kind);
     }
     if (d <= MAX_REG_DIM) {  // static tables of the sorted kernel
@@ -776,11 +803,13 @@ void ptmcmc_destroy(ptmcmc_engine *h)
                     e->d_plo, e->d_phi, e->d_rec_x, e->d_rec_lnl, e->d_rec_lnp, e->d_prop, e->d_acc,
                     e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_part2, e->d_batch, e->d_gram,
                     e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos, e->d_stage,
-                    e->d_carry_code, e->d_carry_L, e->d_Uf, e->d_Pf, e->d_gPfull, e->d_Ut, e->d_snap[0], e->d_snap[1]};
+                    e->d_carry_code, e->d_carry_L, e->d_Uf, e->d_Pf, e->d_gPfull, e->d_Ut, e->d_snap[0], e->d_snap[1], e->d_user_par};
     for (void *p : ptrs)
         if (p) cudaFreeAsync(p, e->stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    for (void *hp : {(void *)e->h_q, (void *)e->h_qxy, (void *)e->h_lnl, (void *)e->h_lp, (void *)e->h_x, (void *)e->h_jump})
+        if (hp) cudaFreeHost(hp);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     for (cudaEvent_t ev : {e->ev_rows, e->ev_copied, e->ev_snap[0], e->ev_snap[1]})
@@ -833,7 +862,12 @@ int32_t ptmcmc_set_state(ptmcmc_engine *h, const double *x0)
     DevParams p = make_params(e);
     {
         LaunchTimer lt(e, PTMCMC_K_INIT);
-        init_eval_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p);
+        if (e->user) {
+            void *args[] = {&p};
+            CUDA_TRY(e, user_launch(e->user->init_eval, chain_blocks(e), MH_THREADS, e->stream, args));
+        } else {
+            init_eval_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p);
+        }
     }
     CUDA_TRY(e, cudaGetLastError());
     return finish_set_state(e);
@@ -849,6 +883,17 @@ int32_t ptmcmc_set_state_external(ptmcmc_engine *h, const double *x0, const doub
     CUDA_TRY(e, cudaMemcpyAsync(e->lnl[e->cur], lnl, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(e->lp[e->cur], lnprior, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // lnl / lnprior may be reused by the caller
+    {   // targets the device knows are evaluated here; lnlike0 = -inf outside the prior (ref :481-483)
+        DevParams p = make_params(e);
+        LaunchTimer lt(e, PTMCMC_K_INIT);
+        if (e->user) {
+            void *args[] = {&p};
+            CUDA_TRY(e, user_launch(e->user->init_eval, chain_blocks(e), MH_THREADS, e->stream, args));
+        } else {
+            init_eval_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p);
+        }
+        CUDA_TRY(e, cudaGetLastError());
+    }
     return finish_set_state(e);
 }
 
@@ -907,10 +952,9 @@ int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
     return 0;
 }
 
-int32_t ptmcmc_propose(ptmcmc_engine *h, double *q, int32_t *jump)
+// start iteration iter + 1: maintenance, jump and proposal of every chain into the device staging (ref :545-601)
+static int propose_core(Engine *e)
 {
-    Engine *e = engine_of(h);
-    if (!e || !q || !jump) return PTMCMC_ERR_ARG;
     if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose before set_state");
     if (e->sharded) return fail(e, PTMCMC_ERR_STATE, "host callbacks are not available on a ladder-sharded engine");
     if (e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose called twice");
@@ -936,6 +980,49 @@ int32_t ptmcmc_propose(ptmcmc_engine *h, double *q, int32_t *jump)
         propose_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, e->d_q, e->d_jump, e->d_wordpos);
     }
     CUDA_TRY(e, cudaGetLastError());
+    return 0;
+}
+
+// finish the iteration from the device staging: Hastings test, swap, buffers and record (ref :605-627)
+static int accept_core(Engine *e)
+{
+    const size_t C = (size_t)e->T * e->W;
+    const long long it = e->iter + 1;
+    DevParams p = make_params(e);
+    p.it0 = p.it1 = it;
+    {
+        LaunchTimer lt(e, PTMCMC_K_ACCEPT);
+        if (e->user) {
+            void *args[] = {&p, &e->d_q, &e->d_qxy, &e->d_lnl_new, &e->d_lp_new, &e->d_jump, &e->d_wordpos};
+            CUDA_TRY(e, user_launch(e->user->accept, chain_blocks(e), MH_THREADS, e->stream, args));
+        } else {
+            accept_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new,
+                                                                         e->d_jump, e->d_wordpos);
+        }
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    e->tm.chain_steps += (long long)C;
+    if (e->T > 1 && it % e->cfg.tskip == 0) {
+        cudaError_t st = launch_swap(e, it);
+        if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "swap kernels: %s", cudaGetErrorString(st));
+    } else {
+        LaunchTimer lt(e, PTMCMC_K_ACCEPT);
+        bookkeep_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, it);
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    e->iter = it;
+    e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
+    e->pending_propose = false;
+    CUDA_TRY(e, sink_flush(e));
+    return 0;
+}
+
+int32_t ptmcmc_propose(ptmcmc_engine *h, double *q, int32_t *jump)
+{
+    Engine *e = engine_of(h);
+    if (!e || !q || !jump) return PTMCMC_ERR_ARG;
+    int rc = propose_core(e);
+    if (rc) return rc;
     const size_t C = (size_t)e->T * e->W;
     CUDA_TRY(e, cudaMemcpyAsync(q, e->d_q, sizeof(double) * C * e->d, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(jump, e->d_jump, sizeof(int) * C, cudaMemcpyDeviceToHost, e->stream));
@@ -950,34 +1037,75 @@ int32_t ptmcmc_accept(ptmcmc_engine *h, const double *q, const double *qxy, cons
     if (!e || !q || !qxy || !lnl || !lnprior) return PTMCMC_ERR_ARG;
     if (!e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_accept without ptmcmc_propose");
     const size_t C = (size_t)e->T * e->W;
-    const long long it = e->iter + 1;
     CUDA_TRY(e, cudaMemcpyAsync(e->d_q, q, sizeof(double) * C * e->d, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(e->d_qxy, qxy, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(e->d_lnl_new, lnl, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(e->d_lp_new, lnprior, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
-    DevParams p = make_params(e);
-    p.it0 = p.it1 = it;
-    {
-        LaunchTimer lt(e, PTMCMC_K_ACCEPT);
-        accept_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new,
-                                                                     e->d_jump, e->d_wordpos);
-    }
-    CUDA_TRY(e, cudaGetLastError());
-    e->tm.chain_steps += (long long)C;
-    if (e->T > 1 && it % e->cfg.tskip == 0) {
-        cudaError_t st = launch_swap(e, it);
-        if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "swap kernels: %s", cudaGetErrorString(st));
-    } else {
-        LaunchTimer lt(e, PTMCMC_K_ACCEPT);
-        bookkeep_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, it);
-    }
-    CUDA_TRY(e, cudaGetLastError());
+    int rc = accept_core(e);
+    if (rc) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // the host buffers may be reused by the caller
-    e->iter = it;
-    e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
-    e->pending_propose = false;
-    CUDA_TRY(e, sink_flush(e));
     return 0;
+}
+
+int32_t ptmcmc_callback_buffers(ptmcmc_engine *h, double **q, int32_t **jump, double **qxy, double **lnl, double **lnprior,
+                                double **x)
+{
+    Engine *e = engine_of(h);
+    if (!e || !q || !jump || !qxy || !lnl || !lnprior || !x) return PTMCMC_ERR_ARG;
+    const size_t C = (size_t)e->T * e->W;
+    if (!e->h_q) {
+        CUDA_TRY(e, cudaHostAlloc((void **)&e->h_q, sizeof(double) * C * e->d, cudaHostAllocDefault));
+        CUDA_TRY(e, cudaHostAlloc((void **)&e->h_x, sizeof(double) * C * e->d, cudaHostAllocDefault));
+        CUDA_TRY(e, cudaHostAlloc((void **)&e->h_qxy, sizeof(double) * C, cudaHostAllocDefault));
+        CUDA_TRY(e, cudaHostAlloc((void **)&e->h_lnl, sizeof(double) * C, cudaHostAllocDefault));
+        CUDA_TRY(e, cudaHostAlloc((void **)&e->h_lp, sizeof(double) * C, cudaHostAllocDefault));
+        CUDA_TRY(e, cudaHostAlloc((void **)&e->h_jump, sizeof(int) * C, cudaHostAllocDefault));
+        memset(e->h_qxy, 0, sizeof(double) * C);
+        memset(e->h_lnl, 0, sizeof(double) * C);
+        memset(e->h_lp, 0, sizeof(double) * C);
+    }
+    *q = e->h_q; *jump = e->h_jump; *qxy = e->h_qxy; *lnl = e->h_lnl; *lnprior = e->h_lp; *x = e->h_x;
+    return 0;
+}
+
+int32_t ptmcmc_propose_pinned(ptmcmc_engine *h, int32_t want_x)
+{
+    Engine *e = engine_of(h);
+    if (!e) return PTMCMC_ERR_ARG;
+    if (!e->h_q) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose_pinned before ptmcmc_callback_buffers");
+    int rc = propose_core(e);
+    if (rc) return rc;
+    const size_t C = (size_t)e->T * e->W;
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_q, e->d_q, sizeof(double) * C * e->d, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_jump, e->d_jump, sizeof(int) * C, cudaMemcpyDeviceToHost, e->stream));
+    if (want_x) {  // the current points in the host layout, for custom jumps (ref :1058-1065: func(x, iter, beta))
+        dim3 grid((unsigned)std::min<long long>(((long long)e->W * e->d + 255) / 256, 4096), (unsigned)e->T);
+        to_host_layout_kernel<<<grid, 256, 0, e->stream>>>(e->x[e->cur], e->d_stage, e->d, e->W);
+        e->tm.launches[PTMCMC_K_PROPOSE] += 1;
+        CUDA_TRY(e, cudaGetLastError());
+        CUDA_TRY(e, cudaMemcpyAsync(e->h_x, e->d_stage, sizeof(double) * C * e->d, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // the one host synchronisation of an iteration
+    e->pending_propose = true;
+    return 0;
+}
+
+int32_t ptmcmc_accept_pinned(ptmcmc_engine *h, int32_t q_modified)
+{
+    Engine *e = engine_of(h);
+    if (!e) return PTMCMC_ERR_ARG;
+    if (!e->pending_propose || !e->h_q) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_accept_pinned without ptmcmc_propose_pinned");
+    const size_t C = (size_t)e->T * e->W;
+    // proposals the host did not touch are still in the device staging: nothing to upload
+    if (q_modified) CUDA_TRY(e, cudaMemcpyAsync(e->d_q, e->h_q, sizeof(double) * C * e->d, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_qxy, e->h_qxy, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
+    if (e->cfg.logl_kind == PTMCMC_LOGL_EXTERNAL)
+        CUDA_TRY(e, cudaMemcpyAsync(e->d_lnl_new, e->h_lnl, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
+    if (e->cfg.logp_kind == PTMCMC_LOGP_EXTERNAL)
+        CUDA_TRY(e, cudaMemcpyAsync(e->d_lp_new, e->h_lp, sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
+    // no synchronisation: the copies and kernels are ordered on the engine's stream, and the host does not write the
+    // buffers again before the next ptmcmc_propose_pinned has synchronised
+    return accept_core(e);
 }
 
 int64_t ptmcmc_iteration(const ptmcmc_engine *h) { return h ? ((const Engine *)h)->iter : -1; }
@@ -1604,7 +1732,20 @@ const char *ptmcmc_mh_kernel_name(ptmcmc_engine *h)
         return buf;
     }
     if (fast_reg_path(e) && e->mh_variant != 2) return sorted_kernel_name(e->d, e->sorted);
-    return "mh_generic_kernel";
+    return e->user ? "mh_generic_kernel (NVRTC, user target)" : "mh_generic_kernel";
+}
+
+int32_t ptmcmc_user_compile_check(const char *logl_source, const char *logp_source, int32_t cc_major, int32_t cc_minor,
+                                  char *log, int64_t log_capacity)
+{
+    std::vector<char> cubin;
+    std::string msg;
+    const int rc = user_compile_cubin(logl_source, logp_source, cc_major, cc_minor, cubin, msg);
+    if (log && log_capacity > 0) {
+        strncpy(log, msg.c_str(), (size_t)log_capacity - 1);
+        log[log_capacity - 1] = 0;
+    }
+    return rc == 0 ? (int32_t)std::min<size_t>(cubin.size(), 0x7FFFFFFF) : PTMCMC_ERR_ARG;
 }
 
 int32_t ptmcmc_measure_fp64_peak(int32_t device, double *tflops)

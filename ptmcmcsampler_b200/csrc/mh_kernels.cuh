@@ -7,6 +7,15 @@
 #pragma once
 #include "mh_common.cuh"
 
+// This header is also the body of the run-time compiled translation unit of a user target (user_target.cu): the
+// caller's CUDA source defines user_logl / user_logp ahead of it, PTMCMC_USER_TARGET is defined, and the kernels get C
+// linkage so that the driver API finds them by name.
+#ifdef PTMCMC_USER_TARGET
+#define PTM_KERNEL extern "C" __global__
+#else
+#define PTM_KERNEL __global__
+#endif
+
 namespace ptm {
 
 // ---------------------------------------------------------------------------------------------
@@ -15,6 +24,9 @@ namespace ptm {
 // ---------------------------------------------------------------------------------------------
 __device__ inline double eval_logp_generic(const DevParams &p, const double *q)
 {
+#ifdef PTMCMC_USER_TARGET
+    if (p.logp_kind == LOGP_USER) return ::user_logp(q, p.d, p.user_par + p.n_logl_par);
+#endif
     if (p.logp_kind == LOGP_UNIFORM) {
         for (int k = 0; k < p.d; ++k)
             if (!in_box(q[k], p.p_lo[k], p.p_hi[k], p.p_inclusive)) return neg_inf();
@@ -26,6 +38,9 @@ __device__ inline double eval_logp_generic(const DevParams &p, const double *q)
 __device__ inline double eval_logl_generic(const DevParams &p, const double *q)
 {
     const int d = p.d;
+#ifdef PTMCMC_USER_TARGET
+    if (p.logl_kind == LOGL_USER) return ::user_logl(q, d, p.user_par);
+#endif
     if (p.logl_kind == LOGL_GAUSSIAN) {
         double acc = 0.0;
         for (int i = 0; i < d; ++i) {
@@ -116,7 +131,7 @@ __device__ inline int propose_generic(const DevParams &p, Stream &st, double tem
     return jump;
 }
 
-__global__ void __launch_bounds__(MH_THREADS) mh_generic_kernel(const DevParams p)
+PTM_KERNEL void __launch_bounds__(MH_THREADS) mh_generic_kernel(const DevParams p)
 {
     const int d = p.d, W = p.W, T = p.T;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,8 +175,10 @@ __global__ void __launch_bounds__(MH_THREADS) mh_generic_kernel(const DevParams 
     p.lp[c] = lp;
 }
 
-// Initial point (ref :478-487): lp = logp(p0); lnlike0 = -inf outside the prior else logl(p0).
-__global__ void __launch_bounds__(MH_THREADS) init_eval_kernel(const DevParams p)
+// Initial point (ref :478-487): lp = logp(p0); lnlike0 = -inf outside the prior else logl(p0).  A target the host
+// evaluates (LOG*_EXTERNAL) keeps the value uploaded beforehand (ptmcmc_set_state_external), so a device prior can be
+// combined with a Python likelihood and vice versa.
+PTM_KERNEL void __launch_bounds__(MH_THREADS) init_eval_kernel(const DevParams p)
 {
     const int d = p.d, W = p.W, T = p.T;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,14 +187,14 @@ __global__ void __launch_bounds__(MH_THREADS) init_eval_kernel(const DevParams p
     double x[MAX_GENERIC_DIM];
     const double *xg = p.x + (size_t)t * d * W + w;
     for (int k = 0; k < d; ++k) x[k] = xg[(size_t)k * W];
-    const double lp = eval_logp_generic(p, x);
+    const double lp = (p.logp_kind != LOGP_EXTERNAL) ? eval_logp_generic(p, x) : p.lp[c];
     p.lp[c] = lp;
-    p.lnl[c] = (lp == neg_inf()) ? neg_inf() : eval_logl_generic(p, x);
+    p.lnl[c] = (lp == neg_inf()) ? neg_inf() : (p.logl_kind != LOGL_EXTERNAL) ? eval_logl_generic(p, x) : p.lnl[c];
 }
 
 // updateChains for iteration `it` of every chain from the state in HBM (used for iteration 0 and by
 // the host-callback path).
-__global__ void __launch_bounds__(MH_THREADS) bookkeep_kernel(const DevParams p, long long it)
+PTM_KERNEL void __launch_bounds__(MH_THREADS) bookkeep_kernel(const DevParams p, long long it)
 {
     const int d = p.d, W = p.W, T = p.T;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,7 +207,7 @@ __global__ void __launch_bounds__(MH_THREADS) bookkeep_kernel(const DevParams p,
 // Reference-style resume (ref :591-599): iterations [it0, it1] take their state from stored rows
 // (host layout rows_x[row][T][W][d]); row of iteration it = it / repeat - row_base.  Only the buffer /
 // record side effects of the step happen (ref :627).
-__global__ void __launch_bounds__(MH_THREADS) replay_kernel(const DevParams p, const double *rows_x,
+PTM_KERNEL void __launch_bounds__(MH_THREADS) replay_kernel(const DevParams p, const double *rows_x,
                                                             const double *rows_lnl, const double *rows_lp,
                                                             long long repeat, long long row_base)
 {
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(MH_THREADS) replay_kernel(const DevParams p, c
 
 // ---- host-callback path (Python logl / logp / custom jumps), one iteration per call pair ------
 // q_out [T][W][d] row-major for the host, jump_out [T][W], word_pos [T][W] = stream position
-__global__ void __launch_bounds__(MH_THREADS) propose_kernel(const DevParams p, double *q_out, int *jump_out,
+PTM_KERNEL void __launch_bounds__(MH_THREADS) propose_kernel(const DevParams p, double *q_out, int *jump_out,
                                                               unsigned *word_pos)
 {
     const int d = p.d, W = p.W, T = p.T;
@@ -237,7 +254,7 @@ __global__ void __launch_bounds__(MH_THREADS) propose_kernel(const DevParams p, 
 }
 
 // q_in [T][W][d], qxy/lnl_new/lp_new [T][W]
-__global__ void __launch_bounds__(MH_THREADS) accept_kernel(const DevParams p, const double *q_in, const double *qxy,
+PTM_KERNEL void __launch_bounds__(MH_THREADS) accept_kernel(const DevParams p, const double *q_in, const double *qxy,
                                                              const double *lnl_new, const double *lp_new,
                                                              const int *jump_in, const unsigned *word_pos)
 {

@@ -1,6 +1,13 @@
 // Device-visible parameter block of the PT-MCMC engine (passed by value to every kernel).
 #pragma once
+#ifdef __CUDACC_RTC__  // NVRTC ships no standard headers
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef int int32_t;
+typedef long long int64_t;
+#else
 #include <cstdint>
+#endif
 
 namespace ptm {
 
@@ -10,8 +17,8 @@ constexpr int MAX_GENERIC_DIM = 128;  // local-memory kernel covers ndim <= 128
 constexpr int MH_THREADS = 128;
 
 enum : int { JUMP_SCAM = 0, JUMP_AM = 1, JUMP_DE = 2, JUMP_PRIOR = 3, JUMP_EXT0 = 4 };
-enum : int { LOGL_EXTERNAL = 0, LOGL_GAUSSIAN = 1, LOGL_CURVED = 2, LOGL_ROSENBROCK = 3 };
-enum : int { LOGP_EXTERNAL = 0, LOGP_UNIFORM = 1, LOGP_FLAT = 2 };
+enum : int { LOGL_EXTERNAL = 0, LOGL_GAUSSIAN = 1, LOGL_CURVED = 2, LOGL_ROSENBROCK = 3, LOGL_USER = 4 };
+enum : int { LOGP_EXTERNAL = 0, LOGP_UNIFORM = 1, LOGP_FLAT = 2, LOGP_USER = 3 };
 
 struct DevParams {
     // geometry
@@ -38,6 +45,9 @@ struct DevParams {
     const double *g_mu, *g_P;  // Gaussian: mean and -0.5*icov folded to an upper-triangular form
     double g_offset, p_inside;
     const double *p_lo, *p_hi;
+    // user targets (CUDA source compiled with NVRTC): parameter blob [logl parameters | logp parameters]
+    const double *user_par;
+    int n_logl_par, n_logp_par;
     // thinned record window: rec_x[row][ntr][W][d], rec_lnl/rec_lnp[row][ntr][W]
     double *rec_x, *rec_lnl, *rec_lnp;
     long long rec_base, rec_cap, thin;
@@ -52,6 +62,7 @@ struct DevParams {
     int tail, pad2;
 };
 
+#ifndef __CUDACC_RTC__
 // round r of Philox4x32-10 uses the key (k0 + r W0, k1 + r W1), Weyl constants of Salmon et al.
 inline void philox_round_keys(unsigned long long seed, uint32_t *rk)
 {
@@ -63,5 +74,6 @@ inline void philox_round_keys(unsigned long long seed, uint32_t *rk)
         k1 += 0xBB67AE85u;
     }
 }
+#endif
 
 }  // namespace ptm

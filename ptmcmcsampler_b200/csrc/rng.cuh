@@ -6,7 +6,14 @@
 // (ref PTMCMCSampler.py:1058), the proposal's draws (:839-873, :897-930, :955-976), then the
 // accept uniform (:616).  No generator state lives in HBM.
 #pragma once
+#ifdef __CUDACC_RTC__  // NVRTC ships no standard headers
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef int int32_t;
+typedef long long int64_t;
+#else
 #include <cstdint>
+#endif
 
 #include "params.h"
 

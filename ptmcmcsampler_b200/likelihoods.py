@@ -15,6 +15,8 @@ from . import _cabi
 
 class DeviceLogLikelihood(object):
     kind = _cabi.LOGL_EXTERNAL
+    source = None        # CUDA source of a user target (SourceLikelihood)
+    user_params = None
 
     def params(self, ndim):
         return None
@@ -22,9 +24,44 @@ class DeviceLogLikelihood(object):
 
 class DeviceLogPrior(object):
     kind = _cabi.LOGP_EXTERNAL
+    source = None
+    user_params = None
 
     def params(self, ndim):
         return None
+
+
+class SourceLikelihood(DeviceLogLikelihood):
+    """An arbitrary log-likelihood as CUDA C++ source, compiled with NVRTC into the engine's MH kernel when the sampler
+    starts (the reference's ``logl(x, *args)`` Python callable, ref :108, :1072-1086, moved onto the device)::
+
+        SourceLikelihood('''
+            double user_logl(const double *x, int ndim, const double *par) {
+                double s = 0.0;
+                for (int i = 0; i < ndim; ++i) s += (x[i] - par[i]) * (x[i] - par[i]);
+                return -0.5 * s;
+            }''', params=mu)
+
+    The source must define ``user_logl(const double *x, int ndim, const double *par)`` returning a double; ``params`` (the
+    reference's ``loglargs``) arrive as ``par``.  Helper functions may be defined alongside; every function of the source
+    is a device function.  A compile error raises ``ValueError`` with the NVRTC log."""
+
+    kind = _cabi.LOGL_USER
+
+    def __init__(self, source, params=None):
+        self.source = source
+        self.user_params = None if params is None else np.ascontiguousarray(params, dtype=np.float64).ravel()
+
+
+class SourcePrior(DeviceLogPrior):
+    """An arbitrary log-prior as CUDA C++ source defining ``user_logp(const double *x, int ndim, const double *par)``;
+    return ``-INFINITY`` outside the support (the log-likelihood is then not evaluated, ref :607-608)."""
+
+    kind = _cabi.LOGP_USER
+
+    def __init__(self, source, params=None):
+        self.source = source
+        self.user_params = None if params is None else np.ascontiguousarray(params, dtype=np.float64).ravel()
 
 
 class GaussianLikelihood(DeviceLogLikelihood):

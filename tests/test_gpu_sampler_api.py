@@ -260,3 +260,68 @@ def test_reference_style_resume_replays_the_chain_file(tmp_path):
         np.savetxt(os.path.join(out, "chain_1.txt"), bad)
         c, _ = _small_sampler(out, 1, 1, resume=True)
         c.sample(p0, 1000, **kw)
+
+
+def _py_targets(d, seed):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((d, d))
+    cov = A @ A.T + 0.5 * np.eye(d)
+    mu, icov = 5.0 * np.ones(d), np.linalg.inv(cov)
+    lo, hi = -50.0 * np.ones(d), 60.0 * np.ones(d)
+
+    def logl(x):
+        r = x - mu
+        return -0.5 * float(r @ (icov @ r))
+
+    def logp(x):
+        return 0.0 if np.all(lo <= x) and np.all(x <= hi) else -np.inf
+
+    return mu, icov, logl, logp
+
+
+def test_device_and_python_targets_can_be_mixed(tmp_path):
+    """A device prior with a Python likelihood, and the reverse, walk the trajectory of the all-device sampler."""
+    d, W, T, N = 6, 5, 3, 200
+    mu, icov, logl, logp = _py_targets(d, 4)
+    p0 = np.random.default_rng(3).uniform(0, 10, (T, W, d))
+    kw = dict(burn=100, covUpdate=50, Tskip=10, thin=5, isave=100)
+    runs = []
+    for name, lk, pr in (("dd", GaussianLikelihood(mu, icov=icov), UniformPrior(-50.0, 60.0)),
+                         ("pd", logl, UniformPrior(-50.0, 60.0)), ("dp", GaussianLikelihood(mu, icov=icov), logp)):
+        s = PTMCMCSampler.PTSampler(d, lk, pr, 0.05 * np.eye(d), outDir=str(tmp_path / name), verbose=False, seed=21,
+                                    ntemps=T, nwalkers=W)
+        s.sample(p0, N, **kw)
+        runs.append(s)
+    for s in runs[1:]:
+        assert np.allclose(s._chain_all, runs[0]._chain_all, rtol=1e-9, atol=1e-9)
+        assert np.allclose(s._lnlike_all, runs[0]._lnlike_all, rtol=1e-9, atol=1e-9)
+        assert s.jumpDict == runs[0].jumpDict
+
+
+def test_resume_with_python_callables(tmp_path):
+    """Reference-style resume (replay of the chain file, ref :290-319, :591-599) and the engine checkpoint with Python
+    logl / logp, as the reference allows for any callable."""
+    d, N = 4, 400
+    mu, icov, logl, logp = _py_targets(d, 7)
+    p0 = np.random.default_rng(5).uniform(0, 10, d)
+    kw = dict(burn=100, covUpdate=50, thin=2, isave=100)
+    out = str(tmp_path / "replay")
+    a = PTMCMCSampler.PTSampler(d, logl, logp, 0.05 * np.eye(d), outDir=out, verbose=False, seed=3)
+    a.sample(p0, N, **kw)
+    first = np.loadtxt(os.path.join(out, "chain_1.txt"))
+    b = PTMCMCSampler.PTSampler(d, logl, logp, 0.05 * np.eye(d), outDir=out, verbose=False, seed=4, resume=True)
+    b.sample(p0, 2 * N, **kw)
+    data = np.loadtxt(os.path.join(out, "chain_1.txt"))
+    assert data.shape[0] == 2 * N // 2 + 1 and np.array_equal(data[:len(first)], first) and b.resumeLength == len(first)
+    # exact continuation from an engine checkpoint
+    out2 = str(tmp_path / "ckpt")
+    full = PTMCMCSampler.PTSampler(d, logl, logp, 0.05 * np.eye(d), outDir=str(tmp_path / "full"), verbose=False, seed=3)
+    full.sample(p0, 2 * N, **kw)
+    c = PTMCMCSampler.PTSampler(d, logl, logp, 0.05 * np.eye(d), outDir=out2, verbose=False, seed=3, checkpoint=True)
+    c.sample(p0, N, **kw)
+    e = PTMCMCSampler.PTSampler(d, logl, logp, 0.05 * np.eye(d), outDir=out2, verbose=False, seed=3, resume=True)
+    e.sample(p0, 2 * N, **kw)
+    for x, y in zip(full.get_state(), e.get_state()):
+        assert np.array_equal(x, y)
+    assert np.array_equal(np.loadtxt(os.path.join(str(tmp_path / "full"), "chain_1.txt"))[:, :d],
+                          np.loadtxt(os.path.join(out2, "chain_1.txt"))[:, :d])
