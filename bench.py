@@ -473,6 +473,80 @@ def side_config(name, local_rank, hbm_peak, hbm_src, fp64_peak, steps=3, warmup=
     return out
 
 
+GAUSS_SOURCE = """
+// par = mu[ndim], icov[ndim * ndim] (row-major): the C2 likelihood written the way a user would write it
+double user_logl(const double *x, int ndim, const double *par) {
+    const double *mu = par, *icov = par + ndim;
+    double acc = 0.0;
+    for (int i = 0; i < ndim; ++i) {
+        double row = 0.0;
+        for (int j = 0; j < ndim; ++j) row += icov[i * ndim + j] * (x[j] - mu[j]);
+        acc += (x[i] - mu[i]) * row;
+    }
+    return -0.5 * acc;
+}
+"""
+
+
+def user_target_run(local_rank):
+    """The C2 workload with the likelihood supplied as CUDA source (compiled with NVRTC into the thread-per-chain
+    kernel): what an arbitrary user likelihood costs on the device."""
+    from ptmcmcsampler_b200 import _cabi
+
+    wl = Workload("C2")
+    kw = wl.engine_kwargs()
+    kw.pop("logl_params")
+    kw["logl_kind"] = _cabi.LOGL_USER
+    t0 = time.perf_counter()
+    eng = _cabi.Engine(wl.d, wl.W, wl.T, wl.cov0, wl.ladder, seed=42, record_rows=(BURN + 100 + 3 * ITERS) // THIN + 2,
+                       device=local_rank, logl_source=GAUSS_SOURCE,
+                       logl_user_params=np.concatenate([wl.mu, wl.icov.ravel()]), **kw)
+    t_create = time.perf_counter() - t0
+    eng.set_state(wl.x0(1, wl.T, wl.W))
+    eng.run(BURN + 100)
+    eng.sync()
+    t0 = time.perf_counter()
+    eng.run(2 * ITERS)
+    eng.sync()
+    dt = time.perf_counter() - t0
+    name = eng.mh_kernel_name
+    eng.close()
+    return {"workload": wl.desc + "; log-likelihood given as CUDA source (SourceLikelihood), box prior built in",
+            "value": wl.W * wl.T * 2 * ITERS / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / 2, "kernel": name,
+            "create_s_including_nvrtc": t_create}
+
+
+def host_callback_run(local_rank):
+    """Python callables in the loop (the reference's own calling convention, vectorised over chains): one host round trip
+    per iteration through the engine's page-locked buffers."""
+    from ptmcmcsampler_b200 import PTMCMCSampler
+
+    wl = Workload("C2")
+    d, W, T, n = wl.d, 1024, 8, 300
+    mu, icov = wl.mu, wl.icov
+
+    def logl(X):
+        D = X - mu
+        return -0.5 * np.einsum("ni,ij,nj->n", D, icov, D)
+
+    def logp(X):
+        return np.where(np.all((X >= -50.0) & (X <= 60.0), axis=1), 0.0, -np.inf)
+
+    outdir = tempfile.mkdtemp(prefix="ptmcmc_bench_cb_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    s = PTMCMCSampler.PTSampler(d, logl, logp, wl.cov0.copy(), outDir=outdir, verbose=False, seed=5, ntemps=T, nwalkers=W,
+                                device=local_rank, vectorized=True)
+    p0 = wl.x0(3, T, W)
+    t0 = time.perf_counter()
+    s.sample(p0, n, burn=100, covUpdate=100, Tskip=10, thin=10, isave=n)
+    dt = time.perf_counter() - t0
+    s.close()
+    import shutil
+
+    shutil.rmtree(outdir, ignore_errors=True)
+    return {"workload": "C2 target as vectorised numpy callables, %d walkers x %d temps, %d iterations" % (W, T, n),
+            "value": W * T * n / dt, "unit": UNIT, "ms_per_iteration": 1e3 * dt / n}
+
+
 def run_engine(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -497,6 +571,8 @@ def run_engine(args, rank, world, local_rank):
     extra = {}
     if world == 1 and not args.no_side:
         extra["configs"] = {name: side_config(name, local_rank, hbm_peak, hbm_src, fp64_peak) for name in ("C3", "C4")}
+        extra["user_target"] = user_target_run(local_rank)
+        extra["host_callback"] = host_callback_run(local_rank)
     if world > 1 and not ladder_mode and not args.no_side:
         # BASELINE config 5: the same GPUs as ONE ladder of 32 N rungs, 32 per GPU, nearest-neighbour swap exchange
         k = max(2, min(args.steps, 5))
