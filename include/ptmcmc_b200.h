@@ -237,6 +237,9 @@ int32_t ptmcmc_maintain(ptmcmc_engine *e);
 int64_t ptmcmc_state_bytes(const ptmcmc_engine *e);
 int32_t ptmcmc_save_state(ptmcmc_engine *e, void *buf, int64_t nbytes);
 int32_t ptmcmc_load_state(ptmcmc_engine *e, const void *buf, int64_t nbytes);
+/* the seed a checkpoint was written with (the loading engine must be created with it: ptmcmc_load_state refuses a
+ * checkpoint whose seed, thin, Tskip, walker offset, ladder or proposal cycle differ from the engine's) */
+int32_t ptmcmc_state_seed(const void *buf, int64_t nbytes, uint64_t *seed);
 /* Reference-style resume (ref :591-599): advance the engine through `nrows * repeat` iterations whose
  * states are given instead of proposed -- row r is used for `repeat` (= thin) consecutive iterations, the
  * first call starting at iteration 1 with row index (iteration / repeat).  Buffers, covariance / DE

@@ -213,8 +213,21 @@ class CurvedProblem(object):
         return -np.inf
 
 
+def read_output_files(outdir):
+    """Everything the reference wrote into its outDir (ref writeOutput / _writeToFile :341-372, :722-766): text files
+    as bytes, cov.npy as an array."""
+    files = {}
+    for name in sorted(os.listdir(outdir)):
+        path = os.path.join(outdir, name)
+        if name.endswith(".txt"):
+            files[name] = open(path, "rb").read()
+        elif name == "cov.npy":
+            files[name] = np.load(path)
+    return files
+
+
 def run_reference(ndim, logl, logp, cov0, p0s, niter, seed, ntemps=1, shim=True, sample_kwargs=None,
-                  groups=None, ext_jumps=(), ladder=None):
+                  groups=None, ext_jumps=(), ladder=None, outdir=None, resume=False):
     """Run the reference with one sampler per temperature and trace every iteration.
 
     p0s: [ntemps][ndim] initial points.  ext_jumps: list of (callable(x, iter, beta), weight) added
@@ -225,12 +238,12 @@ def run_reference(ndim, logl, logp, cov0, p0s, niter, seed, ntemps=1, shim=True,
     comms = ThreadComm.world(ntemps) if ntemps > 1 else [ref.MPI.COMM_WORLD]
     out = [None] * ntemps
     errors = []
-    outdir = tempfile.mkdtemp(prefix="ptmcmc_ref_")
+    outdir = outdir or tempfile.mkdtemp(prefix="ptmcmc_ref_")
 
     def worker(rank):
         try:
             sampler = ref.PTSampler(ndim, logl, logp, np.copy(cov0), groups=groups, comm=comms[rank],
-                                    outDir=outdir, verbose=False, seed=seed)
+                                    outDir=outdir, verbose=False, seed=seed, resume=resume)
             if shim:
                 sampler.stream = ShimStream(seed, 0, rank)
             for entry in ext_jumps:
@@ -295,9 +308,13 @@ def run_reference(ndim, logl, logp, cov0, p0s, niter, seed, ntemps=1, shim=True,
         else:
             names[entry[0].__name__] = next_ext
             next_ext += 1
+    names[None] = -1  # iterations replayed from the chain file on resume (ref :591-599) propose nothing
+
     def _by_id(col):
         arr = np.zeros((ntemps, max(names.values()) + 1), dtype=np.int64)
         for nm, jid in names.items():
+            if nm is None:
+                continue
             for t in range(ntemps):
                 arr[t, jid] = out[t]["sampler"].jumpDict.get(nm, [0, 0])[col]
         return arr

@@ -131,6 +131,14 @@ class PTSampler(object):
                 outDir = os.path.join(outDir, "rank%d" % r)
         self._lo, self._Tloc = 0, self.nchain
         self._comm = None
+        if seed is None and resume:
+            # an engine checkpoint continues exactly only under the seed it was written with (the draws are keyed by it)
+            for cand in ("engine_state.npy", "engine_state_%d.npy" % self._shard_rank):
+                path = os.path.join(outDir, cand)
+                if os.path.isfile(path):
+                    seed = _cabi.checkpoint_seed(np.load(path, mmap_mode="r")[:4096])
+                    if seed is not None:
+                        break
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")
         self.seed = int(seed)

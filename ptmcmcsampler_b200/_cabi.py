@@ -63,7 +63,7 @@ SYMBOLS = [
     "ptmcmc_test_normals", "ptmcmc_measure_fp64_peak", "ptmcmc_set_sink", "ptmcmc_sink_wait", "ptmcmc_snapshot_bytes",
     "ptmcmc_snapshot", "ptmcmc_snapshot_wait", "ptmcmc_adapt_begin_dev", "ptmcmc_adapt_finish_dev", "ptmcmc_factor_dev",
     "ptmcmc_factor_refresh", "ptmcmc_user_compile_check", "ptmcmc_callback_buffers", "ptmcmc_propose_pinned",
-    "ptmcmc_accept_pinned",
+    "ptmcmc_accept_pinned", "ptmcmc_state_seed",
 ]
 
 _lib = None
@@ -138,6 +138,7 @@ def load():
     L.ptmcmc_state_bytes.argtypes = [h]
     L.ptmcmc_save_state.argtypes = [h, C.c_void_p, C.c_int64]
     L.ptmcmc_load_state.argtypes = [h, C.c_void_p, C.c_int64]
+    L.ptmcmc_state_seed.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]
     L.ptmcmc_replay.argtypes = [h, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, _dp]
     L.ptmcmc_mh_kernel_name.restype = C.c_char_p
     L.ptmcmc_mh_kernel_name.argtypes = [h]
@@ -587,6 +588,14 @@ class Engine(object):
     @property
     def mh_kernel_name(self):
         return self._L.ptmcmc_mh_kernel_name(self._h).decode()
+
+
+def checkpoint_seed(buf):
+    """Seed recorded in an engine checkpoint (``Engine.save_state`` bytes); None if ``buf`` is not one."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    seed = C.c_uint64()
+    rc = load().ptmcmc_state_seed(buf.ctypes.data, buf.size, C.byref(seed))
+    return int(seed.value) if rc == 0 else None
 
 
 def user_compile_check(logl_source=None, logp_source=None, cc=(10, 0)):

@@ -337,19 +337,21 @@ __global__ void __launch_bounds__(256) de_append_kernel(const double *am, double
                                                         long long burn, long long new_head)
 {
     __shared__ double tile[32][33];
-    // grid: (ceil(W/32), ceil(d/32), cu)
-    const long long slot = blockIdx.z;
-    const long long dst_slot = (new_head + (burn - cu) + slot) % burn;
+    // grid: (ceil(W/32), ceil(d/32), min(cu, 65535)); a block strides over the slots (gridDim.z is capped at 65535)
     const int w0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    for (int kk = ty; kk < 32; kk += 8) {
-        const int k = k0 + kk, w = w0 + tx;
-        tile[kk][tx] = (k < d && w < W) ? am[((size_t)slot * d + k) * W + w] : 0.0;
-    }
-    __syncthreads();
-    for (int ww = ty; ww < 32; ww += 8) {
-        const int w = w0 + ww, k = k0 + tx;
-        if (w < W && k < d) de[((size_t)dst_slot * W + w) * d + k] = tile[tx][ww];
+    for (long long slot = blockIdx.z; slot < cu; slot += gridDim.z) {
+        const long long dst_slot = (new_head + (burn - cu) + slot) % burn;
+        for (int kk = ty; kk < 32; kk += 8) {
+            const int k = k0 + kk, w = w0 + tx;
+            tile[kk][tx] = (k < d && w < W) ? am[((size_t)slot * d + k) * W + w] : 0.0;
+        }
+        __syncthreads();
+        for (int ww = ty; ww < 32; ww += 8) {
+            const int w = w0 + ww, k = k0 + tx;
+            if (w < W && k < d) de[((size_t)dst_slot * W + w) * d + k] = tile[tx][ww];
+        }
+        __syncthreads();
     }
 }
 

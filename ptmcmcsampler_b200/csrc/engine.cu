@@ -367,7 +367,7 @@ int de_update(Engine *e)
     {
         LaunchTimer lt(e, PTMCMC_K_DE);
         const long long new_head = (e->de_head + cu) % burn;
-        dim3 grid((e->W + 31) / 32, (e->d + 31) / 32, (unsigned)cu);
+        dim3 grid((e->W + 31) / 32, (e->d + 31) / 32, (unsigned)std::min<long long>(cu, 65535));
         de_append_kernel<<<grid, 256, 0, e->stream>>>(e->d_am, e->d_de, e->d, e->W, cu, burn, new_head);
         e->de_head = new_head;
     }
@@ -1456,7 +1456,28 @@ struct StateHeader {
     int32_t version, d, W, T, Tg, temp_offset, njumps, de_in_cycle;
     int64_t cov_update, burn, iter, de_head, swap_proposed, swap_events, nsamp, adapt_done_iter, de_done_iter;
     int64_t usize, ssize;
+    // what keys the draws and the record layout: a checkpoint continues exactly only under the same values
+    uint64_t seed, config_hash;
+    int64_t thin, tskip;
+    int32_t walker_offset, pad;
 };
+
+// FNV-1a over the ladder, the MH temperatures and the proposal cycle
+uint64_t config_hash_of(const Engine *e)
+{
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](const void *p, size_t n) {
+        const unsigned char *b = (const unsigned char *)p;
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    mix(e->ladder.data(), sizeof(double) * e->ladder.size());
+    mix(e->mh_temp.data(), sizeof(double) * e->mh_temp.size());
+    const int nc = e->cfg.ncycle;
+    mix(e->cfg.cycle_jump, sizeof(int32_t) * nc);
+    mix(e->cfg.cycle_weight, sizeof(int32_t) * nc);
+    mix(&e->cfg.de_weight, sizeof(int32_t));
+    return h;
+}
 constexpr uint64_t STATE_MAGIC = 0x3030324250544d43ull;  // "CMTPB200"
 
 struct StateField {
@@ -1501,6 +1522,8 @@ int32_t ptmcmc_save_state(ptmcmc_engine *h, void *buf, int64_t nbytes)
     hd.swap_proposed = e->swap_proposed; hd.swap_events = e->swap_events; hd.nsamp = e->nsamp;
     hd.adapt_done_iter = e->adapt_done_iter; hd.de_done_iter = e->de_done_iter;
     hd.usize = e->uoff[e->ngroups]; hd.ssize = e->soff[e->ngroups];
+    hd.seed = e->cfg.seed; hd.config_hash = config_hash_of(e);
+    hd.thin = e->cfg.thin; hd.tskip = e->cfg.tskip; hd.walker_offset = e->cfg.walker_offset;
     char *out = (char *)buf;
     memcpy(out, &hd, sizeof hd);
     out += sizeof hd;
@@ -1526,6 +1549,16 @@ int32_t ptmcmc_load_state(ptmcmc_engine *h, const void *buf, int64_t nbytes)
         hd.ssize != e->soff[e->ngroups])
         return fail(e, PTMCMC_ERR_ARG, "checkpoint was written by an engine with a different configuration");
     if (hd.njumps != e->njumps) return fail(e, PTMCMC_ERR_ARG, "checkpoint has %d jump kinds, engine %d", hd.njumps, e->njumps);
+    if (hd.seed != e->cfg.seed)
+        return fail(e, PTMCMC_ERR_ARG, "checkpoint was written with seed %llu, engine has %llu: the draws are keyed by the seed, "
+                    "so the run would not continue where it stopped (ptmcmc_state_seed reads it back)",
+                    (unsigned long long)hd.seed, (unsigned long long)e->cfg.seed);
+    if (hd.thin != e->cfg.thin || hd.tskip != e->cfg.tskip || hd.walker_offset != e->cfg.walker_offset)
+        return fail(e, PTMCMC_ERR_ARG, "checkpoint was written with thin=%lld Tskip=%lld walker_offset=%d, engine has %lld / %lld / %d",
+                    (long long)hd.thin, (long long)hd.tskip, hd.walker_offset, (long long)e->cfg.thin, (long long)e->cfg.tskip,
+                    e->cfg.walker_offset);
+    if (hd.config_hash != config_hash_of(e))
+        return fail(e, PTMCMC_ERR_ARG, "checkpoint was written with a different ladder or proposal cycle");
     if (nbytes < ptmcmc_state_bytes(h)) return fail(e, PTMCMC_ERR_ARG, "checkpoint truncated");
     const char *in = (const char *)buf + sizeof hd;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -1548,6 +1581,16 @@ int32_t ptmcmc_load_state(ptmcmc_engine *h, const void *buf, int64_t nbytes)
     cudaError_t st = build_u_frags(e);
     if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "fragment rebuild: %s", cudaGetErrorString(st));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int32_t ptmcmc_state_seed(const void *buf, int64_t nbytes, uint64_t *seed)
+{
+    if (!buf || !seed || nbytes < (int64_t)sizeof(StateHeader)) return PTMCMC_ERR_ARG;
+    StateHeader hd;
+    memcpy(&hd, buf, sizeof hd);
+    if (hd.magic != STATE_MAGIC || hd.version != PTMCMC_ABI_VERSION) return PTMCMC_ERR_ARG;
+    *seed = hd.seed;
     return 0;
 }
 

@@ -80,7 +80,49 @@ def traj_case(name, d, T, N, seed, sample_kwargs, groups=None, curved=False, pmi
     goff = np.cumsum([0] + [len(g) for g in groups]) if groups is not None else np.array([0, d])
     save(name, d=d, T=T, N=N, seed=seed, cov0=cov0, p0=p0, group_offsets=goff, group_indices=gflat,
          has_groups=int(groups is not None), ext=int(ext), prior_weight=int(prior_weight),
-         **{"kw_" + k: v for k, v in sample_kwargs.items()}, **meta, **r)
+         **{"kw_" + k: v for k, v in sample_kwargs.items()}, **meta, **r, **output_files(r["_outdir"]))
+
+
+def output_files(outdir):
+    """The files the reference wrote (chain_*.txt, jumps.txt, *_jump.txt as bytes; cov.npy as an array), keyed
+    ``file_<name with . -> _>`` plus the list of names."""
+    files = rh.read_output_files(outdir)
+    out = {"file_names": np.array(sorted(files))}
+    for name, val in files.items():
+        out["file_" + name.replace(".", "_")] = val if isinstance(val, np.ndarray) else np.frombuffer(val, dtype=np.uint8)
+    return out
+
+
+def resume_case(name, d, N, seed, sample_kwargs):
+    """Reference run of N iterations, then a second sampler with resume=True on the same outDir to 2N (ref :290-319,
+    :474-476, :591-599), both under the shim stream.  The proposal cycle is a deterministic plugin jump plus DE only
+    (SCAMweight = AMweight = 0), so the trajectory does not depend on LAPACK's eigenvector signs."""
+    import shutil
+
+    pb = gaussian_problem(d, seed, 0.0, 10.0)
+    rng = np.random.default_rng(seed + 1000)
+    p0 = rng.uniform(0.0, 10.0, (1, d))
+    cov0 = np.diag(0.01 * (1.0 + np.arange(d)))
+
+    def golden_ext_jump(x, it, beta):
+        frac = np.modf(np.abs(np.sin(np.arange(1, len(x) + 1) * (it + 1.0) + 13.0 * x)) * 1e4)[0]
+        return pb.a + (pb.b - pb.a) * (0.45 + 0.1 * frac), 0.05 * np.sin(it) * beta
+
+    ext = [(golden_ext_jump, 7)]
+    first = rh.run_reference(d, pb.lnlikefn, pb.lnpriorfn, cov0, p0, N, seed=seed, sample_kwargs=sample_kwargs, ext_jumps=ext)
+    files_first = output_files(first["_outdir"])
+    second = rh.run_reference(d, pb.lnlikefn, pb.lnpriorfn, cov0, p0, 2 * N, seed=seed, sample_kwargs=sample_kwargs,
+                              ext_jumps=ext, outdir=first["_outdir"], resume=True)
+    s2 = second["_samplers"][0]
+    save(name, d=d, T=1, N=N, seed=seed, cov0=cov0, p0=p0, ext=1, kind="gaussian", pb_mu=pb.mu, pb_icov=pb.icov, pb_lo=pb.a,
+         pb_hi=pb.b, inclusive=1, **{"kw_" + k: v for k, v in sample_kwargs.items()},
+         **{"first_" + k: v for k, v in files_first.items()},
+         **{"second_" + k: v for k, v in output_files(first["_outdir"]).items()},
+         resume_length=int(s2.resumeLength), naccepted=float(s2.naccepted), jump=second["jump"], acc=second["acc"],
+         x=second["x"], lnl=second["lnl"], chain=second["chain"], chain_lnl=second["chain_lnl"],
+         chain_lnp=second["chain_lnp"], am=second["am"], de=second["de"], cov=second["cov"], mu=second["mu"],
+         m2=second["m2"], jump_prop=second["jump_prop"], jump_acc=second["jump_acc"], ladder=second["ladder"])
+    shutil.rmtree(first["_outdir"], ignore_errors=True)
 
 
 def stats_case(name, d, T, N, nrep, sample_kwargs, pmin, pmax, seed0, burn_frac=0.25):
@@ -124,6 +166,9 @@ def main():
     # the device-side prior-draw jump against the reference running the equivalent plugin
     kw6 = dict(burn=100, thin=1, covUpdate=50, SCAMweight=15, AMweight=15, DEweight=20, isave=1000, Tskip=10)
     traj_case("traj_t2_prior_d4", 4, 2, 300, 77, kw6, pmin=0.0, pmax=10.0, prior_weight=10)
+    # reference-style resume: 300 iterations, then resume=True on the same directory to 600
+    kw7 = dict(burn=100, thin=2, covUpdate=50, SCAMweight=0, AMweight=0, DEweight=40, isave=100, Tskip=100)
+    resume_case("resume_t1_d4", 4, 300, 55, kw7)
     if "--traj-only" in sys.argv:  # the statistical bands do not depend on the oracle's draw functions
         return
     # statistical bands (reference's own PCG64 stream)

@@ -160,7 +160,7 @@ def _small_sampler(outdir, W, T, seed=5, **kw):
     lk, pr = GaussianLikelihood(np.full(d, 5.0), cov=cov), UniformPrior(-50, 60)
     s = PTMCMCSampler.PTSampler(d, lk, pr, np.eye(d) * 0.01, outDir=outdir, verbose=False, seed=seed, ntemps=T,
                                 nwalkers=W, **kw)
-    p0 = np.random.default_rng(seed).uniform(0, 10, (T, W, d))
+    p0 = np.random.default_rng(5 if seed is None else seed).uniform(0, 10, (T, W, d))
     return s, p0
 
 
@@ -234,6 +234,33 @@ def test_checkpoint_resume_is_exact(tmp_path):
     fa = np.loadtxt(os.path.join(str(tmp_path / "a"), "chain_1.0.txt"))
     fc = np.loadtxt(os.path.join(str(tmp_path / "b"), "chain_1.0.txt"))
     assert fa.shape == fc.shape == (121, 10) and np.array_equal(fa[:, :8], fc[:, :8])
+    # rows before the checkpoint: walker 0's come back from its chain file, nothing stale is exposed
+    assert np.array_equal(c._chain_all[:61, 0], fc[:61, :6]) and np.all(c._chain_all[:61, 1:] == 0)
+    with pytest.raises(ValueError):
+        c.write_walker_chain(3)
+
+
+def test_checkpoint_resume_recovers_the_seed_and_rejects_a_changed_schedule(tmp_path):
+    """seed=None on resume takes the seed from the checkpoint (the draws are keyed by it); a checkpoint written under another
+    thin / Tskip / ladder is refused instead of silently continuing a different run."""
+    from ptmcmcsampler_b200 import _cabi
+
+    kw = dict(burn=100, covUpdate=50, Tskip=10, thin=5, isave=100)
+    a, p0 = _small_sampler(str(tmp_path / "a"), 8, 3, seed=77)
+    a.sample(p0, 400, **kw)
+    b, _ = _small_sampler(str(tmp_path / "b"), 8, 3, seed=77, checkpoint=True)
+    b.sample(p0, 200, **kw)
+    c, _ = _small_sampler(str(tmp_path / "b"), 8, 3, seed=None, resume=True)
+    assert c.seed == 77
+    c.sample(p0, 400, **kw)
+    for x, y in zip(a.get_state(), c.get_state()):
+        assert np.array_equal(x, y)
+    bad, _ = _small_sampler(str(tmp_path / "b"), 8, 3, seed=78, resume=True)
+    with pytest.raises(_cabi.EngineError):
+        bad.sample(p0, 600, **kw)
+    bad2, _ = _small_sampler(str(tmp_path / "b"), 8, 3, seed=77, resume=True)
+    with pytest.raises(_cabi.EngineError):
+        bad2.sample(p0, 600, **dict(kw, Tskip=20))
 
 
 def test_reference_style_resume_replays_the_chain_file(tmp_path):
