@@ -844,6 +844,7 @@ class PTSampler(object):
             eng.replay(n, self.thin, rows_x[first:last + 1], rows_lnl[first:last + 1], rows_lp[first:last + 1])
             done += n
             self._pull_rows()
+        self._maybe_add_de_bulk(0, total)                      # DE joined the cycle during the replay (ref :563-585)
         self.ind_next_write = R                                # these rows are already in the file (ref :476)
         self._acc_offset = total * float(rc[-1, -2])           # ref :599
         self._resumed_at = total

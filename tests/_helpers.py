@@ -21,7 +21,7 @@ def golden_ext_jump_factory(lo, hi):
 
 
 def fixture_groups(g):
-    if not int(g["has_groups"]):
+    if "has_groups" not in g or not int(g["has_groups"]):
         return None
     off, idx = g["group_offsets"], g["group_indices"]
     return [idx[off[i]:off[i + 1]].astype(np.int32) for i in range(len(off) - 1)]
