@@ -213,6 +213,42 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
             const int jump = pick_jump(p, st);
             s_jt[tid] = (unsigned char)jump;
             kind = (jump == JUMP_AM) ? 0 : (jump == JUMP_SCAM) ? 1 : 2;
+            // Every scalar draw of a SCAM or DE step is made here, by the chain's own thread, before any state is touched:
+            // phase R is then nothing but evenly spread tasks (gathers and AM normals), none of them a long serial one.
+            if (kind == 1) {  // SCAM (ref :839-873): prob, k, normal, accept uniform = words 2..5
+                st.j = 2;
+                const double prob = word_to_unit(st.next());
+                const double scale = cov_jump_scale(prob, s_temp[tid]);
+                const int k = (int)word_to_int(st.next(), (unsigned long long)d);
+                const double cd = 2.4 / sqrt(2.0) * scale;
+                double z0, z1;
+                word_to_normals(st.next(), z0, z1);
+                s_sca[tid] = z0 * cd * sSs[k];  // the step is coef * U[:, k] (ref :868-873)
+                s_rowm[tid] = (unsigned long long)k * (unsigned long long)d;
+                s_uword[tid] = st.next();
+            } else if (kind == 2) {
+                // DE (ref :955-976): the two history rows (words 2, 3, redrawn while equal), prob, scale, accept uniform;
+                // the rows are prefetched into L2 for the gather tasks of phase R
+                st.j = 2;
+                const unsigned long long mm = word_to_int(st.next(), bufsize);
+                unsigned long long nn = word_to_int(st.next(), bufsize);
+                while (mm == nn) nn = word_to_int(st.next(), bufsize);
+                const unsigned long long om = de_row_offset(mm, bufsize, W, p.burn, p.de_head) * (unsigned long long)d;
+                const unsigned long long on = de_row_offset(nn, bufsize, W, p.burn, p.de_head) * (unsigned long long)d;
+                s_rowm[tid] = om;
+                s_rown[tid] = on;
+                for (int b = 0; b < 8 * d; b += 128) {
+                    prefetch_l2(reinterpret_cast<const char *>(p.de + om) + b);
+                    prefetch_l2(reinterpret_cast<const char *>(p.de + on) + b);
+                }
+                prefetch_l2(p.de + om + d - 1);
+                prefetch_l2(p.de + on + d - 1);
+                const double prob = word_to_unit(st.next());
+                double scale = 1.0;
+                if (!(prob > 0.5)) scale = word_to_unit(st.next()) * 2.4 / sqrt(2.0 * d) * sqrt(1.0 / s_beta[tid]);
+                s_sca[tid] = scale;
+                s_uword[tid] = st.next();
+            }
         }
 #pragma unroll
         for (int kk = 0; kk < 3; ++kk) {
@@ -231,71 +267,58 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
 
         // ================= phase R: every draw after word 1, as evenly spread tasks
         {
-            // task order: DE first (their history rows are prefetched into L2 while the rest of the phase
-            // computes), then SCAM, then the AM (chain, block) pairs
-            const int tA = nA * am_tasks, nSD = nS + nD, ntask = nSD + tA;
-            for (int q = tid; q < ntask; q += MMA_THREADS) {
-                if (q >= nSD) {
-                    // AM (ref :897-930): word 2 = prob, 3 + j = normal pair j, 3 + npairs = accept u
-                    const int qa = q - nSD;
-                    const int ai = qa % nA, b = 1 + qa / nA;
-                    const int cl = s_list[ai];
-                    const uint4 blk = philox4x32_10(p, (uint32_t)it, (PURPOSE_MH << 24) | (uint32_t)b,
-                                                    (uint32_t)(p.walker_offset + s_cw[cl]),
-                                                    (uint32_t)(p.temp_offset + s_ct[cl]));
+            // task order: the gathers first, one task per (DE or SCAM chain, 8 columns) -- DE: B[mm] - B[nn], SCAM: coef * row k
+            // of the transposed factor -- into the chain's zq row (every load of the block in flight at once, their latency
+            // hidden by the AM tasks that follow); then the AM (chain, Philox block) pairs
+            const int tG = (nD + nS) * NT;
+            for (int q = tid; q < tG; q += MMA_THREADS) {
+                const int ci = q % (nD + nS), seg = q / (nD + nS);
+                const bool de = ci < nD;
+                const int cl = de ? s_list[2 * nc + ci] : s_list[nc + ci - nD];
+                const double *bm = (de ? p.de : a.Ut) + s_rowm[cl], *bn = p.de + (de ? s_rown[cl] : 0ull);
+                const double coef = de ? 1.0 : s_sca[cl];
+                const int col = 8 * seg;
+                double *dst = zq + cl * ld + col;
+                if ((d & 1) == 0) {  // rows are 16-byte aligned
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int wi = 2 * b + h;
-                        const uint64_t word = h ? ((uint64_t)blk.z | ((uint64_t)blk.w << 32))
-                                                : ((uint64_t)blk.x | ((uint64_t)blk.y << 32));
-                        if (wi == 2) {
-                            s_sca[cl] = 2.4 / sqrt(2.0 * d) * cov_jump_scale(word_to_unit(word), s_temp[cl]);
-                        } else if (wi < uword) {
-                            double z0, z1;
-                            word_to_normals(word, z0, z1);
-                            const int j = 2 * (wi - 3);
-                            zq[cl * ld + j] = z0;
-                            if (j + 1 < KP) zq[cl * ld + j + 1] = z1;
-                        } else if (wi == uword) {
-                            s_uword[cl] = word;
+                    for (int k = 0; k < 8; k += 2) {
+                        double2 v = make_double2(0.0, 0.0);
+                        if (col + k < d) {
+                            const double2 vm = __ldg(reinterpret_cast<const double2 *>(bm + col + k));
+                            double2 vn = make_double2(0.0, 0.0);
+                            if (de) vn = __ldg(reinterpret_cast<const double2 *>(bn + col + k));
+                            v = make_double2(coef * (vm.x - vn.x), coef * (vm.y - vn.y));
                         }
+                        *reinterpret_cast<double2 *>(dst + k) = v;
                     }
                 } else {
-                    const bool scam = q >= nD;
-                    const int cl = scam ? s_list[nc + q - nD] : s_list[2 * nc + q];
-                    const double temp = s_temp[cl];
-                    Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + s_cw[cl]),
-                              (uint32_t)(p.temp_offset + s_ct[cl]));
-                    st.j = 2;
-                    if (scam) {  // ref :839-873
-                        const double prob = word_to_unit(st.next());
-                        const double scale = cov_jump_scale(prob, temp);
-                        const int k = (int)word_to_int(st.next(), (unsigned long long)d);
-                        const double cd = 2.4 / sqrt(2.0) * scale;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        dst[k] = (col + k < d) ? coef * (__ldg(bm + col + k) - (de ? __ldg(bn + col + k) : 0.0)) : 0.0;
+                }
+            }
+            const int tA = nA * am_tasks;
+            for (int q = tid; q < tA; q += MMA_THREADS) {
+                // AM (ref :897-930): word 2 = prob, 3 + j = normal pair j, 3 + npairs = accept u
+                const int ai = q % nA, b = 1 + q / nA;
+                const int cl = s_list[ai];
+                const uint4 blk = philox4x32_10(p, (uint32_t)it, (PURPOSE_MH << 24) | (uint32_t)b,
+                                                (uint32_t)(p.walker_offset + s_cw[cl]), (uint32_t)(p.temp_offset + s_ct[cl]));
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int wi = 2 * b + h;
+                    const uint64_t word = h ? ((uint64_t)blk.z | ((uint64_t)blk.w << 32)) : ((uint64_t)blk.x | ((uint64_t)blk.y << 32));
+                    if (wi == 2) {
+                        s_sca[cl] = 2.4 / sqrt(2.0 * d) * cov_jump_scale(word_to_unit(word), s_temp[cl]);
+                    } else if (wi < uword) {
                         double z0, z1;
-                        word_to_normals(st.next(), z0, z1);
-                        s_sca[cl] = z0 * cd * sSs[k];
-                        s_rowm[cl] = (unsigned long long)k;
-                    } else {  // DE, ref :955-976
-                        const unsigned long long mm = word_to_int(st.next(), bufsize);
-                        unsigned long long nn = word_to_int(st.next(), bufsize);
-                        while (mm == nn) nn = word_to_int(st.next(), bufsize);
-                        const unsigned long long om = de_row_offset(mm, bufsize, W, p.burn, p.de_head) * (unsigned long long)d;
-                        const unsigned long long on = de_row_offset(nn, bufsize, W, p.burn, p.de_head) * (unsigned long long)d;
-                        for (int b = 0; b < 8 * d; b += 128) {
-                            prefetch_l2(reinterpret_cast<const char *>(p.de + om) + b);
-                            prefetch_l2(reinterpret_cast<const char *>(p.de + on) + b);
-                        }
-                        prefetch_l2(p.de + om + d - 1);
-                        prefetch_l2(p.de + on + d - 1);
-                        const double prob = word_to_unit(st.next());
-                        double scale = 1.0;
-                        if (!(prob > 0.5)) scale = word_to_unit(st.next()) * 2.4 / sqrt(2.0 * d) * sqrt(1.0 / s_beta[cl]);
-                        s_sca[cl] = scale;
-                        s_rowm[cl] = om;
-                        s_rown[cl] = on;
+                        word_to_normals(word, z0, z1);
+                        const int j = 2 * (wi - 3);
+                        zq[cl * ld + j] = z0;
+                        if (j + 1 < KP) zq[cl * ld + j + 1] = z1;
+                    } else if (wi == uword) {
+                        s_uword[cl] = word;
                     }
-                    s_uword[cl] = st.next();
                 }
             }
         }
@@ -388,37 +411,16 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
             const int cl = tile * 8 + r;
             const bool live = c0 + cl < TW;
             const int jump = s_jt[cl] & 0x7F;
-            // the step q - x of this lane's columns: AM from zq (phase P); SCAM = coef * U[:, k] read from the
-            // transposed factor (ref :868-873); DE = scale * (B[mm] - B[nn]) gathered here, every load of the
-            // tile in flight at once (ref :978-983; the rows were prefetched into L2 in phase R)
+            // the step q - x of this lane's columns, from the chain's zq row for every kind: AM = U delta (phase P), SCAM =
+            // coef * U[:, k] and DE = B[mm] - B[nn] (phase R; DE times its scale, ref :978-983)
             double stp[NT][2];
             {
-                const double sc = s_sca[cl];
-                const bool is_scam = live && jump == JUMP_SCAM, is_de = live && jump == JUMP_DE;
-                const double *r0 = is_scam ? a.Ut + s_rowm[cl] * (unsigned long long)d : p.de + (is_de ? s_rowm[cl] : 0ull);
-                const double *r1 = p.de + (is_de ? s_rown[cl] : 0ull);
-                const bool vec = (d & 1) == 0;  // rows are 16-byte aligned
+                const double mult = (live && jump == JUMP_DE) ? s_sca[cl] : 1.0;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    const int col = 8 * nt + 2 * t;
-                    double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
-                    if (is_scam || is_de) {
-                        if (vec) {
-                            if (col < d) va = __ldg(reinterpret_cast<const double2 *>(r0 + col));
-                            if (is_de && col < d) vb = __ldg(reinterpret_cast<const double2 *>(r1 + col));
-                        } else {
-                            if (col < d) va.x = __ldg(r0 + col);
-                            if (col + 1 < d) va.y = __ldg(r0 + col + 1);
-                            if (is_de && col < d) vb.x = __ldg(r1 + col);
-                            if (is_de && col + 1 < d) vb.y = __ldg(r1 + col + 1);
-                        }
-                        stp[nt][0] = sc * (va.x - vb.x);
-                        stp[nt][1] = sc * (va.y - vb.y);
-                    } else {
-                        const double2 z = *reinterpret_cast<const double2 *>(zq + cl * ld + col);
-                        stp[nt][0] = z.x;
-                        stp[nt][1] = z.y;
-                    }
+                    const double2 z = *reinterpret_cast<const double2 *>(zq + cl * ld + 8 * nt + 2 * t);
+                    stp[nt][0] = mult * z.x;
+                    stp[nt][1] = mult * z.y;
                 }
             }
             double q[NT][2], dv[NT][2];
