@@ -15,12 +15,13 @@ Differences a reference user should know:
   or plain callables (evaluated on the host once per iteration, as are custom Python jumps);
 * random numbers come from a counter-based Philox stream keyed by ``seed`` instead of PCG64, so
   runs agree with the reference in distribution, not draw by draw;
-* the gradient proposals (NUTS / HMC / MALA, ref nutsjump.py) are not part of this engine.
+* the gradient proposals (NUTS / HMC / MALA, ref nutsjump.py) are host-side plugins built from the user's Python
+  gradients (``ptmcmcsampler_b200.nutsjump``): registered when both ``logl_grad`` and ``logp_grad`` are given, as in the
+  reference, and executed between the engine's propose / accept calls.
 """
 import os
 import sys
 import time
-import warnings
 
 import numpy as np
 
@@ -42,6 +43,23 @@ def shift_array(arr, num, fill_value=0.0):
     else:
         out[...] = arr
     return out
+
+
+def integrated_time(x, c=5.0):
+    """Integrated autocorrelation time of a 1-D series: tau = 1 + 2 sum_{t <= M} rho(t) with the smallest window
+    M >= c tau (Sokal's self-consistent rule, the estimate the ``acor`` package returns)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x)
+    x = x - x.mean()
+    if n < 4 or not np.any(x):
+        return 1.0
+    f = np.fft.rfft(x, 2 * int(2 ** np.ceil(np.log2(n))))
+    acf = np.fft.irfft(f * np.conjugate(f))[:n]
+    acf /= acf[0]
+    taus = 2.0 * np.cumsum(acf) - 1.0
+    window = np.arange(n) >= c * taus
+    m = int(np.argmax(window)) if window.any() else n - 1
+    return float(max(1.0, taus[m]))
 
 
 class _function_wrapper(object):
@@ -149,10 +167,11 @@ class PTSampler(object):
         self._dev_logp = logp if isinstance(logp, DeviceLogPrior) else None
         self.logl = logl if self._dev_logl is not None else _function_wrapper(logl, loglargs, loglkwargs)
         self.logp = logp if self._dev_logp is not None else _function_wrapper(logp, logpargs, logpkwargs)
+        # gradient proposals need both gradients, as in the reference (ref :110-115)
+        self.logl_grad = self.logp_grad = None
         if logl_grad is not None and logp_grad is not None:
-            warnings.warn("gradient proposals (NUTS/HMC/MALA) are outside this engine; logl_grad/logp_grad are ignored")
-        self.logl_grad = None
-        self.logp_grad = None
+            self.logl_grad = _function_wrapper(logl_grad, loglargs, loglkwargs)
+            self.logp_grad = _function_wrapper(logp_grad, logpargs, logpkwargs)
 
         self.outDir = outDir
         self.verbose = verbose
@@ -317,8 +336,6 @@ class PTSampler(object):
         self.covUpdate, self.burn, self.Tskip, self.thin, self.isave = int(covUpdate), int(burn), int(Tskip), int(thin), int(isave)
         self.SCAMweight, self.AMweight, self.DEweight = int(SCAMweight), int(AMweight), int(DEweight)
         self.Niter, self.neff, self.tstart = Niter, neff, 0
-        if neff:
-            raise NotImplementedError("neff needs the optional acor package and is outside this engine")
 
         N = int(maxIter / thin) + 1
         W = self.nwalkers
@@ -339,6 +356,18 @@ class PTSampler(object):
         self.swapProposed = 0
         self.nswap_accepted = 0
 
+        # gradient-based jumps first, as the reference registers them (ref :226-258); host-side plugins built from the
+        # user's gradient callables (nutsjump.py)
+        if self.logl_grad is not None and self.logp_grad is not None:
+            from . import nutsjump
+
+            gkw = dict(rng=self.stream, batched_gradients=self.vectorized)
+            cov0 = np.array(self.cov, dtype=np.float64)
+            self.addProposalToCycle(nutsjump.MALAJump(self.logl_grad, self.logp_grad, cov0, self.burn, **gkw), int(MALAweight))
+            self.addProposalToCycle(nutsjump.HMCJump(self.logl_grad, self.logp_grad, cov0, self.burn, stepsize=HMCstepsize,
+                                                     nminsteps=2, nmaxsteps=HMCsteps, **gkw), int(HMCweight))
+            self.addProposalToCycle(nutsjump.NUTSJump(self.logl_grad, self.logp_grad, cov0, self.burn, delta=0.6, **gkw),
+                                    int(NUTSweight))
         self.addProposalToCycle(self.covarianceJumpProposalSCAM, self.SCAMweight)
         self.addProposalToCycle(self.covarianceJumpProposalAM, self.AMweight)
         if len(self.propCycle) == 0:
@@ -371,6 +400,7 @@ class PTSampler(object):
         self.resumeLength = 0
         self.resumechain = None
         self._resumed_at = 0
+        self._last_neff = 0.0
         self._state_file = os.path.join(self.outDir, "engine_state.npy" if self._shard_world == 1
                                         else "engine_state_%d.npy" % self._shard_rank)
         self._resume_state = self.resume and os.path.isfile(self._state_file)
@@ -762,11 +792,17 @@ class PTSampler(object):
 
         iter = i0
         pending, slot = None, 0
+        stopped_early = False
         while iter < self.Niter:
             # advance to the next multiple of isave, the reference's write cadence (ref :338-339)
             nxt = min(self.Niter, (iter // self.isave + 1) * self.isave)
+            if self.neff:
+                nxt = min(nxt, (iter // 1000 + 1) * 1000)  # the effective-sample check runs every 1000 iterations (ref :511)
             self._advance(nxt - iter, iter)
             iter = nxt
+            if self.neff and iter % 1000 == 0 and iter > 2 * self.burn and iter < self.Niter and self._neff_reached(iter):
+                stopped_early = True   # ref :510-521
+                self.Niter = iter
             if iter % self.isave == 0 or iter >= self.Niter:
                 if self._async:
                     # the engine returns as soon as the segment is enqueued: snapshot what this write needs in stream
@@ -787,7 +823,20 @@ class PTSampler(object):
             sys.stderr.write("sample(): init+set_state %.1f, row0 %.1f, enqueue %.1f, last boundary %.1f, finish %.1f ms\n"
                              % tuple(1e3 * (b - a) for a, b in zip(_t[:-1], _t[1:])))
         if self.verbose:
-            print("\nRun Complete")
+            print("\nRun Complete with {0} effective samples".format(int(self._last_neff)) if stopped_early
+                  else "\nRun Complete")
+
+    def _neff_reached(self, iter):
+        """Effective number of samples of walker 0's T=1 chain past burn-in (ref :510-521).  The reference uses the optional
+        ``acor`` C extension; the same estimate (integrated autocorrelation time, self-consistent window) is computed here
+        with numpy, on the thinned rows, in units of iterations."""
+        self._pull_rows()
+        r0, r1 = self.burn // self.thin, min(iter // self.thin, self._rows_pulled)
+        if r1 - r0 < 16:
+            return False
+        tau = max(integrated_time(self._chain[r0:r1, k]) for k in range(self.ndim)) * self.thin
+        self._last_neff = iter / max(1.0, tau)
+        return int(self._last_neff) >= self.neff
 
     def _resume(self, x0):
         """Bring the engine to the iteration a previous run stopped at; returns that iteration."""
