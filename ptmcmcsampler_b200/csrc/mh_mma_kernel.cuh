@@ -267,58 +267,70 @@ __global__ void __launch_bounds__(MMA_THREADS, MINB) mh_mma_kernel(const __grid_
 
         // ================= phase R: every draw after word 1, as evenly spread tasks
         {
-            // task order: the gathers first, one task per (DE or SCAM chain, 8 columns) -- DE: B[mm] - B[nn], SCAM: coef * row k
-            // of the transposed factor -- into the chain's zq row (every load of the block in flight at once, their latency
-            // hidden by the AM tasks that follow); then the AM (chain, Philox block) pairs
-            const int tG = (nD + nS) * NT;
-            for (int q = tid; q < tG; q += MMA_THREADS) {
-                const int ci = q % (nD + nS), seg = q / (nD + nS);
-                const bool de = ci < nD;
-                const int cl = de ? s_list[2 * nc + ci] : s_list[nc + ci - nD];
-                const double *bm = (de ? p.de : a.Ut) + s_rowm[cl], *bn = p.de + (de ? s_rown[cl] : 0ull);
-                const double coef = de ? 1.0 : s_sca[cl];
-                const int col = 8 * seg;
-                double *dst = zq + cl * ld + col;
-                if ((d & 1) == 0) {  // rows are 16-byte aligned
+            // One gather task per (DE or SCAM chain, 8 columns) -- DE: B[mm] - B[nn], SCAM: coef * row k of the transposed
+            // factor -- into the chain's zq row, and one task per AM (chain, Philox block) pair.  A thread ISSUES the loads of
+            // its r-th gather task, runs its r-th AM task (normals from one Philox block), and only then consumes the loads:
+            // the gather latency (L2 after the prefetch of phase A) is spent on the draw arithmetic.
+            const int nG = nD + nS, tG = nG * NT, tA = nA * am_tasks;
+            const bool vec = (d & 1) == 0;  // rows are 16-byte aligned
+            for (int q = tid; q < tG || q < tA; q += MMA_THREADS) {
+                const bool hg = q < tG, ha = q < tA;
+                double2 vm[4], vn[4];
+                double coef = 1.0;
+                double *dst = zq;
+                int col = 0;
+                if (hg) {
+                    const int ci = q % nG, seg = q / nG;
+                    const bool de = ci < nD;
+                    const int cl = de ? s_list[2 * nc + ci] : s_list[nc + ci - nD];
+                    const double *bm = (de ? p.de : a.Ut) + s_rowm[cl], *bn = p.de + (de ? s_rown[cl] : 0ull);
+                    coef = de ? 1.0 : s_sca[cl];
+                    col = 8 * seg;
+                    dst = zq + cl * ld + col;
 #pragma unroll
-                    for (int k = 0; k < 8; k += 2) {
-                        double2 v = make_double2(0.0, 0.0);
-                        if (col + k < d) {
-                            const double2 vm = __ldg(reinterpret_cast<const double2 *>(bm + col + k));
-                            double2 vn = make_double2(0.0, 0.0);
-                            if (de) vn = __ldg(reinterpret_cast<const double2 *>(bn + col + k));
-                            v = make_double2(coef * (vm.x - vn.x), coef * (vm.y - vn.y));
+                    for (int k = 0; k < 4; ++k) {
+                        vm[k] = vn[k] = make_double2(0.0, 0.0);
+                        const int c = col + 2 * k;
+                        if (vec) {
+                            if (c < d) {
+                                vm[k] = __ldg(reinterpret_cast<const double2 *>(bm + c));
+                                if (de) vn[k] = __ldg(reinterpret_cast<const double2 *>(bn + c));
+                            }
+                        } else {
+                            if (c < d) vm[k].x = __ldg(bm + c);
+                            if (c + 1 < d) vm[k].y = __ldg(bm + c + 1);
+                            if (de && c < d) vn[k].x = __ldg(bn + c);
+                            if (de && c + 1 < d) vn[k].y = __ldg(bn + c + 1);
                         }
-                        *reinterpret_cast<double2 *>(dst + k) = v;
                     }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        dst[k] = (col + k < d) ? coef * (__ldg(bm + col + k) - (de ? __ldg(bn + col + k) : 0.0)) : 0.0;
                 }
-            }
-            const int tA = nA * am_tasks;
-            for (int q = tid; q < tA; q += MMA_THREADS) {
-                // AM (ref :897-930): word 2 = prob, 3 + j = normal pair j, 3 + npairs = accept u
-                const int ai = q % nA, b = 1 + q / nA;
-                const int cl = s_list[ai];
-                const uint4 blk = philox4x32_10(p, (uint32_t)it, (PURPOSE_MH << 24) | (uint32_t)b,
-                                                (uint32_t)(p.walker_offset + s_cw[cl]), (uint32_t)(p.temp_offset + s_ct[cl]));
+                if (ha) {
+                    // AM (ref :897-930): word 2 = prob, 3 + j = normal pair j, 3 + npairs = accept u
+                    const int ai = q % nA, b = 1 + q / nA;
+                    const int cl = s_list[ai];
+                    const uint4 blk = philox4x32_10(p, (uint32_t)it, (PURPOSE_MH << 24) | (uint32_t)b,
+                                                    (uint32_t)(p.walker_offset + s_cw[cl]), (uint32_t)(p.temp_offset + s_ct[cl]));
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int wi = 2 * b + h;
-                    const uint64_t word = h ? ((uint64_t)blk.z | ((uint64_t)blk.w << 32)) : ((uint64_t)blk.x | ((uint64_t)blk.y << 32));
-                    if (wi == 2) {
-                        s_sca[cl] = 2.4 / sqrt(2.0 * d) * cov_jump_scale(word_to_unit(word), s_temp[cl]);
-                    } else if (wi < uword) {
-                        double z0, z1;
-                        word_to_normals(word, z0, z1);
-                        const int j = 2 * (wi - 3);
-                        zq[cl * ld + j] = z0;
-                        if (j + 1 < KP) zq[cl * ld + j + 1] = z1;
-                    } else if (wi == uword) {
-                        s_uword[cl] = word;
+                    for (int h = 0; h < 2; ++h) {
+                        const int wi = 2 * b + h;
+                        const uint64_t word = h ? ((uint64_t)blk.z | ((uint64_t)blk.w << 32)) : ((uint64_t)blk.x | ((uint64_t)blk.y << 32));
+                        if (wi == 2) {
+                            s_sca[cl] = 2.4 / sqrt(2.0 * d) * cov_jump_scale(word_to_unit(word), s_temp[cl]);
+                        } else if (wi < uword) {
+                            double z0, z1;
+                            word_to_normals(word, z0, z1);
+                            const int j = 2 * (wi - 3);
+                            zq[cl * ld + j] = z0;
+                            if (j + 1 < KP) zq[cl * ld + j + 1] = z1;
+                        } else if (wi == uword) {
+                            s_uword[cl] = word;
+                        }
                     }
+                }
+                if (hg) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        *reinterpret_cast<double2 *>(dst + 2 * k) = make_double2(coef * (vm[k].x - vn[k].x), coef * (vm[k].y - vn[k].y));
                 }
             }
         }
