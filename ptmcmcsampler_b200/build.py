@@ -54,6 +54,7 @@ def build(force=False, verbose=False, all_cfgs=None):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DPTMCMC_ALL_SORT_CFGS"] if all_cfgs else [])
+    flags += os.environ.get("PTMCMC_NVCC_EXTRA", "").split()  # development aid, e.g. -DPTMCMC_MMA_CLOCKS
     hdrs = headers() + [os.path.abspath(__file__)]
 
     def compile_one(src):

@@ -258,7 +258,7 @@ bool fast_reg_path(const Engine *e) { return e->identity_group && e->d <= MAX_RE
 cudaError_t build_u_frags(Engine *e)
 {
     if (!e->mma_ok) return cudaSuccess;
-    cudaError_t st = launch_frag_build(e->d_U, e->d, e->mma.nt, 1, e->d_Uf, e->stream);
+    cudaError_t st = launch_frag_build(e->d_U, e->d, e->mma.nt, 1, 0, e->d_Uf, e->stream);
     if (st == cudaSuccess) st = launch_transpose(e->d_U, e->d, e->d_Ut, e->stream);
     e->tm.launches[PTMCMC_K_ADAPT] += 2;
     return st;
@@ -730,15 +730,6 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     e->mma_ok = cfg->logl_kind == PTMCMC_LOGL_GAUSSIAN && e->identity_group && e->mma.nt > 0 &&
                 (cfg->logp_kind == PTMCMC_LOGP_UNIFORM || cfg->logp_kind == PTMCMC_LOGP_FLAT);
     if (e->mma_ok) {
-        mma_geometry(e->mma, 0);
-        e->mma_ok = e->mma.nt > 0;
-    }
-    if (e->mma_ok) {
-        const size_t nf = (size_t)e->mma.nt * e->mma.nt * 64;
-        CUDA_TRY(nullptr, dalloc(&e->d_Uf, nf));
-        CUDA_TRY(nullptr, dalloc(&e->d_Pf, nf));
-        CUDA_TRY(nullptr, dalloc(&e->d_gPfull, (size_t)d * d));
-        CUDA_TRY(nullptr, dalloc(&e->d_Ut, (size_t)d * d));
         const double *A = cfg->logl_params + d;
         std::vector<double> Pn((size_t)d * d), Lc((size_t)d * d, 0.0);
         for (int i = 0; i < d; ++i)
@@ -761,8 +752,18 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
         }
         e->mma.tri = spd;
         if (spd) Pn = Lc;
-        CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_gPfull, Pn.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice, e->stream));
-        CUDA_TRY(nullptr, launch_frag_build(e->d_gPfull, d, e->mma.nt, 0, e->d_Pf, e->stream));
+        mma_geometry(e->mma, 0);
+        e->mma_ok = e->mma.nt > 0;
+        if (e->mma_ok) {
+            const size_t nf = (size_t)e->mma.nt * e->mma.nt * 64;
+            CUDA_TRY(nullptr, dalloc(&e->d_Uf, nf));
+            CUDA_TRY(nullptr, dalloc(&e->d_Pf, nf));
+            CUDA_TRY(nullptr, dalloc(&e->d_gPfull, (size_t)d * d));
+            CUDA_TRY(nullptr, dalloc(&e->d_Ut, (size_t)d * d));
+            CUDA_TRY(nullptr, cudaMemcpy(e->d_gPfull, Pn.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice));
+            CUDA_TRY(nullptr, launch_frag_build(e->d_gPfull, d, e->mma.nt, 0, mma_pf_tiles(e->mma) != e->mma.nt * e->mma.nt,
+                                                e->d_Pf, e->stream));
+        }
     }
     const double t_alloc = now();
     // initial factor (ref :138-145)
@@ -1771,7 +1772,8 @@ const char *ptmcmc_mh_kernel_name(ptmcmc_engine *h)
     if (!e) return "";
     if (use_mma(e)) {
         static thread_local char buf[64];
-        snprintf(buf, sizeof buf, "mh_mma_kernel<%d> (%d chains per block)", e->mma.nt, e->mma.nc);
+        snprintf(buf, sizeof buf, "%s<%d> (%d chains per block)", e->mma.split ? "mh_mma_split_kernel" : "mh_mma_kernel", e->mma.nt,
+                 e->mma.nc);
         return buf;
     }
     if (fast_reg_path(e) && e->mh_variant != 2) return sorted_kernel_name(e->d, e->sorted);

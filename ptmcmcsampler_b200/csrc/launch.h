@@ -30,13 +30,15 @@ const char *sorted_kernel_name(int d, const SortedGeom &g);
 struct MmaGeom {
     int nt;        // n-tiles (ndim <= 8 nt), 0 = not available
     int nc, ld, smem;
-    bool tri;
+    bool split;    // ndim > 32: mh_mma_split_kernel (two blocks of <= 32 chains per SM); set by mma_geometry
+    bool tri;      // the form is held as a Cholesky factor (set before mma_geometry: the split kernels pack its tiles)
 };
 int mma_pick_nt(int d);
+int mma_pf_tiles(const MmaGeom &g);
 void mma_geometry(MmaGeom &g, int nc_request);
 cudaError_t launch_mma(const DevParams &p, const MmaGeom &g, const double *Uf, const double *Pf, const double *Ut,
                        int device, cudaStream_t stream);
-cudaError_t launch_frag_build(const double *src, int d, int nt, int transpose, double *out, cudaStream_t stream);
+cudaError_t launch_frag_build(const double *src, int d, int nt, int transpose, int packed, double *out, cudaStream_t stream);
 cudaError_t launch_transpose(const double *src, int d, double *dst, cudaStream_t stream);
 
 }  // namespace ptm

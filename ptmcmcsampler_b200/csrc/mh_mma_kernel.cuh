@@ -34,15 +34,37 @@ namespace ptm {
 constexpr int MMA_THREADS = 256;
 constexpr int MMA_WARPS = MMA_THREADS / 32;
 
+// -DPTMCMC_MMA_CLOCKS: thread 0 of every block adds the clocks between the block barriers to g_mma_clk[phase]
+// (development aid, read with ptmcmc_debug_mma_clocks; the barrier release times are the same for every warp)
+#ifdef PTMCMC_MMA_CLOCKS
+__device__ unsigned long long g_mma_clk[8];
+#define PTM_CLK(i)                                                         \
+    if (threadIdx.x == 0) {                                                \
+        const long long now_ = clock64();                                  \
+        atomicAdd(&g_mma_clk[i], (unsigned long long)(now_ - clk_prev_));  \
+        clk_prev_ = now_;                                                  \
+    }
+#else
+#define PTM_CLK(i)
+#endif
+
 // Fragment-order image of the d x d matrix M used as the B operand of  Y[c][n] = sum_k A[c][k] M(k, n):
-//   out[((kk*NT + nt)*32 + lane)*2 + e] = M(8kk + 2(lane&3) + e, 8nt + (lane>>2)),  zero padded.
+//   out[((tile(kk, nt))*32 + lane)*2 + e] = M(8kk + 2(lane&3) + e, 8nt + (lane>>2)),  zero padded,
+// tile(kk, nt) = kk*NT + nt, or kk(kk+1)/2 + nt over the tiles kk >= nt only when `packed` (a lower-triangular M).
 // transpose: M(k, n) = src[n*d + k] (the AM mat-vec uses U^T), else src[k*d + n].
-__global__ void frag_build_kernel(const double *src, int d, int NT, int transpose, double *out)
+__host__ __device__ inline int mma_tiles(int NT, bool packed) { return packed ? NT * (NT + 1) / 2 : NT * NT; }
+
+__global__ void frag_build_kernel(const double *src, int d, int NT, int transpose, int packed, double *out)
 {
-    const int total = NT * NT * 64;
+    const int total = mma_tiles(NT, packed != 0) * 64;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int e = idx & 1, lane = (idx >> 1) & 31, tile = idx >> 6;
-        const int nt = tile % NT, kk = tile / NT;
+        int nt = tile % NT, kk = tile / NT;
+        if (packed) {
+            kk = 0;
+            while ((kk + 1) * (kk + 2) / 2 <= tile) ++kk;
+            nt = tile - kk * (kk + 1) / 2;
+        }
         const int k = 8 * kk + 2 * (lane & 3) + e, n = 8 * nt + (lane >> 2);
         double v = 0.0;
         if (k < d && n < d) v = transpose ? src[n * d + k] : src[k * d + n];
@@ -52,7 +74,7 @@ __global__ void frag_build_kernel(const double *src, int d, int NT, int transpos
 
 // shared-memory carve-up (all offsets in bytes, 16-byte aligned); see mma_smem_bytes()
 struct MmaLayout {
-    int xs, zq, pf, uf, ss, mu, lo, hi, lnl, lp, temp, beta, sca, logu, rowm, rown, ct, cw, cnt, list, jt, count, total;
+    int xs, zq, pf, uf, ss, mu, lo, hi, lnl, lp, temp, beta, sca, logu, rowm, rown, part, ct, cw, cnt, list, jt, count, total;
     __host__ __device__ int take(int bytes)
     {
         const int at = total;
@@ -61,23 +83,25 @@ struct MmaLayout {
     }
 };
 
-__host__ __device__ inline MmaLayout mma_layout(int NT, int nc, int ld, bool usmem)
+// pf_tiles: 8x8 tiles of the form's fragment image held in shared memory (mma_tiles); the per-kind lists and jump ids
+// are double-buffered (the split kernel draws the next iteration's jump kinds while the current one finishes)
+__host__ __device__ inline MmaLayout mma_layout(int NT, int nc, int ld, bool usmem, int pf_tiles)
 {
     MmaLayout L;
     L.total = 0;
     const int KP = 8 * NT;
     L.xs = L.take(nc * ld * 8);
     L.zq = L.take(nc * ld * 8);
-    L.pf = L.take(NT * NT * 64 * 8);
+    L.pf = L.take(pf_tiles * 64 * 8);
     L.uf = L.take(usmem ? NT * NT * 64 * 8 : 0);
     L.ss = L.take(KP * 8); L.mu = L.take(KP * 8); L.lo = L.take(KP * 8); L.hi = L.take(KP * 8);
     L.lnl = L.take(nc * 8); L.lp = L.take(nc * 8); L.temp = L.take(nc * 8); L.beta = L.take(nc * 8);
     L.sca = L.take(nc * 8); L.logu = L.take(nc * 8);
-    L.rowm = L.take(nc * 8); L.rown = L.take(nc * 8);
+    L.rowm = L.take(nc * 8); L.rown = L.take(nc * 8); L.part = L.take(nc * 8);
     L.ct = L.take(nc * 4); L.cw = L.take(nc * 4);
     L.cnt = L.take(6 * nc * 4);
-    L.list = L.take(3 * nc * 2);
-    L.jt = L.take(nc);
+    L.list = L.take(2 * 3 * nc * 2);
+    L.jt = L.take(2 * nc);
     L.count = L.take(8 * 4);
     return L;
 }
@@ -96,6 +120,7 @@ struct MmaArgs {
     int ld;               // row stride of the per-chain shared-memory rows (doubles, = 8 mod 16)
     int tri;              // 1: Pf holds the Cholesky factor L of sym(icov) (lower triangular) scaled by 1/sqrt(2):
                           //    lnl = offset - |d^T L / sqrt(2)|^2, and the all-zero tiles kk < nt are skipped
+    int pf_tiles;         // tiles of Pf: NT*NT, or NT(NT+1)/2 in packed lower-triangular order (split kernel with tri)
     MmaLayout L;          // computed on the host: the offsets are then plain constant-bank operands
 };
 

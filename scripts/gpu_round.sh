@@ -12,7 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 2 --warmup 3 --no-side > gpurun_out/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:mh_sorted_kernel -s 12 -c 1 -f -o gpurun_out/prof_mh_r02 \
     python scripts/quick_bench.py 20 8192 32 1000 1 > gpurun_out/prof_mh_r02.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:mh_mma_kernel -s 12 -c 1 -f -o gpurun_out/prof_mma_c3_r02 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:mh_mma_split_kernel -s 12 -c 1 -f -o gpurun_out/prof_mma_c3_r02 \
     python scripts/config_bench.py c3 200 1 > gpurun_out/prof_mma_c3_r02.log 2>&1
 ls -la gpurun_out
 tail -n 3 gpurun_out/pytest_gpu.log; tail -n 2 gpurun_out/smoke.log

@@ -77,7 +77,7 @@ def test_c3_full_size_matches_oracle():
     ladder = np.minimum((1 + np.sqrt(2.0 / d)) ** np.arange(T), 1e30)
     o, g = make_pair(d, W, T, np.diag(0.01 * s * s), seed=7, target=tgt, cov_update=100, burn=100, tskip=50, thin=10,
                      niter=niter, record_hot=False, ladder=ladder, nthreads=os.cpu_count() or 4)
-    assert "mh_mma_kernel" in g.mh_kernel_name
+    assert "mh_mma_split_kernel" in g.mh_kernel_name
     x0 = np.random.default_rng(1).standard_normal((T, W, d)) * s
     compare_full(o, g, x0, niter, 50, T, 1e-8)
 
@@ -135,7 +135,7 @@ def test_d100_reaches_target_covariance():
                      logl_params=np.concatenate([np.zeros(d), np.linalg.inv(cov).ravel(), [0.0]]),
                      logp_params=np.concatenate([-500 * np.ones(d), 500 * np.ones(d), [0.0, 1.0]]),
                      record_rows=niter // 10 + 2, record_hot=True)
-    assert "mh_mma_kernel" in e.mh_kernel_name
+    assert "mh_mma_split_kernel" in e.mh_kernel_name
     e.set_state(np.random.default_rng(1).standard_normal((T, W, d)) * s)
     e.run(niter)
     ch = e.chain()[0]

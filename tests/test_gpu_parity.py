@@ -149,6 +149,23 @@ def test_tensor_core_kernel_matches_oracle(d, W, T):
     compare(o, g, x0, niter, tskip, T, chunks=(0.33, 0.7, 1.0), ftol=1e-8 if d > 32 else FTOL)
 
 
+@pytest.mark.parametrize("d,W,T", [(100, 24, 2), (40, 50, 1), (128, 9, 2)])
+def test_tensor_core_split_kernel_symmetric_form_and_trace(d, W, T, monkeypatch):
+    """ndim > 32 (mh_mma_split_kernel) with the form kept symmetric (what a matrix that is not positive definite gets)
+    instead of the packed Cholesky factor, the jump trace on, and the one-block-per-SM kernel it replaced (A/B switch)."""
+    niter, tskip = 120, 10
+    cov0 = np.diag(0.01 * (1.0 + np.arange(d)))
+    x0 = np.random.default_rng(d).uniform(0, 10, (T, W, d))
+    for env in ({"PTMCMC_MMA_FULL": "1"}, {"PTMCMC_MMA_SPLIT": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        o, g = make_pair(d, W, T, cov0, seed=11 + d, target=gaussian_target(d, d), niter=niter, tskip=tskip, variant=3)
+        assert ("mh_mma_split_kernel" in g.mh_kernel_name) == ("PTMCMC_MMA_FULL" in env)
+        compare(o, g, x0, niter, tskip, T, chunks=(0.5, 1.0), ftol=1e-8)
+        for k in env:
+            monkeypatch.delenv(k)
+
+
 def test_tensor_core_kernel_truncated_box_and_outside_start():
     d, W, T, niter = 6, 40, 3, 250
     tgt = gaussian_target(d, 3, lo=3.0, hi=7.0)
