@@ -34,6 +34,15 @@ __device__ __forceinline__ bool in_box(double v, double lo, double hi, int inclu
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
+// 16-byte read-only load that does not allocate in L1: streams (history rows, fragment images larger than L1) must not
+// evict what lives there (the kernel's local-memory lines, small tables)
+__device__ __forceinline__ double2 ldg_stream(const double2 *ptr)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(ptr));
+    return v;
+}
+
 // physical row of logical DE-history row r (ring with head slot); 32-bit arithmetic when it fits
 __device__ __forceinline__ unsigned long long de_row_offset(unsigned long long r, unsigned long long bufsize, int W,
                                                             long long burn, long long head)

@@ -120,9 +120,9 @@ cudaError_t launch_transpose(const double *src, int d, double *dst, cudaStream_t
 extern "C" void ptmcmc_debug_mma_clocks(unsigned long long *out, int reset)
 {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, ptm::g_mma_clk, sizeof(unsigned long long) * 8);
+    cudaMemcpyFromSymbol(out, ptm::g_mma_clk, sizeof(unsigned long long) * 32);
     if (reset) {
-        unsigned long long z[8] = {};
+        unsigned long long z[32] = {};
         cudaMemcpyToSymbol(ptm::g_mma_clk, z, sizeof z);
     }
 }

@@ -37,15 +37,33 @@ constexpr int MMA_WARPS = MMA_THREADS / 32;
 // -DPTMCMC_MMA_CLOCKS: thread 0 of every block adds the clocks between the block barriers to g_mma_clk[phase]
 // (development aid, read with ptmcmc_debug_mma_clocks; the barrier release times are the same for every warp)
 #ifdef PTMCMC_MMA_CLOCKS
-__device__ unsigned long long g_mma_clk[8];
+__device__ unsigned long long g_mma_clk[32];
 #define PTM_CLK(i)                                                         \
     if (threadIdx.x == 0) {                                                \
         const long long now_ = clock64();                                  \
         atomicAdd(&g_mma_clk[i], (unsigned long long)(now_ - clk_prev_));  \
         clk_prev_ = now_;                                                  \
     }
+// finer marks inside a phase, by one chosen thread: PTM_SUB0 starts, PTM_SUB(i) adds the clocks since the last mark
+#define PTM_SUB0 long long sub_prev_ = clock64();
+#define PTM_SUB(i, cond)                                                   \
+    if (cond) {                                                            \
+        const long long now_ = clock64();                                  \
+        atomicAdd(&g_mma_clk[i], (unsigned long long)(now_ - sub_prev_));  \
+        sub_prev_ = now_;                                                  \
+    }
+#define PTM_SUB_RESTART sub_prev_ = clock64();
+// per-warp arrival at the end of a phase: PTM_WARP0 after the barrier that starts it, PTM_WARP(base) before the one ending it
+#define PTM_WARP0 const long long warp_t0_ = clock64();
+#define PTM_WARP(base) \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_mma_clk[(base) + (threadIdx.x >> 5)], (unsigned long long)(clock64() - warp_t0_));
 #else
+#define PTM_WARP0
+#define PTM_WARP(base)
 #define PTM_CLK(i)
+#define PTM_SUB0
+#define PTM_SUB(i, cond)
+#define PTM_SUB_RESTART
 #endif
 
 // Fragment-order image of the d x d matrix M used as the B operand of  Y[c][n] = sum_k A[c][k] M(k, n):
@@ -84,7 +102,7 @@ struct MmaLayout {
 };
 
 // pf_tiles: 8x8 tiles of the form's fragment image held in shared memory (mma_tiles); the per-kind lists and jump ids
-// are double-buffered (the split kernel draws the next iteration's jump kinds while the current one finishes)
+// are triple-buffered (the split kernel draws the jump kinds two iterations ahead)
 __host__ __device__ inline MmaLayout mma_layout(int NT, int nc, int ld, bool usmem, int pf_tiles)
 {
     MmaLayout L;
@@ -96,13 +114,13 @@ __host__ __device__ inline MmaLayout mma_layout(int NT, int nc, int ld, bool usm
     L.uf = L.take(usmem ? NT * NT * 64 * 8 : 0);
     L.ss = L.take(KP * 8); L.mu = L.take(KP * 8); L.lo = L.take(KP * 8); L.hi = L.take(KP * 8);
     L.lnl = L.take(nc * 8); L.lp = L.take(nc * 8); L.temp = L.take(nc * 8); L.beta = L.take(nc * 8);
-    L.sca = L.take(nc * 8); L.logu = L.take(nc * 8);
-    L.rowm = L.take(nc * 8); L.rown = L.take(nc * 8); L.part = L.take(nc * 8);
+    L.sca = L.take(2 * nc * 8); L.logu = L.take(2 * nc * 8);  // [2]: the split kernel draws them an iteration ahead
+    L.rowm = L.take(2 * nc * 8); L.rown = L.take(2 * nc * 8); L.part = L.take(nc * 8);
     L.ct = L.take(nc * 4); L.cw = L.take(nc * 4);
     L.cnt = L.take(6 * nc * 4);
-    L.list = L.take(2 * 3 * nc * 2);
-    L.jt = L.take(2 * nc);
-    L.count = L.take(8 * 4);
+    L.list = L.take(3 * 3 * nc * 2);
+    L.jt = L.take(3 * nc);
+    L.count = L.take(16 * 4);
     return L;
 }
 

@@ -9,19 +9,23 @@
 //   * two blocks of <= 32 chains per SM at <= 128 registers: one block's draw phases run under the other's tensor phases.
 //     Shared memory per block: the chains' rows and the form's fragment image (packed lower triangle of the Cholesky
 //     factor when the form is positive definite); the factor's image is read through L1 / L2;
-//   * the jump kinds of iteration it+1 are drawn (state-free, counter-based) by an otherwise idle warp while iteration it
-//     finishes; the scalar draws of the DE and of the SCAM steps run on two different warps, branch-free, with their Philox
-//     blocks generated side by side, while the other six warps draw the AM normals;
-//   * phase P: items (AM tile, <= 4 n-tiles) over all warps, the factor's fragments prefetched PD k-tiles ahead;
+//   * everything random about a step except the AM normals is state-free and small, so it is drawn one iteration AHEAD by
+//     warps that are idle while the others run the Hastings tests: the jump kinds and per-kind lists of iteration it+1
+//     (one warp), then its DE chains' history rows / scales / accept words, the rows prefetched into L2 a whole
+//     iteration before the gather (same warp), and its SCAM chains' component / coefficient / accept word (another warp),
+//     each branch-free with its Philox blocks generated side by side.  Lists, jump ids and these scalars are
+//     double-buffered by the parity of the iteration;
+//   * phase R is then evenly spread tasks only: gathers (loads issued first) and (AM chain, Philox block) normals;
+//   * phase P: every warp takes <= 2 n-tiles of ALL AM tiles, so each fragment of the factor is fetched once per block
+//     and feeds up to 16 DMMAs; fragments are prefetched PD k-tiles ahead;
 //   * phase L: two warps per 8-chain tile, each a balanced part of the (triangular) quadratic form.
 //
-// Per iteration, per block (6 block barriers):
-//   R1  warp 0: buffers / record of iteration it-1, then the DE chains' scalar draws (history rows prefetched into L2);
-//       warp 1: the SCAM chains' scalar draws; warps 2..7: (AM chain, Philox block) tasks -> normals into zq
-//   R2  gather tasks (DE or SCAM chain, 8 columns) -> the step into the chain's zq row
-//   P   zq <- U (z * cd * sqrt(S)) for the AM chains, 8 at a time, by DMMA
-//   L   per (tile, half): proposal, box test, part of the quadratic form by DMMA; then per tile: Hastings test, state update,
-//       while the last warp draws the jump kinds of iteration it+1 and sorts the chains into per-kind lists
+// Per iteration, per block (5 block barriers):
+//   R   warp 0: buffers / record of iteration it-1; all: gather tasks (DE or SCAM chain, 8 columns) -> the step into the
+//       chain's zq row, and (AM chain, Philox block) tasks -> normals into zq
+//   P   zq <- U (z * cd * sqrt(S)) for the AM chains by DMMA (results written after a barrier)
+//   L   per (tile, half): proposal, box test, part of the quadratic form by DMMA; barrier; per tile: Hastings test, state
+//       update, while warps 7 and 6 make the draws of iteration it+1
 #pragma once
 #include "mh_mma_kernel.cuh"
 
@@ -112,17 +116,18 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
     double *s_lp = reinterpret_cast<double *>(smem_raw + L.lp);
     double *s_temp = reinterpret_cast<double *>(smem_raw + L.temp);
     double *s_beta = reinterpret_cast<double *>(smem_raw + L.beta);
-    double *s_sca = reinterpret_cast<double *>(smem_raw + L.sca);    // AM: cd; SCAM: coefficient; DE: scale
-    unsigned long long *s_rowm = reinterpret_cast<unsigned long long *>(smem_raw + L.rowm);  // DE row offsets;
-    unsigned long long *s_rown = reinterpret_cast<unsigned long long *>(smem_raw + L.rown);  // SCAM: rowm = k d
-    unsigned long long *s_uword = reinterpret_cast<unsigned long long *>(smem_raw + L.logu);  // accept-uniform word
+    // per-chain scalars of a step, [2][nc] by the parity of the iteration
+    double *s_sca2 = reinterpret_cast<double *>(smem_raw + L.sca);    // AM: cd; SCAM: coefficient; DE: scale
+    unsigned long long *s_rowm2 = reinterpret_cast<unsigned long long *>(smem_raw + L.rowm);  // DE row offsets;
+    unsigned long long *s_rown2 = reinterpret_cast<unsigned long long *>(smem_raw + L.rown);  // SCAM: rowm = k d
+    unsigned long long *s_uword2 = reinterpret_cast<unsigned long long *>(smem_raw + L.logu);  // accept-uniform word
     double *s_part = reinterpret_cast<double *>(smem_raw + L.part);
     int *s_ct = reinterpret_cast<int *>(smem_raw + L.ct);
     int *s_cw = reinterpret_cast<int *>(smem_raw + L.cw);
     unsigned *s_cnt = reinterpret_cast<unsigned *>(smem_raw + L.cnt);
-    unsigned short *s_list2 = reinterpret_cast<unsigned short *>(smem_raw + L.list);  // [2][3][nc]
-    unsigned char *s_jt2 = smem_raw + L.jt;                                             // [2][nc]
-    int *s_count = reinterpret_cast<int *>(smem_raw + L.count);                         // [2][4]
+    unsigned short *s_list2 = reinterpret_cast<unsigned short *>(smem_raw + L.list);  // [3][3][nc], slot = iteration mod 3
+    unsigned char *s_jt2 = smem_raw + L.jt;                                             // [3][nc]
+    int *s_count = reinterpret_cast<int *>(smem_raw + L.count);                         // [3][4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = lane >> 2, t = lane & 3;
@@ -154,21 +159,17 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
         s_beta[tid] = 1.0 / tp;
         s_ct[tid] = tme;
         s_cw[tid] = wme;
-        s_jt2[tid] = s_jt2[nc + tid] = 0;
+        s_jt2[tid] = s_jt2[nc + tid] = s_jt2[2 * nc + tid] = 0;
 #pragma unroll
         for (int j = 0; j < 6; ++j) s_cnt[j * nc + tid] = 0;
     }
     const int inclusive = p.p_inclusive;
-    long long am_slot = p.it0 % p.cov_update, thin_ctr = p.it0 % p.thin, row = p.it0 / p.thin - p.rec_base;
-    const bool cold = have && tme == 0 && p.temp_offset == 0 && p.am != nullptr;
-    const bool recorded = have && tme < p.ntr;
     const int npairs = (d + 1) >> 1, uword = 3 + npairs, am_tasks = ((uword + 2) >> 1) - 1;
     const unsigned long long bufsize = (unsigned long long)p.burn * (unsigned long long)W;
     const int ntiles = nc >> 3;
 
     // jump kind of iteration `it` (ref :1058) for the chains of the block, by the lanes of ONE warp, and the per-kind lists
-    auto pick_kinds = [&](long long it) {
-        const int buf = (int)(it & 1);
+    auto pick_kinds = [&](long long it, int buf) {  // buf: list slot = it mod 3
         const bool mine = lane < nc && c0 + lane < TW;
         int kind = 3;
         if (mine) {
@@ -185,17 +186,76 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
             if (lane == 0) s_count[4 * buf + kk] = __popc(m);
         }
     };
+    // DE chains of iteration `it` (ref :955-976), one per lane: the two history rows (words 2, 3, redrawn while equal), prob,
+    // scale, accept uniform; the rows are prefetched into L2 for the gather tasks of phase R
+    auto draw_de = [&](long long it, int slot) {  // slot: list slot = it mod 3; the scalars go by the parity of it
+        const int buf = (int)(it & 1), nD = s_count[4 * slot + 2];
+        for (int i = lane; i < nD; i += 32) {
+            const int cl = s_list2[(slot * 3 + 2) * nc + i];
+            const Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + s_cw[cl]),
+                            (uint32_t)(p.temp_offset + s_ct[cl]));
+            const uint4 b1 = st.block(1), b2 = st.block(2), b3 = st.block(3);
+            const unsigned long long mm = word_to_int(lo_word(b1), bufsize);
+            unsigned long long nn = word_to_int(hi_word(b1), bufsize);
+            uint32_t j = 4;
+            auto word = [&](uint32_t jj) {
+                return jj == 4 ? lo_word(b2) : jj == 5 ? hi_word(b2) : jj == 6 ? lo_word(b3) : jj == 7 ? hi_word(b3) : stream_word(st, jj);
+            };
+            while (mm == nn) nn = word_to_int(word(j++), bufsize);
+            const unsigned long long om = de_row_offset(mm, bufsize, W, p.burn, p.de_head) * (unsigned long long)d;
+            const unsigned long long on = de_row_offset(nn, bufsize, W, p.burn, p.de_head) * (unsigned long long)d;
+            s_rowm2[buf * nc + cl] = om;
+            s_rown2[buf * nc + cl] = on;
+            for (int b = 0; b < 8 * d; b += 128) {
+                prefetch_l2(reinterpret_cast<const char *>(p.de + om) + b);
+                prefetch_l2(reinterpret_cast<const char *>(p.de + on) + b);
+            }
+            prefetch_l2(p.de + om + d - 1);
+            prefetch_l2(p.de + on + d - 1);
+            const double prob = word_to_unit(word(j++));
+            double scale = 1.0;
+            if (!(prob > 0.5)) scale = word_to_unit(word(j++)) * 2.4 / sqrt(2.0 * d) * sqrt(1.0 / s_beta[cl]);
+            s_sca2[buf * nc + cl] = scale;
+            s_uword2[buf * nc + cl] = word(j++);
+        }
+    };
+    // SCAM chains of iteration `it` (ref :839-873), one per lane: prob, k, normal, accept uniform = words 2..5; the step is
+    // coef * U[:, k] (ref :868-873)
+    auto draw_scam = [&](long long it, int slot) {
+        const int buf = (int)(it & 1), nS = s_count[4 * slot + 1];
+        for (int i = lane; i < nS; i += 32) {
+            const int cl = s_list2[(slot * 3 + 1) * nc + i];
+            const Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + s_cw[cl]),
+                            (uint32_t)(p.temp_offset + s_ct[cl]));
+            const uint4 b1 = st.block(1), b2 = st.block(2);
+            const double prob = word_to_unit(lo_word(b1));
+            const double scale = cov_jump_scale(prob, s_temp[cl]);
+            const int k = (int)word_to_int(hi_word(b1), (unsigned long long)d);
+            const double cd = 2.4 / sqrt(2.0) * scale;
+            double z0, z1;
+            word_to_normals(lo_word(b2), z0, z1);
+            s_sca2[buf * nc + cl] = z0 * cd * sSs[k];
+            s_rowm2[buf * nc + cl] = (unsigned long long)k * (unsigned long long)d;
+            s_uword2[buf * nc + cl] = hi_word(b2);
+        }
+    };
     // buffers / record of iteration ib (ref :627) for the chain of thread tid < nc
-    auto bookkeeping = [&](long long ib) {
-        if (have) {
-            if (p.trace && ib - 1 < p.trace_cap) p.trace[((size_t)(ib - 1) * T + tme) * W + wme] = s_jt2[(int)(ib & 1) * nc + tid];
+    // few blocks have anything to write: the first chain's rung decides for the block (chains are rung-major)
+    const bool bk_block = p.trace != nullptr || (int)(c0 / W) < max(p.ntr, (p.temp_offset == 0 && p.am != nullptr) ? 1 : 0);
+    auto bookkeeping = [&](long long ib, int slot) {
+        // nothing of this rare path stays in registers (or local memory) over the loop: the chain's coordinates come from
+        // shared memory, the ring slot and record row from the iteration number
+        if (bk_block && tid < nc && c0 + tid < TW) {
+            const int tb = s_ct[tid], wb = s_cw[tid];
+            if (p.trace && ib - 1 < p.trace_cap) p.trace[((size_t)(ib - 1) * T + tb) * W + wb] = s_jt2[slot * nc + tid];
             if (ib < p.it1 || p.tail) {
-                if (cold) {
-                    double *dst = p.am + (size_t)am_slot * d * W + wme;
+                if (tb == 0 && p.temp_offset == 0 && p.am != nullptr) {
+                    double *dst = p.am + (size_t)(ib % p.cov_update) * d * W + wb;
                     for (int k = 0; k < d; ++k) dst[(size_t)k * W] = xs[tid * ld + k];
                 }
-                if (recorded && thin_ctr == 0 && row >= 0 && row < p.rec_cap) {
-                    const size_t rr = ((size_t)row * p.ntr + tme) * W + wme;
+                const long long row = ib / p.thin - p.rec_base;
+                if (tb < p.ntr && ib % p.thin == 0 && row >= 0 && row < p.rec_cap) {
+                    const size_t rr = ((size_t)row * p.ntr + tb) * W + wb;
                     double *dst = p.rec_x + rr * d;
                     for (int k = 0; k < d; ++k) dst[k] = xs[tid * ld + k];
                     p.rec_lnl[rr] = s_lnl[tid];
@@ -203,197 +263,190 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
                 }
             }
         }
-        if (++am_slot == p.cov_update) am_slot = 0;
-        if (++thin_ctr == p.thin) { thin_ctr = 0; ++row; }
     };
 
+    // the draws run ahead of the steps: jump kinds and lists two iterations, the DE / SCAM scalars one
+    int l3 = (int)(p.it0 % 3);  // list slot of the current iteration
+    const auto next3 = [](int s) { return s == 2 ? 0 : s + 1; };
     __syncthreads();
-    if (warp == MMA_WARPS - 1 && p.it0 <= p.it1) pick_kinds(p.it0);
+    if (warp == MMA_WARPS - 1 && p.it0 <= p.it1) pick_kinds(p.it0, l3);
+    __syncthreads();
+    if (p.it0 <= p.it1) {
+        if (warp == MMA_WARPS - 1 && p.it0 < p.it1) pick_kinds(p.it0 + 1, next3(l3));
+        if (warp == MMA_WARPS - 2) draw_de(p.it0, l3);
+        if (warp == MMA_WARPS - 3) draw_scam(p.it0, l3);
+    }
     __syncthreads();
 #ifdef PTMCMC_MMA_CLOCKS
     long long clk_prev_ = clock64();
 #endif
 
-    for (long long it = p.it0; it <= p.it1; ++it) {
+    for (long long it = p.it0; it <= p.it1; ++it, l3 = next3(l3)) {
         const int buf = (int)(it & 1);
-        const unsigned short *s_list = s_list2 + buf * 3 * nc;
-        unsigned char *s_jt = s_jt2 + buf * nc;
-        const int nA = s_count[4 * buf], nS = s_count[4 * buf + 1], nD = s_count[4 * buf + 2];
+        const unsigned short *s_list = s_list2 + l3 * 3 * nc;
+        unsigned char *s_jt = s_jt2 + l3 * nc;
+        double *s_sca = s_sca2 + buf * nc;
+        const unsigned long long *s_rowm = s_rowm2 + buf * nc, *s_rown = s_rown2 + buf * nc;
+        unsigned long long *s_uword = s_uword2 + buf * nc;
+        const int nA = s_count[4 * l3], nS = s_count[4 * l3 + 1], nD = s_count[4 * l3 + 2];
 
-        // ================= phase R1: every scalar draw after the jump index
-        if (warp == 0) {
-            if (it > p.it0) bookkeeping(it - 1);
-            // DE (ref :955-976): the two history rows (words 2, 3, redrawn while equal), prob, scale, accept uniform;
-            // the rows are prefetched into L2 for the gather tasks of phase R2
-            for (int i = lane; i < nD; i += 32) {
-                const int cl = s_list[2 * nc + i];
-                const Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + s_cw[cl]),
-                                (uint32_t)(p.temp_offset + s_ct[cl]));
-                const uint4 b1 = st.block(1), b2 = st.block(2), b3 = st.block(3);
-                const unsigned long long mm = word_to_int(lo_word(b1), bufsize);
-                unsigned long long nn = word_to_int(hi_word(b1), bufsize);
-                uint32_t j = 4;
-                auto word = [&](uint32_t jj) {
-                    return jj == 4 ? lo_word(b2) : jj == 5 ? hi_word(b2) : jj == 6 ? lo_word(b3) : jj == 7 ? hi_word(b3) : stream_word(st, jj);
-                };
-                while (mm == nn) nn = word_to_int(word(j++), bufsize);
-                const unsigned long long om = de_row_offset(mm, bufsize, W, p.burn, p.de_head) * (unsigned long long)d;
-                const unsigned long long on = de_row_offset(nn, bufsize, W, p.burn, p.de_head) * (unsigned long long)d;
-                s_rowm[cl] = om;
-                s_rown[cl] = on;
-                for (int b = 0; b < 8 * d; b += 128) {
-                    prefetch_l2(reinterpret_cast<const char *>(p.de + om) + b);
-                    prefetch_l2(reinterpret_cast<const char *>(p.de + on) + b);
-                }
-                prefetch_l2(p.de + om + d - 1);
-                prefetch_l2(p.de + on + d - 1);
-                const double prob = word_to_unit(word(j++));
-                double scale = 1.0;
-                if (!(prob > 0.5)) scale = word_to_unit(word(j++)) * 2.4 / sqrt(2.0 * d) * sqrt(1.0 / s_beta[cl]);
-                s_sca[cl] = scale;
-                s_uword[cl] = word(j++);
-            }
-        } else if (warp == 1) {
-            // SCAM (ref :839-873): prob, k, normal, accept uniform = words 2..5; the step is coef * U[:, k] (ref :868-873)
-            for (int i = lane; i < nS; i += 32) {
-                const int cl = s_list[nc + i];
-                const Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + s_cw[cl]),
-                                (uint32_t)(p.temp_offset + s_ct[cl]));
-                const uint4 b1 = st.block(1), b2 = st.block(2);
-                const double prob = word_to_unit(lo_word(b1));
-                const double scale = cov_jump_scale(prob, s_temp[cl]);
-                const int k = (int)word_to_int(hi_word(b1), (unsigned long long)d);
-                const double cd = 2.4 / sqrt(2.0) * scale;
-                double z0, z1;
-                word_to_normals(lo_word(b2), z0, z1);
-                s_sca[cl] = z0 * cd * sSs[k];
-                s_rowm[cl] = (unsigned long long)k * (unsigned long long)d;
-                s_uword[cl] = hi_word(b2);
-            }
-        } else {
-            // AM (ref :897-930): word 2 = prob, 3 + j = normal pair j, 3 + npairs = accept u; one task per Philox block
-            const int tA = nA * am_tasks;
-            for (int q = tid - 64; q < tA; q += MMA_THREADS - 64) {
-                const int ai = q % nA, b = 1 + q / nA;
-                const int cl = s_list[ai];
-                const uint4 blk = philox4x32_10(p, (uint32_t)it, (PURPOSE_MH << 24) | (uint32_t)b,
-                                                (uint32_t)(p.walker_offset + s_cw[cl]), (uint32_t)(p.temp_offset + s_ct[cl]));
+        // ================= phase R: evenly spread tasks.  One gather task per (DE or SCAM chain, 8 columns) -- DE: B[mm] -
+        // B[nn], SCAM: coef * row k of the transposed factor -- into the chain's zq row, and one task per AM (chain, Philox
+        // block) pair.  A thread ISSUES the loads of its r-th gather task, runs its r-th AM task (normals from one Philox
+        // block), and only then consumes the loads.
+        PTM_WARP0
+        PTM_SUB0
+        PTM_SUB(24, tid == 0)
+        if (warp == 0 && it > p.it0) bookkeeping(it - 1, l3 == 0 ? 2 : l3 - 1);
+        PTM_SUB(11, tid == 0)
+        {
+            // AM tasks take two Philox blocks (generated side by side: the draw arithmetic is a latency chain) and count up
+            // from thread 0, gather tasks count down from the last thread
+            const int nG = nD + nS, tG = nG * NT, am_tasks2 = (am_tasks + 1) >> 1, tA = nA * am_tasks2;
+            const bool vec = (d & 1) == 0;  // rows are 16-byte aligned
+            PTM_SUB(5, tid == 0)
+            for (int qa = tid, qg = MMA_THREADS - 1 - tid; qg < tG || qa < tA; qa += MMA_THREADS, qg += MMA_THREADS) {
+                const bool hg = qg < tG, ha = qa < tA;
+                double2 vm[4], vn[4];
+                double coef = 1.0;
+                double *dst = zq;
+                if (hg) {
+                    const int ci = qg % nG, seg = qg / nG;
+                    const bool de = ci < nD;
+                    const int cl = de ? s_list[2 * nc + ci] : s_list[nc + ci - nD];
+                    const double *bm = (de ? p.de : a.Ut) + s_rowm[cl], *bn = p.de + (de ? s_rown[cl] : 0ull);
+                    coef = de ? 1.0 : s_sca[cl];
+                    const int col = 8 * seg;
+                    dst = zq + cl * ld + col;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int wi = 2 * b + h;
-                    const uint64_t word = h ? hi_word(blk) : lo_word(blk);
-                    if (wi == 2) {
-                        s_sca[cl] = 2.4 / sqrt(2.0 * d) * cov_jump_scale(word_to_unit(word), s_temp[cl]);
-                    } else if (wi < uword) {
-                        double z0, z1;
-                        word_to_normals(word, z0, z1);
-                        const int j = 2 * (wi - 3);
-                        zq[cl * ld + j] = z0;
-                        if (j + 1 < KP) zq[cl * ld + j + 1] = z1;
-                    } else if (wi == uword) {
-                        s_uword[cl] = word;
+                    for (int k = 0; k < 4; ++k) {
+                        vm[k] = vn[k] = make_double2(0.0, 0.0);
+                        const int c = col + 2 * k;
+                        if (vec) {
+                            if (c < d) {
+                                vm[k] = __ldg(reinterpret_cast<const double2 *>(bm + c));
+                                if (de) vn[k] = __ldg(reinterpret_cast<const double2 *>(bn + c));
+                            }
+                        } else {
+                            if (c < d) vm[k].x = __ldg(bm + c);
+                            if (c + 1 < d) vm[k].y = __ldg(bm + c + 1);
+                            if (de && c < d) vn[k].x = __ldg(bn + c);
+                            if (de && c + 1 < d) vn[k].y = __ldg(bn + c + 1);
+                        }
                     }
                 }
+                PTM_SUB(8, tid == 0)
+                if (ha) {
+                    // AM (ref :897-930): word 2 = prob, 3 + j = normal pair j, 3 + npairs = accept u
+                    const int ai = qa % nA, b0 = 1 + 2 * (qa / nA);
+                    const int cl = s_list[ai];
+                    const uint32_t cw = (uint32_t)(p.walker_offset + s_cw[cl]), ct = (uint32_t)(p.temp_offset + s_ct[cl]);
+                    uint4 blk[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) blk[e] = philox4x32_10(p, (uint32_t)it, (PURPOSE_MH << 24) | (uint32_t)(b0 + e), cw, ct);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int wi = 2 * (b0 + e) + h;
+                            const uint64_t word = h ? hi_word(blk[e]) : lo_word(blk[e]);
+                            if (wi == 2) {
+                                s_sca[cl] = 2.4 / sqrt(2.0 * d) * cov_jump_scale(word_to_unit(word), s_temp[cl]);
+                            } else if (wi < uword) {
+                                double z0, z1;
+                                word_to_normals(word, z0, z1);
+                                const int j = 2 * (wi - 3);
+                                zq[cl * ld + j] = z0;
+                                if (j + 1 < KP) zq[cl * ld + j + 1] = z1;
+                            } else if (wi == uword) {
+                                s_uword[cl] = word;
+                            }
+                        }
+                    }
+                }
+                PTM_SUB(9, tid == 0)
+                if (hg) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        *reinterpret_cast<double2 *>(dst + 2 * k) = make_double2(coef * (vm[k].x - vn[k].x), coef * (vm[k].y - vn[k].y));
+                }
+                PTM_SUB(10, tid == 0)
             }
         }
+        PTM_WARP(16)
         __syncthreads();
         PTM_CLK(0)
 
-        // ================= phase R2: one gather task per (DE or SCAM chain, 8 columns) -- DE: B[mm] - B[nn], SCAM:
-        // coef * row k of the transposed factor -- into the chain's zq row
+        // ================= phase P: the AM chains: zq <- U (z * cd * sqrt(S)) on the tensor cores (q = x + U delta equals
+        // the reference's U (U^T x + delta), ref :923-931).  Warp g takes n-tiles [g NT/8, (g+1) NT/8) of ALL AM tiles (<= 4:
+        // a block holds <= 32 chains), so a fragment of the factor (from L2, PD k-tiles in flight) is fetched once per block.
+        // Every warp reads whole z rows, so the results are written after a barrier.
         {
-            const int nG = nD + nS, tG = nG * NT;
-            const bool vec = (d & 1) == 0;  // rows are 16-byte aligned
-            for (int q = tid; q < tG; q += MMA_THREADS) {
-                const int ci = q % nG, seg = q / nG;
-                const bool de = ci < nD;
-                const int cl = de ? s_list[2 * nc + ci] : s_list[nc + ci - nD];
-                const double *bm = (de ? p.de : a.Ut) + s_rowm[cl], *bn = p.de + (de ? s_rown[cl] : 0ull);
-                const double coef = de ? 1.0 : s_sca[cl];
-                const int col = 8 * seg;
-                double2 vm[4], vn[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    vm[k] = vn[k] = make_double2(0.0, 0.0);
-                    const int c = col + 2 * k;
-                    if (vec) {
-                        if (c < d) {
-                            vm[k] = __ldg(reinterpret_cast<const double2 *>(bm + c));
-                            if (de) vn[k] = __ldg(reinterpret_cast<const double2 *>(bn + c));
-                        }
-                    } else {
-                        if (c < d) vm[k].x = __ldg(bm + c);
-                        if (c + 1 < d) vm[k].y = __ldg(bm + c + 1);
-                        if (de && c < d) vn[k].x = __ldg(bn + c);
-                        if (de && c + 1 < d) vn[k].y = __ldg(bn + c + 1);
-                    }
-                }
-                double *dst = zq + cl * ld + col;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    *reinterpret_cast<double2 *>(dst + 2 * k) = make_double2(coef * (vm[k].x - vn[k].x), coef * (vm[k].y - vn[k].y));
-            }
-        }
-        __syncthreads();
-        PTM_CLK(1)
-
-        // ================= phase P: the AM chains, 8 at a time: zq <- U (z * cd * sqrt(S)) on the tensor cores
-        // (q = x + U delta equals the reference's U (U^T x + delta), ref :923-931).  Items (AM tile, group of <= 4 n-tiles),
-        // MMA_WARPS of them per round; an item reads its tile's whole z rows, so a round's results are written after a
-        // barrier (later rounds touch other tiles' rows only).  The factor's fragments come from L2: PD k-tiles in flight.
-        {
-            constexpr int NGP = NT <= 8 ? 2 : 4, TPR = MMA_WARPS / NGP, PD = NT < 4 ? NT : 4;
+            constexpr int CN = (NT + MMA_WARPS - 1) / MMA_WARPS, MT = 2, PD = NT < 6 ? NT : 6;
             const int nTA = (nA + 7) >> 3;
-            const double2 *ufb = reinterpret_cast<const double2 *>(a.Uf) + lane;
-            for (int t0 = 0; t0 < nTA; t0 += TPR) {
-                const int ta = t0 + warp / NGP, g = warp % NGP;
-                const int n0 = g * NT / NGP, cnt = (g + 1) * NT / NGP - n0;
-                const bool item = ta < nTA;
-                const int ai = ta * 8 + r;
-                const bool live = item && ai < nA;
-                const int cl = s_list[live ? ai : nA - 1];
-                double acc[4][2];
+            const int n0 = warp * NT / MMA_WARPS, cnt = (warp + 1) * NT / MMA_WARPS - n0;
+            const double2 *uf = reinterpret_cast<const double2 *>(a.Uf) + lane + n0 * 32;
+            PTM_SUB0
+            for (int tp = 0; tp < nTA; tp += MT) {  // MT tiles per pass (a second pass only when > 16 chains drew AM)
+                double acc[MT][CN][2];
+                const double *zr[MT];
+                double cdt[MT];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = 0.0;
-                if (item) {
-                    const double cd = s_sca[cl];
-                    const double2 *uf = ufb + n0 * 32;
-                    const double *zrow = zq + cl * ld + 2 * t;
-                    double2 b[PD][4];
+                for (int ta = 0; ta < MT; ++ta) {
+                    const int ai = (tp + ta) * 8 + r;
+                    const int cl = s_list[ai < nA ? ai : nA - 1];
+                    zr[ta] = zq + cl * ld + 2 * t;
+                    cdt[ta] = s_sca[cl];
+#pragma unroll
+                    for (int j = 0; j < CN; ++j) acc[ta][j][0] = acc[ta][j][1] = 0.0;
+                }
+                if (cnt > 0) {
+                    double2 b[PD][CN];
 #pragma unroll
                     for (int s = 0; s < PD; ++s)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) b[s][j] = (j < cnt) ? __ldg(uf + (s * NT + j) * 32) : make_double2(0.0, 0.0);
+                        for (int j = 0; j < CN; ++j) b[s][j] = (j < cnt) ? __ldg(uf + (s * NT + j) * 32) : make_double2(0.0, 0.0);
 #pragma unroll
                     for (int kk = 0; kk < NT; ++kk) {
                         // the padded columns of z hold finite values and meet zero rows of the fragment image
-                        const double2 z = *reinterpret_cast<const double2 *>(zrow + 8 * kk);
                         const double2 sv = *reinterpret_cast<const double2 *>(sSs + 8 * kk + 2 * t);
-                        const double a0 = z.x * cd * sv.x, a1 = z.y * cd * sv.y;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j < cnt) dmma884(acc[j][0], acc[j][1], a0, b[kk % PD][j].x);
+                        for (int ta = 0; ta < MT; ++ta) {
+                            if (tp + ta < nTA) {
+                                const double2 z = *reinterpret_cast<const double2 *>(zr[ta] + 8 * kk);
+                                const double a0 = z.x * cdt[ta] * sv.x, a1 = z.y * cdt[ta] * sv.y;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j < cnt) dmma884(acc[j][0], acc[j][1], a1, b[kk % PD][j].y);
+                                for (int j = 0; j < CN; ++j) {
+                                    if (j < cnt) {
+                                        dmma884(acc[ta][j][0], acc[ta][j][1], a0, b[kk % PD][j].x);
+                                        dmma884(acc[ta][j][0], acc[ta][j][1], a1, b[kk % PD][j].y);
+                                    }
+                                }
+                            }
+                        }
                         if (kk + PD < NT) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
+                            for (int j = 0; j < CN; ++j)
                                 if (j < cnt) b[kk % PD][j] = __ldg(uf + ((kk + PD) * NT + j) * 32);
                         }
                     }
                 }
+                PTM_SUB(12, tid == 0)
                 __syncthreads();
-                if (live) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < cnt)
-                            *reinterpret_cast<double2 *>(zq + cl * ld + 8 * (n0 + j) + 2 * t) = make_double2(acc[j][0], acc[j][1]);
+                for (int ta = 0; ta < MT; ++ta) {
+                    if ((tp + ta) * 8 + r < nA) {
+#pragma unroll
+                        for (int j = 0; j < CN; ++j)
+                            if (j < cnt)
+                                *reinterpret_cast<double2 *>(const_cast<double *>(zr[ta]) + 8 * (n0 + j)) =
+                                    make_double2(acc[ta][j][0], acc[ta][j][1]);
+                    }
                 }
             }
         }
         __syncthreads();
-        PTM_CLK(2)
+        PTM_CLK(1)
 
         // ================= phase L: log-prior, quadratic form on the tensor cores (warp = (tile, half); half 1 leaves its
         // part in s_part), Hastings test
@@ -409,6 +462,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
             constexpr int ST = mma_split_at(NT, true), SF = mma_split_at(NT, false);
             bool inside = true;
             double part = 0.0;
+            PTM_SUB0
             if (active) {
                 if (half == 0)
                     part = tri ? quad_part<NT, 0, ST, true, true>(xrow, zrow, mult, mus, los, his, inclusive, pf, t, inside)
@@ -420,8 +474,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
                 part += __shfl_xor_sync(0xffffffffu, part, 2);
                 if (half == 1 && t == 0) s_part[cl] = part;
             }
+            PTM_SUB(13, tid == 0)
             __syncthreads();
-            PTM_CLK(3)
+            PTM_CLK(2)
+            PTM_SUB_RESTART
             if (active && half == 0) {
                 // the four lanes of a quad hold one chain: all must be inside
                 const unsigned bal = __ballot_sync(0xffffffffu, inside);
@@ -454,22 +510,37 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
                         s_jt[cl] = (unsigned char)(jump | 0x80);
                     }
                 }
-            } else if (warp == MMA_WARPS - 1 && it < p.it1) {
-                pick_kinds(it + 1);  // state-free: under the Hastings tests of this iteration
+                PTM_SUB(14, tid == 0)
+            } else if (warp >= MMA_WARPS - 3 && it < p.it1) {
+                // state-free draws under the Hastings tests of this iteration: warp 7 the jump kinds and lists of iteration
+                // it+2, warp 6 the DE chains and warp 5 the SCAM chains of iteration it+1
+                const int s1 = next3(l3);
+                if (warp == MMA_WARPS - 1) {
+                    if (it + 2 <= p.it1) pick_kinds(it + 2, next3(s1));
+                    PTM_SUB(15, lane == 0)
+                } else if (warp == MMA_WARPS - 2) {
+                    draw_de(it + 1, s1);
+                    PTM_SUB(7, lane == 0)
+                } else {
+                    draw_scam(it + 1, s1);
+                    PTM_SUB(6, lane == 0)
+                }
             }
         }
         __syncthreads();
-        PTM_CLK(4)
+        PTM_CLK(3)
     }
-    if (warp == 0 && p.it1 >= p.it0) bookkeeping(p.it1);
-    if (have) {
-        for (int k = 0; k < d; ++k) p.x[((size_t)tme * d + k) * W + wme] = xs[tid * ld + k];
-        p.lnl[cme] = s_lnl[tid];
-        p.lp[cme] = s_lp[tid];
+    if (warp == 0 && p.it1 >= p.it0) bookkeeping(p.it1, l3 == 0 ? 2 : l3 - 1);
+    if (tid < nc && c0 + tid < TW) {
+        const int tb = s_ct[tid], wb = s_cw[tid];
+        const long long cb = c0 + tid;
+        for (int k = 0; k < d; ++k) p.x[((size_t)tb * d + k) * W + wb] = xs[tid * ld + k];
+        p.lnl[cb] = s_lnl[tid];
+        p.lp[cb] = s_lp[tid];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            p.prop[(size_t)j * TW + cme] += s_cnt[j * nc + tid];
-            p.acc[(size_t)j * TW + cme] += s_cnt[(3 + j) * nc + tid];
+            p.prop[(size_t)j * TW + cb] += s_cnt[j * nc + tid];
+            p.acc[(size_t)j * TW + cb] += s_cnt[(3 + j) * nc + tid];
         }
     }
 }

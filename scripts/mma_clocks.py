@@ -23,16 +23,27 @@ eng.run(1100)
 eng.sync()
 fn = _cabi._lib.ptmcmc_debug_mma_clocks
 fn.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
-out = (ctypes.c_uint64 * 8)()
+out = (ctypes.c_uint64 * 32)()
 fn(out, 1)
 eng.run(iters - 1100 if iters > 1100 else 100)
 eng.sync()
 fn(out, 0)
 v = np.array(list(out), dtype=float)
-names = ["A (bookkeeping, jump pick, scalar draws, lists)", "R (gathers + AM normals)", "P mma", "P write-back", "L"]
+names = ["R (gathers, AM normals)", "P (AM mat-vec by DMMA)", "L (quadratic form by DMMA)",
+         "epilogue (Hastings, update; draws of the next iteration)", "-"]
+if "split" not in eng.mh_kernel_name:
+    names = ["A (bookkeeping, jump pick, scalar draws, lists)", "R (gathers + AM normals)", "P mma", "P write-back", "L"]
 nc = int(eng.mh_kernel_name.split("(")[1].split()[0])
 n = (iters - 1100 if iters > 1100 else 100) * ((T * W + nc - 1) // nc)
 print("kernel", eng.mh_kernel_name)
 for k, nm in enumerate(names):
     print("%-52s %8.0f clk / block-iteration  %5.1f %%" % (nm, v[k] / n, 100 * v[k] / v[:5].sum()))
 print("total %.0f" % (v[:5].sum() / n))
+if "split" in eng.mh_kernel_name:
+    sub = {8: "R thread 0, first task: gather loads issued", 9: "R thread 0: AM task", 10: "R thread 0: loads consumed, stored",
+           24: "R thread 0: nothing (two clock reads)", 11: "R thread 0: bookkeeping", 5: "R thread 0: setup", 12: "P thread 0: mat-vec before the barrier", 13: "L thread 0: quadratic form before the barrier",
+           14: "epilogue warp 0: Hastings test, update", 15: "epilogue warp 7: jump kinds + lists (+ named barrier)",
+           7: "epilogue warp 7: DE draws", 6: "epilogue warp 6: wait for the lists + SCAM draws"}
+    for k, nm in sub.items():
+        print("  %-58s %8.0f clk" % (nm, v[k] / n))
+    print("  R: arrival of warps 0..7 at the closing barrier:", " ".join("%.0f" % (x / n) for x in v[16:24]))
