@@ -760,7 +760,8 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
             CUDA_TRY(nullptr, dalloc(&e->d_Pf, nf));
             CUDA_TRY(nullptr, dalloc(&e->d_gPfull, (size_t)d * d));
             CUDA_TRY(nullptr, dalloc(&e->d_Ut, (size_t)d * d));
-            CUDA_TRY(nullptr, cudaMemcpy(e->d_gPfull, Pn.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice));
+            // on the engine's stream: the buffers are stream-ordered allocations (a pageable source is staged before the call returns)
+            CUDA_TRY(nullptr, cudaMemcpyAsync(e->d_gPfull, Pn.data(), sizeof(double) * d * d, cudaMemcpyHostToDevice, e->stream));
             CUDA_TRY(nullptr, launch_frag_build(e->d_gPfull, d, e->mma.nt, 0, mma_pf_tiles(e->mma) != e->mma.nt * e->mma.nt,
                                                 e->d_Pf, e->stream));
         }
