@@ -240,6 +240,16 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
         }
     };
     // buffers / record of iteration ib (ref :627) for the chain of thread tid < nc
+    // AM chains of iteration `it` (ref :897-920), one per lane: word 2 -> the jump scale cd (the normals follow in phase R)
+    auto draw_am = [&](long long it, int slot) {
+        const int buf = (int)(it & 1), nA = s_count[4 * slot];
+        for (int i = lane; i < nA; i += 32) {
+            const int cl = s_list2[(slot * 3) * nc + i];
+            const Stream st(p, PURPOSE_MH, (unsigned long long)it, (uint32_t)(p.walker_offset + s_cw[cl]),
+                            (uint32_t)(p.temp_offset + s_ct[cl]));
+            s_sca2[buf * nc + cl] = 2.4 / sqrt(2.0 * d) * cov_jump_scale(word_to_unit(lo_word(st.block(1))), s_temp[cl]);
+        }
+    };
     // few blocks have anything to write: the first chain's rung decides for the block (chains are rung-major)
     const bool bk_block = p.trace != nullptr || (int)(c0 / W) < max(p.ntr, (p.temp_offset == 0 && p.am != nullptr) ? 1 : 0);
     auto bookkeeping = [&](long long ib, int slot) {
@@ -275,6 +285,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
         if (warp == MMA_WARPS - 1 && p.it0 < p.it1) pick_kinds(p.it0 + 1, next3(l3));
         if (warp == MMA_WARPS - 2) draw_de(p.it0, l3);
         if (warp == MMA_WARPS - 3) draw_scam(p.it0, l3);
+        if (warp == MMA_WARPS - 4) draw_am(p.it0, l3);
     }
     __syncthreads();
 #ifdef PTMCMC_MMA_CLOCKS
@@ -340,6 +351,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
                     // AM (ref :897-930): word 2 = prob, 3 + j = normal pair j, 3 + npairs = accept u
                     const int ai = qa % nA, b0 = 1 + 2 * (qa / nA);
                     const int cl = s_list[ai];
+                    const double cd = s_sca[cl];
                     const uint32_t cw = (uint32_t)(p.walker_offset + s_cw[cl]), ct = (uint32_t)(p.temp_offset + s_ct[cl]);
                     uint4 blk[2];
 #pragma unroll
@@ -351,13 +363,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
                             const int wi = 2 * (b0 + e) + h;
                             const uint64_t word = h ? hi_word(blk[e]) : lo_word(blk[e]);
                             if (wi == 2) {
-                                s_sca[cl] = 2.4 / sqrt(2.0 * d) * cov_jump_scale(word_to_unit(word), s_temp[cl]);
+                                // the jump scale was drawn ahead (draw_am)
                             } else if (wi < uword) {
+                                // delta = z cd sqrt(S) (ref :923-926) is what phase P multiplies; padded columns get sqrt(S) = 0
                                 double z0, z1;
                                 word_to_normals(word, z0, z1);
                                 const int j = 2 * (wi - 3);
-                                zq[cl * ld + j] = z0;
-                                if (j + 1 < KP) zq[cl * ld + j + 1] = z1;
+                                const double2 sv = *reinterpret_cast<const double2 *>(sSs + j);
+                                *reinterpret_cast<double2 *>(zq + cl * ld + j) = make_double2(z0 * cd * sv.x, z1 * cd * sv.y);
                             } else if (wi == uword) {
                                 s_uword[cl] = word;
                             }
@@ -390,13 +403,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
             for (int tp = 0; tp < nTA; tp += MT) {  // MT tiles per pass (a second pass only when > 16 chains drew AM)
                 double acc[MT][CN][2];
                 const double *zr[MT];
-                double cdt[MT];
 #pragma unroll
                 for (int ta = 0; ta < MT; ++ta) {
                     const int ai = (tp + ta) * 8 + r;
                     const int cl = s_list[ai < nA ? ai : nA - 1];
                     zr[ta] = zq + cl * ld + 2 * t;
-                    cdt[ta] = s_sca[cl];
 #pragma unroll
                     for (int j = 0; j < CN; ++j) acc[ta][j][0] = acc[ta][j][1] = 0.0;
                 }
@@ -408,18 +419,15 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
                         for (int j = 0; j < CN; ++j) b[s][j] = (j < cnt) ? __ldg(uf + (s * NT + j) * 32) : make_double2(0.0, 0.0);
 #pragma unroll
                     for (int kk = 0; kk < NT; ++kk) {
-                        // the padded columns of z hold finite values and meet zero rows of the fragment image
-                        const double2 sv = *reinterpret_cast<const double2 *>(sSs + 8 * kk + 2 * t);
 #pragma unroll
                         for (int ta = 0; ta < MT; ++ta) {
                             if (tp + ta < nTA) {
-                                const double2 z = *reinterpret_cast<const double2 *>(zr[ta] + 8 * kk);
-                                const double a0 = z.x * cdt[ta] * sv.x, a1 = z.y * cdt[ta] * sv.y;
+                                const double2 dl = *reinterpret_cast<const double2 *>(zr[ta] + 8 * kk);  // delta, scaled in phase R
 #pragma unroll
                                 for (int j = 0; j < CN; ++j) {
                                     if (j < cnt) {
-                                        dmma884(acc[ta][j][0], acc[ta][j][1], a0, b[kk % PD][j].x);
-                                        dmma884(acc[ta][j][0], acc[ta][j][1], a1, b[kk % PD][j].y);
+                                        dmma884(acc[ta][j][0], acc[ta][j][1], dl.x, b[kk % PD][j].x);
+                                        dmma884(acc[ta][j][0], acc[ta][j][1], dl.y, b[kk % PD][j].y);
                                     }
                                 }
                             }
@@ -511,9 +519,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
                     }
                 }
                 PTM_SUB(14, tid == 0)
-            } else if (warp >= MMA_WARPS - 3 && it < p.it1) {
+            } else if (warp >= MMA_WARPS - 4 && it < p.it1) {
                 // state-free draws under the Hastings tests of this iteration: warp 7 the jump kinds and lists of iteration
-                // it+2, warp 6 the DE chains and warp 5 the SCAM chains of iteration it+1
+                // it+2, warp 6 the DE chains, warp 5 the SCAM chains and warp 4 the AM chains' jump scales of iteration it+1
                 const int s1 = next3(l3);
                 if (warp == MMA_WARPS - 1) {
                     if (it + 2 <= p.it1) pick_kinds(it + 2, next3(s1));
@@ -521,9 +529,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) mh_mma_split_kernel(const __gr
                 } else if (warp == MMA_WARPS - 2) {
                     draw_de(it + 1, s1);
                     PTM_SUB(7, lane == 0)
-                } else {
+                } else if (warp == MMA_WARPS - 3) {
                     draw_scam(it + 1, s1);
                     PTM_SUB(6, lane == 0)
+                } else {
+                    draw_am(it + 1, s1);
                 }
             }
         }
