@@ -113,6 +113,7 @@ struct Engine {
     unsigned char *d_trace = nullptr;
     short *d_swapmaps = nullptr;
     int *d_map = nullptr;
+    double *d_swap_prep = nullptr;  // [4][T][W]: state-independent terms of a swap sweep (swap_prep_kernel)
     double *d_part2 = nullptr, *d_batch = nullptr, *d_gram = nullptr;
     double *d_stage = nullptr;  // [T][W][d] staging in the host layout
     int mom_blocks = 0, gram_kp = 0, jac_smem_doubles = 0;
@@ -251,6 +252,7 @@ Engine *engine_of(const ptmcmc_engine *h)
 }
 
 int chain_blocks(const Engine *e) { return (int)(((long long)e->T * e->W + MH_THREADS - 1) / MH_THREADS); }
+int chain_blocks256(const Engine *e) { return (int)(((long long)e->T * e->W + 255) / 256); }
 
 // the specialised kernels know the three reference proposals; a cycle with the prior-draw jump runs in the generic one
 bool fast_reg_path(const Engine *e) { return e->identity_group && e->d <= MAX_REG_DIM && e->njumps == 3 && !e->user; }
@@ -293,10 +295,11 @@ cudaError_t launch_mh(Engine *e, long long it0, long long it1, bool tail)
 cudaError_t launch_swap(Engine *e, long long it)
 {
     DevParams p = make_params(e);
-    LaunchTimer lt(e, PTMCMC_K_SWAP, 2);
+    LaunchTimer lt(e, PTMCMC_K_SWAP, 3);
     short *tr = nullptr;
     if (e->d_swapmaps && e->swap_events < e->cfg.trace_iters) tr = e->d_swapmaps + (size_t)e->swap_events * e->W * e->T;
-    swap_decide_kernel<<<(e->W + 127) / 128, 128, 0, e->stream>>>(p, it, e->d_map, tr);
+    swap_prep_kernel<<<chain_blocks256(e), 256, 0, e->stream>>>(p, it, e->Tg, 0.0, 0, e->d_swap_prep);
+    swap_decide_kernel<<<(e->W + 127) / 128, 128, 0, e->stream>>>(p, e->d_swap_prep, e->d_map, tr);
     const int nxt = e->cur ^ 1;
     swap_apply_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, it, e->d_map, e->x[nxt], e->lnl[nxt], e->lp[nxt]);
     e->cur = nxt;
@@ -690,6 +693,7 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     CUDA_TRY(nullptr, dalloc(&e->d_acc, C * e->njumps));
     CUDA_TRY(nullptr, dalloc(&e->d_swap_acc, C));
     CUDA_TRY(nullptr, dalloc(&e->d_map, C));
+    CUDA_TRY(nullptr, dalloc(&e->d_swap_prep, 4 * C));
     if (e->sharded) {
         CUDA_TRY(nullptr, dalloc(&e->d_carry_code, W));
         CUDA_TRY(nullptr, dalloc(&e->d_carry_L, W));
@@ -803,7 +807,7 @@ void ptmcmc_destroy(ptmcmc_engine *h)
                     e->d_cov, e->d_mu, e->d_m2, e->d_U, e->d_S, e->d_sqrtS, e->d_goff, e->d_gidx, e->d_uoff,
                     e->d_soff, e->d_ord, e->d_work_a, e->d_work_v, e->d_am, e->d_de, e->d_gmu, e->d_gP,
                     e->d_plo, e->d_phi, e->d_rec_x, e->d_rec_lnl, e->d_rec_lnp, e->d_prop, e->d_acc,
-                    e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_part2, e->d_batch, e->d_gram,
+                    e->d_swap_acc, e->d_trace, e->d_swapmaps, e->d_map, e->d_swap_prep, e->d_part2, e->d_batch, e->d_gram,
                     e->d_q, e->d_qxy, e->d_lnl_new, e->d_lp_new, e->d_jump, e->d_wordpos, e->d_stage,
                     e->d_carry_code, e->d_carry_L, e->d_Uf, e->d_Pf, e->d_gPfull, e->d_Ut, e->d_snap[0], e->d_snap[1], e->d_user_par};
     for (void *p : ptrs)
@@ -939,6 +943,15 @@ int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
         if (swap_now && e->sharded) {
             e->pending_swap = true;  // the neighbour exchange is driven by the caller
             e->swept = false;
+            {
+                // everything of the sweep that does not wait for the hotter shard's carry, right behind the MH kernel
+                DevParams p = make_params(e);
+                LaunchTimer lt(e, PTMCMC_K_SWAP);
+                swap_prep_kernel<<<chain_blocks256(e), 256, 0, e->stream>>>(p, seg_end, e->Tg, e->cfg.ladder_above,
+                                                                             e->cfg.temp_offset + e->T < e->Tg ? 1 : 0,
+                                                                             e->d_swap_prep);
+            }
+            if (cudaGetLastError() != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "swap_prep_kernel");
         } else if (swap_now) {
             st = launch_swap(e, seg_end);
             if (st != cudaSuccess) return fail(e, PTMCMC_ERR_CUDA, "swap kernels: %s", cudaGetErrorString(st));
@@ -1393,7 +1406,7 @@ int32_t ptmcmc_swap_sweep(ptmcmc_engine *h, const double *dev_carry_in, double *
     DevParams p = make_params(e);
     {
         LaunchTimer lt(e, PTMCMC_K_SWAP);
-        swap_sweep_kernel<<<(e->W + 127) / 128, 128, 0, e->stream>>>(p, e->iter, e->Tg, e->cfg.ladder_above, dev_carry_in,
+        swap_sweep_kernel<<<(e->W + 127) / 128, 128, 0, e->stream>>>(p, e->cfg.ladder_above, e->d_swap_prep, dev_carry_in,
                                                                       dev_carry_out, e->d_map, e->d_carry_code,
                                                                       e->d_carry_L);
     }

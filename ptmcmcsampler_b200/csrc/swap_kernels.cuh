@@ -10,37 +10,116 @@
 
 namespace ptm {
 
-// map_out[t][w] = rung whose state moves to rung t.  Because the sweep visits each pair once,
-// top-down, only the state currently sitting at position sc+1 (the "carry") is ever displaced.
-__global__ void __launch_bounds__(128) swap_decide_kernel(const DevParams p, long long it, int *map_out,
+// dst[k W] = src[k W], k < d, with four loads in flight (d is a run-time value: the plain loop waits for each load)
+__device__ __forceinline__ void copy_strided(double *dst, const double *src, int d, int W)
+{
+    int k = 0;
+    for (; k + 4 <= d; k += 4) {
+        const double v0 = src[(size_t)k * W], v1 = src[(size_t)(k + 1) * W], v2 = src[(size_t)(k + 2) * W],
+                     v3 = src[(size_t)(k + 3) * W];
+        dst[(size_t)k * W] = v0;
+        dst[(size_t)(k + 1) * W] = v1;
+        dst[(size_t)(k + 2) * W] = v2;
+        dst[(size_t)(k + 3) * W] = v3;
+    }
+    for (; k < d; ++k) dst[(size_t)k * W] = src[(size_t)k * W];
+}
+
+// The sweep is a dependent chain over the rungs of a walker; everything about a pair that does not depend on the
+// travelling state is computed for all pairs at once beforehand (thread per pair and walker): the accept uniform and
+// the two terms of the log acceptance ratio that hold the lower rung's own lnL.  prep[0][sc][w] = u of pair (sc, sc+1) (and prep[3] = log u)
+// (global pair g uses word Tg-2-g of the swap stream: hottest pair first), prep[1] = -La/Ta, prep[2] = La/Tb with La the
+// lnL at local rung sc.  Pair index T-1 is the boundary pair with the hotter shard (Tb = ladder_above), present when
+// has_above.  The chain that remains per pair is two divisions, three additions, exp and a compare (ref :673-679, same
+// four-term order, see swap_accept below).
+__global__ void __launch_bounds__(256) swap_prep_kernel(const DevParams p, long long it, int Tg, double ladder_above,
+                                                        int has_above, double *prep)
+{
+    const int W = p.W, T = p.T;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)T * W) return;
+    const int sc = (int)(idx / W), w = (int)(idx % W);
+    if (sc == T - 1 && !has_above) return;
+    const double La = p.lnl[idx];
+    const double Ta = p.ladder[sc], Tb = (sc == T - 1) ? ladder_above : p.ladder[sc + 1];
+    Stream st(p, PURPOSE_SWAP, (unsigned long long)it, (uint32_t)(p.walker_offset + w), 0u);
+    st.seek((uint32_t)(Tg - 2 - (p.temp_offset + sc)));
+    const size_t C = (size_t)T * W;
+    const double u = word_to_unit(st.next());
+    prep[idx] = u;
+    prep[C + idx] = -La / Ta;
+    prep[2 * C + idx] = La / Tb;
+    prep[3 * C + idx] = log(u);
+}
+
+// pair sc of walker w against the travelling state's lnL (Lb): u <= exp(-La/Ta - Lb/Tb + Lb/Ta + La/Tb).
+// exp is monotone and both exp and log are good to an ulp, so unless lar and log(u) agree to 1e-12 the comparison of the
+// logarithms decides exactly as the reference's does; the exponential is evaluated only in that band (and for NaN / inf).
+__device__ __forceinline__ bool swap_accept_prep(double u, double logu, double a1, double a4, double Lb, double Ta, double Tb)
+{
+    double lar = a1;
+    lar += -Lb / Tb;
+    lar += Lb / Ta;
+    lar += a4;
+    const double gap = lar - logu, band = 1e-12 * fmax(1.0, fabs(lar));
+    if (gap > band) return true;
+    if (gap < -band) return false;
+    return u <= exp(lar);
+}
+
+// The local pairs (T-2 .. 0) of walker w, top-down, starting from the state `carry` (lnL Lcarry) at position T-1.
+// map_out[t][w] = rung whose state moves to rung t: because the sweep visits each pair once, only the state currently
+// sitting at position sc+1 (the "carry") is ever displaced.  The operands of SWEEP_CHUNK pairs are loaded together (their
+// addresses do not depend on the chain), so the chain pays one memory round trip per chunk instead of one per pair.
+constexpr int SWEEP_CHUNK = 8;
+__device__ __forceinline__ void sweep_local_pairs(const DevParams &p, const double *prep, int w, int &carry, double &Lcarry,
+                                                  int *map_out)
+{
+    const int W = p.W, T = p.T;
+    const size_t C = (size_t)T * W;
+    for (int sc0 = T - 2; sc0 >= 0; sc0 -= SWEEP_CHUNK) {
+        double u[SWEEP_CHUNK], lu[SWEEP_CHUNK], a1[SWEEP_CHUNK], a4[SWEEP_CHUNK], La[SWEEP_CHUNK], Ta[SWEEP_CHUNK], Tb[SWEEP_CHUNK];
+#pragma unroll
+        for (int j = 0; j < SWEEP_CHUNK; ++j) {
+            const int sc = sc0 - j;
+            if (sc >= 0) {
+                const size_t idx = (size_t)sc * W + w;
+                u[j] = prep[idx];
+                a1[j] = prep[C + idx];
+                a4[j] = prep[2 * C + idx];
+                lu[j] = prep[3 * C + idx];
+                La[j] = p.lnl[idx];  // swap_map[sc] == sc: not visited yet
+                Ta[j] = p.ladder[sc];
+                Tb[j] = p.ladder[sc + 1];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SWEEP_CHUNK; ++j) {
+            const int sc = sc0 - j;
+            if (sc >= 0) {
+                const size_t idx = (size_t)sc * W + w;
+                if (swap_accept_prep(u[j], lu[j], a1[j], a4[j], Lcarry, Ta[j], Tb[j])) {  // ref :679-681
+                    map_out[idx + W] = sc;
+                    atomicAdd(&p.swap_acc[idx], 1ull);  // a reduction: the chain does not wait for the counter's old value
+                } else {
+                    map_out[idx + W] = carry;
+                    carry = sc;
+                    Lcarry = La[j];
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) swap_decide_kernel(const DevParams p, const double *prep, int *map_out,
                                                           short *swapmap_trace)
 {
     const int W = p.W, T = p.T;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
-    Stream st(p, PURPOSE_SWAP, (unsigned long long)it, (uint32_t)(p.walker_offset + w), 0u);
     int carry = T - 1;
     double Lcarry = p.lnl[(size_t)(T - 1) * W + w];
-    for (int sc = T - 2; sc >= 0; --sc) {
-        const double La = p.lnl[(size_t)sc * W + w];  // swap_map[sc] == sc: not visited yet
-        const double Lb = Lcarry;
-        const double Ta = p.ladder[sc], Tb = p.ladder[sc + 1];
-        // ref :673-676, same four-term order
-        double lar = -La / Ta;
-        lar += -Lb / Tb;
-        lar += Lb / Ta;
-        lar += La / Tb;
-        const double ratio = exp(lar);
-        const double u = word_to_unit(st.next());
-        if (u <= ratio) {  // ref :679-681
-            map_out[(size_t)(sc + 1) * W + w] = sc;
-            p.swap_acc[(size_t)sc * W + w] += 1;
-        } else {
-            map_out[(size_t)(sc + 1) * W + w] = carry;
-            carry = sc;
-            Lcarry = La;
-        }
-    }
+    sweep_local_pairs(p, prep, w, carry, Lcarry, map_out);
     map_out[w] = carry;
     if (swapmap_trace)
         for (int j = 0; j < T; ++j) swapmap_trace[(size_t)w * T + j] = (short)map_out[(size_t)j * W + w];
@@ -59,7 +138,7 @@ __global__ void __launch_bounds__(MH_THREADS) swap_apply_kernel(const DevParams 
     const int src = map[c];
     const double *xs = p.x + (size_t)src * d * W + w;
     double *xd = x_new + (size_t)t * d * W + w;
-    for (int k = 0; k < d; ++k) xd[(size_t)k * W] = xs[(size_t)k * W];
+    copy_strided(xd, xs, d, W);
     const double lnl = p.lnl[(size_t)src * W + w], lp = p.lp[(size_t)src * W + w];
     lnl_new[c] = lnl;
     lp_new[c] = lp;
@@ -100,40 +179,28 @@ __global__ void __launch_bounds__(256) swap_pack_top_kernel(const DevParams p, d
     }
 }
 
-// thread per walker: boundary pair with the hotter shard (if any), then the local pairs, top-down.
-// The sweep draws one uniform per pair, hottest pair first: global pair sc uses word Tg-2-sc.
-__global__ void __launch_bounds__(128) swap_sweep_kernel(const DevParams p, long long it, int Tg, double ladder_above,
+// thread per walker: boundary pair with the hotter shard (if any), then the local pairs, top-down, on the terms of
+// swap_prep_kernel (launched when the segment ended, long before the carry arrives).
+__global__ void __launch_bounds__(128) swap_sweep_kernel(const DevParams p, double ladder_above, const double *prep,
                                                          const double *carry_in, double *carry_out, int *map_out,
                                                          int *carry_code, double *carry_L)
 {
     const int d = p.d, W = p.W, T = p.T;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
-    Stream st(p, PURPOSE_SWAP, (unsigned long long)it, (uint32_t)(p.walker_offset + w), 0u);
+    const size_t C = (size_t)T * W;
     int carry = T - 1;
     double Lcarry = p.lnl[(size_t)(T - 1) * W + w];
     if (carry_in) {
-        st.seek((uint32_t)(Tg - 2 - (p.temp_offset + T - 1)));
+        const size_t idx = (size_t)(T - 1) * W + w;
         const double Lb = carry_in[(size_t)d * W + w];
-        if (swap_accept(Lcarry, Lb, p.ladder[T - 1], ladder_above, word_to_unit(st.next()))) {
-            p.swap_acc[(size_t)(T - 1) * W + w] += 1;
+        if (swap_accept_prep(prep[idx], prep[3 * C + idx], prep[C + idx], prep[2 * C + idx], Lb, p.ladder[T - 1], ladder_above)) {
+            atomicAdd(&p.swap_acc[idx], 1ull);  // a reduction: the chain does not wait for the counter's old value
             carry = T;  // the foreign state keeps travelling down
             Lcarry = Lb;
         }
-    } else {
-        st.seek((uint32_t)(Tg - 2 - (p.temp_offset + T - 2)));
     }
-    for (int sc = T - 2; sc >= 0; --sc) {
-        const double La = p.lnl[(size_t)sc * W + w];
-        if (swap_accept(La, Lcarry, p.ladder[sc], p.ladder[sc + 1], word_to_unit(st.next()))) {
-            map_out[(size_t)(sc + 1) * W + w] = sc;
-            p.swap_acc[(size_t)sc * W + w] += 1;
-        } else {
-            map_out[(size_t)(sc + 1) * W + w] = carry;
-            carry = sc;
-            Lcarry = La;
-        }
-    }
+    sweep_local_pairs(p, prep, w, carry, Lcarry, map_out);
     carry_code[w] = carry;
     carry_L[w] = Lcarry;
     if (carry_out) {
@@ -179,7 +246,7 @@ __global__ void __launch_bounds__(MH_THREADS) swap_finish_kernel(const DevParams
     const double lnl = msg ? msg[(size_t)d * W + w] : p.lnl[(size_t)code * W + w];
     const double lp = msg ? msg[(size_t)(d + 1) * W + w] : p.lp[(size_t)code * W + w];
     double *xd = x_new + (size_t)t * d * W + w;
-    for (int k = 0; k < d; ++k) xd[(size_t)k * W] = xs[(size_t)k * W];
+    copy_strided(xd, xs, d, W);
     lnl_new[c] = lnl;
     lp_new[c] = lp;
     if (swapmap_trace)
