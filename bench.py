@@ -343,6 +343,8 @@ def device_run(wl, args_steps, args_warmup, rank, world, local_rank, group=None,
     ev1.record(stream)
     eng.sync()
     torch.cuda.synchronize()
+    if comm is not None:
+        comm.check(eng)  # the peer-memory swap exchange: no message timed out
     if world > 1:
         dist.barrier()
     t_wall1 = time.time()
@@ -365,6 +367,7 @@ def device_run(wl, args_steps, args_warmup, rank, world, local_rank, group=None,
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return dict(ms=ms, steps=args_steps, launches=launches, tm=tm, kernel=kernel, wall=(t_wall0, t_wall1), Tg=Tg,
+                p2p=bool(comm is not None and comm.p2p),
                 value=world * W * T * ITERS * args_steps / (ms * 1e-3))
 
 
@@ -578,8 +581,10 @@ def run_engine(args, rank, world, local_rank):
         k = max(2, min(args.steps, 5))
         r5 = device_run(wl, k, 2, rank, world, local_rank, ladder_mode=True)
         extra["c5_ladder"] = {
-            "workload": "C5: %d-rung ladder as 32 rungs per GPU x %d GPUs, 8192 walkers, 20-dim Gaussian, NCCL nearest-neighbour "
-                        "exchange of the boundary rung at every swap; factor and AM ring broadcast from the T=1 shard" % (run["Tg"] * world, world),
+            "workload": "C5: %d-rung ladder as 32 rungs per GPU x %d GPUs, 8192 walkers, 20-dim Gaussian, nearest-neighbour "
+                        "exchange of the boundary rung at every swap; factor and AM ring broadcast from the T=1 shard (NCCL)" % (run["Tg"] * world, world),
+            "swap_exchange": "peer memory: the swap kernels store into the neighbour's mailbox over NVLink and spin on a flag"
+                             if r5["p2p"] else "NCCL send / receive",
             "value": r5["value"], "unit": UNIT, "ms_per_step": r5["ms"] / k, "steps": k, "warmup": 2,
             "fraction_of_walker_sharded": r5["value"] / run["value"], "gpu_launches": r5["launches"],
             "roofline": roofline_of(wl, r5, hbm_peak, hbm_src, fp64_peak),

@@ -816,6 +816,8 @@ class PTSampler(object):
         _t.append(time.perf_counter())
         if pending is not None:
             self._write_boundary(*pending)
+        if self._comm is not None:
+            self._comm.check(self._engine)  # ladder shards exchanging through peer memory: every message arrived
         _t.append(time.perf_counter())
         self._finish()
         if _dbg:

@@ -63,7 +63,8 @@ SYMBOLS = [
     "ptmcmc_test_normals", "ptmcmc_measure_fp64_peak", "ptmcmc_set_sink", "ptmcmc_sink_wait", "ptmcmc_snapshot_bytes",
     "ptmcmc_snapshot", "ptmcmc_snapshot_wait", "ptmcmc_adapt_begin_dev", "ptmcmc_adapt_finish_dev", "ptmcmc_factor_dev",
     "ptmcmc_factor_refresh", "ptmcmc_user_compile_check", "ptmcmc_callback_buffers", "ptmcmc_propose_pinned",
-    "ptmcmc_accept_pinned", "ptmcmc_state_seed",
+    "ptmcmc_accept_pinned", "ptmcmc_state_seed", "ptmcmc_p2p_open", "ptmcmc_p2p_connect", "ptmcmc_swap_p2p",
+    "ptmcmc_p2p_error",
 ]
 
 _lib = None
@@ -132,6 +133,10 @@ def load():
     L.ptmcmc_swap_pack_top.argtypes = [h, C.c_void_p]
     L.ptmcmc_swap_sweep.argtypes = [h, C.c_void_p, C.c_void_p]
     L.ptmcmc_swap_finish.argtypes = [h, C.c_void_p]
+    L.ptmcmc_p2p_open.argtypes = [h, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.ptmcmc_p2p_connect.argtypes = [h, C.c_void_p, C.c_void_p, C.c_int32]
+    L.ptmcmc_swap_p2p.argtypes = [h, C.c_int32]
+    L.ptmcmc_p2p_error.argtypes = [h]
     L.ptmcmc_am_ring.argtypes = [h, C.POINTER(C.c_void_p), _i64p]
     L.ptmcmc_maintain.argtypes = [h]
     L.ptmcmc_state_bytes.restype = C.c_int64
@@ -491,6 +496,31 @@ class Engine(object):
 
     def swap_finish(self, below_ptr):
         self._check(self._L.ptmcmc_swap_finish(self._h, below_ptr or None))
+
+    # the same exchange through peer memory: the kernels write into the neighbour's mailbox themselves
+    def p2p_open(self, want_handle=True):
+        """Allocate this shard's mailbox: (64-byte CUDA IPC handle or None, device address)."""
+        hd = (C.c_ubyte * 64)() if want_handle else None
+        ptr = C.c_void_p()
+        self._check(self._L.ptmcmc_p2p_open(self._h, hd, C.byref(ptr)))
+        return (bytes(hd) if want_handle else None), ptr.value
+
+    def p2p_connect(self, above, below):
+        """``above`` / ``below``: the hotter / colder neighbour's mailbox, as 64-byte IPC handles (other processes) or as
+        device addresses (same process); None where there is no neighbour."""
+        ipc = isinstance(above if above is not None else below, (bytes, bytearray))
+        if ipc:
+            keep = [C.create_string_buffer(bytes(v), 64) if v is not None else None for v in (above, below)]
+            args = [C.cast(k, C.c_void_p) if k is not None else None for k in keep]
+        else:
+            args = [C.c_void_p(v) if v is not None else None for v in (above, below)]
+        self._check(self._L.ptmcmc_p2p_connect(self._h, args[0], args[1], 1 if ipc else 0))
+
+    def swap_p2p(self, phase):
+        self._check(self._L.ptmcmc_swap_p2p(self._h, phase))
+
+    def p2p_error(self):
+        self._check(self._L.ptmcmc_p2p_error(self._h))
 
     def am_ring(self):
         """(device address, number of doubles) of the AM ring."""

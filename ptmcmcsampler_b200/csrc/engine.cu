@@ -113,6 +113,13 @@ struct Engine {
     unsigned char *d_trace = nullptr;
     short *d_swapmaps = nullptr;
     int *d_map = nullptr;
+    // neighbour exchange of the sharded swap through peer memory (ptmcmc_p2p_*): my mailbox holds, per parity of the
+    // swap's sequence number, the carry from the hotter shard and the top rung of the colder one, then 8 flags
+    double *p2p_box = nullptr, *p2p_above = nullptr, *p2p_below = nullptr;
+    bool p2p_above_ipc = false, p2p_below_ipc = false, p2p_on = false;
+    unsigned long long p2p_seq = 0;
+    unsigned *d_p2p_ctr = nullptr;
+    int *d_p2p_err = nullptr;
     double *d_swap_prep = nullptr;  // [4][T][W]: state-independent terms of a swap sweep (swap_prep_kernel)
     double *d_part2 = nullptr, *d_batch = nullptr, *d_gram = nullptr;
     double *d_stage = nullptr;  // [T][W][d] staging in the host layout
@@ -814,6 +821,10 @@ void ptmcmc_destroy(ptmcmc_engine *h)
         if (p) cudaFreeAsync(p, e->stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    if (e->p2p_above_ipc) cudaIpcCloseMemHandle(e->p2p_above);
+    if (e->p2p_below_ipc) cudaIpcCloseMemHandle(e->p2p_below);
+    for (void *pp : {(void *)e->p2p_box, (void *)e->d_p2p_ctr, (void *)e->d_p2p_err})
+        if (pp) cudaFree(pp);
     for (void *hp : {(void *)e->h_q, (void *)e->h_qxy, (void *)e->h_lnl, (void *)e->h_lp, (void *)e->h_x, (void *)e->h_jump})
         if (hp) cudaFreeHost(hp);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -1389,7 +1400,7 @@ int32_t ptmcmc_swap_pack_top(ptmcmc_engine *h, double *dev_msg)
     {
         LaunchTimer lt(e, PTMCMC_K_SWAP);
         const long long n = (long long)(e->d + 3) * e->W;
-        swap_pack_top_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 2048), 256, 0, e->stream>>>(p, dev_msg);
+        swap_pack_top_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 2048), 256, 0, e->stream>>>(p, dev_msg, P2PSync{});
     }
     CUDA_TRY(e, cudaGetLastError());
     return 0;
@@ -1408,7 +1419,7 @@ int32_t ptmcmc_swap_sweep(ptmcmc_engine *h, const double *dev_carry_in, double *
         LaunchTimer lt(e, PTMCMC_K_SWAP);
         swap_sweep_kernel<<<(e->W + 127) / 128, 128, 0, e->stream>>>(p, e->cfg.ladder_above, e->d_swap_prep, dev_carry_in,
                                                                       dev_carry_out, e->d_map, e->d_carry_code,
-                                                                      e->d_carry_L);
+                                                                      e->d_carry_L, P2PSync{});
     }
     CUDA_TRY(e, cudaGetLastError());
     e->carry_in = dev_carry_in;
@@ -1432,7 +1443,7 @@ int32_t ptmcmc_swap_finish(ptmcmc_engine *h, const double *dev_below_top)
         swap_finish_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, e->iter, e->Tg, e->cfg.ladder_below, e->d_map,
                                                                           e->d_carry_code, e->d_carry_L, e->carry_in,
                                                                           dev_below_top, e->x[nxt], e->lnl[nxt], e->lp[nxt],
-                                                                          tr);
+                                                                          tr, P2PSync{});
     }
     CUDA_TRY(e, cudaGetLastError());
     e->cur = nxt;
@@ -1443,6 +1454,144 @@ int32_t ptmcmc_swap_finish(ptmcmc_engine *h, const double *dev_below_top)
     e->carry_in = nullptr;
     e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
     CUDA_TRY(e, sink_flush(e));
+    return 0;
+}
+
+// ---- the same three steps with the messages moved by the kernels themselves through peer memory ------------------
+namespace {
+inline double *p2p_slot(double *box, size_t n, int par, int kind) { return box + (size_t)(par * 2 + kind) * n; }
+inline unsigned long long *p2p_flag(double *box, size_t n, int par, int kind)
+{
+    return reinterpret_cast<unsigned long long *>(box + 4 * n) + (par * 2 + kind);
+}
+}  // namespace
+
+int32_t ptmcmc_p2p_open(ptmcmc_engine *h, void *ipc_handle_out, void **mailbox_out)
+{
+    Engine *e = engine_of(h);
+    if (!e) return PTMCMC_ERR_ARG;
+    if (!e->sharded) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_p2p_open on an engine that is not a ladder shard");
+    const size_t n = (size_t)(e->d + 3) * e->W, bytes = 4 * n * sizeof(double) + 64;
+    if (!e->p2p_box) {
+        // cudaMalloc, not the stream-ordered pool: the allocation is exported to the neighbours' processes
+        CUDA_TRY(e, cudaMalloc(&e->p2p_box, bytes));
+        CUDA_TRY(e, cudaMemset(e->p2p_box, 0, bytes));
+        CUDA_TRY(e, cudaMalloc(&e->d_p2p_ctr, 4 * sizeof(unsigned)));
+        CUDA_TRY(e, cudaMemset(e->d_p2p_ctr, 0, 4 * sizeof(unsigned)));
+        CUDA_TRY(e, cudaMalloc(&e->d_p2p_err, sizeof(int)));
+        CUDA_TRY(e, cudaMemset(e->d_p2p_err, 0, sizeof(int)));
+    }
+    if (mailbox_out) *mailbox_out = e->p2p_box;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t hd;
+        CUDA_TRY(e, cudaIpcGetMemHandle(&hd, e->p2p_box));
+        static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(ipc_handle_out, &hd, sizeof hd);
+    }
+    return 0;
+}
+
+int32_t ptmcmc_p2p_connect(ptmcmc_engine *h, const void *above, const void *below, int32_t ipc)
+{
+    Engine *e = engine_of(h);
+    if (!e) return PTMCMC_ERR_ARG;
+    if (!e->p2p_box) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_p2p_connect before ptmcmc_p2p_open");
+    const bool hottest = e->cfg.temp_offset + e->T == e->Tg, coldest = e->cfg.temp_offset == 0;
+    if ((above == nullptr) != hottest || (below == nullptr) != coldest)
+        return fail(e, PTMCMC_ERR_ARG, "above is NULL exactly on the hottest shard, below exactly on the coldest");
+    auto map = [&](const void *src, double **dst, bool *is_ipc) -> cudaError_t {
+        *dst = nullptr;
+        *is_ipc = false;
+        if (!src) return cudaSuccess;
+        if (!ipc) {
+            *dst = (double *)src;  // a mailbox of another engine in this process
+            return cudaSuccess;
+        }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, src, sizeof hd);
+        void *ptr = nullptr;
+        cudaError_t st = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (st == cudaSuccess) {
+            *dst = (double *)ptr;
+            *is_ipc = true;
+        }
+        return st;
+    };
+    CUDA_TRY(e, map(above, &e->p2p_above, &e->p2p_above_ipc));
+    CUDA_TRY(e, map(below, &e->p2p_below, &e->p2p_below_ipc));
+    e->p2p_seq = 0;
+    e->p2p_on = true;
+    return 0;
+}
+
+int32_t ptmcmc_swap_p2p(ptmcmc_engine *h, int32_t phase)
+{
+    Engine *e = engine_of(h);
+    if (!e) return PTMCMC_ERR_ARG;
+    if (!e->p2p_on) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_swap_p2p before ptmcmc_p2p_connect");
+    if (!e->sharded || !e->pending_swap) return fail(e, PTMCMC_ERR_STATE, "no sharded swap is pending");
+    const bool hottest = e->cfg.temp_offset + e->T == e->Tg, coldest = e->cfg.temp_offset == 0;
+    const size_t n = (size_t)(e->d + 3) * e->W;
+    const unsigned long long seq = e->p2p_seq + 1;
+    const int par = (int)(seq & 1ull);
+    DevParams p = make_params(e);
+    if (phase == 0) {  // my top rung into the hotter neighbour's mailbox
+        if (hottest) return 0;
+        LaunchTimer lt(e, PTMCMC_K_SWAP);
+        const P2PSync sync{nullptr, p2p_flag(e->p2p_above, n, par, 1), e->d_p2p_ctr, seq, e->d_p2p_err};
+        swap_pack_top_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 2048), 256, 0, e->stream>>>(
+            p, p2p_slot(e->p2p_above, n, par, 1), sync);
+    } else if (phase == 1) {  // wait for the carry, sweep, carry into the colder neighbour's mailbox
+        if (e->swept) return fail(e, PTMCMC_ERR_STATE, "no sharded swap sweep is due");
+        const double *cin = hottest ? nullptr : p2p_slot(e->p2p_box, n, par, 0);
+        double *cout = coldest ? nullptr : p2p_slot(e->p2p_below, n, par, 0);
+        const P2PSync sync{hottest ? nullptr : p2p_flag(e->p2p_box, n, par, 0), coldest ? nullptr : p2p_flag(e->p2p_below, n, par, 0),
+                           e->d_p2p_ctr + 1, seq, e->d_p2p_err};
+        {
+            LaunchTimer lt(e, PTMCMC_K_SWAP);
+            swap_sweep_kernel<<<(e->W + 127) / 128, 128, 0, e->stream>>>(p, e->cfg.ladder_above, e->d_swap_prep, cin, cout, e->d_map,
+                                                                          e->d_carry_code, e->d_carry_L, sync);
+        }
+        e->carry_in = cin;
+        e->swept = true;
+    } else if (phase == 2) {  // wait for the colder neighbour's top rung, resolve position 0, permute
+        if (!e->swept) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_swap_p2p(2) before ptmcmc_swap_p2p(1)");
+        const double *below_top = coldest ? nullptr : p2p_slot(e->p2p_box, n, par, 1);
+        const P2PSync sync{coldest ? nullptr : p2p_flag(e->p2p_box, n, par, 1), nullptr, nullptr, seq, e->d_p2p_err};
+        short *tr = nullptr;
+        if (e->d_swapmaps && e->swap_events < e->cfg.trace_iters) tr = e->d_swapmaps + (size_t)e->swap_events * e->W * e->T;
+        const int nxt = e->cur ^ 1;
+        {
+            LaunchTimer lt(e, PTMCMC_K_SWAP);
+            swap_finish_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, e->iter, e->Tg, e->cfg.ladder_below, e->d_map,
+                                                                              e->d_carry_code, e->d_carry_L, e->carry_in, below_top,
+                                                                              e->x[nxt], e->lnl[nxt], e->lp[nxt], tr, sync);
+        }
+        e->cur = nxt;
+        e->swap_proposed++;
+        e->swap_events++;
+        e->pending_swap = false;
+        e->swept = false;
+        e->carry_in = nullptr;
+        e->p2p_seq = seq;
+        e->rows = std::max(e->rows, (long long)(e->iter / e->cfg.thin + 1));
+        CUDA_TRY(e, sink_flush(e));
+    } else {
+        return fail(e, PTMCMC_ERR_ARG, "ptmcmc_swap_p2p: phase is 0 (pack), 1 (sweep) or 2 (finish)");
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    return 0;
+}
+
+int32_t ptmcmc_p2p_error(ptmcmc_engine *h)
+{
+    Engine *e = engine_of(h);
+    if (!e) return PTMCMC_ERR_ARG;
+    if (!e->d_p2p_err) return 0;
+    int err = 0;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaMemcpy(&err, e->d_p2p_err, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) return fail(e, PTMCMC_ERR_STATE, "a neighbour's swap message did not arrive within the time limit");
     return 0;
 }
 

@@ -152,6 +152,51 @@ __global__ void __launch_bounds__(MH_THREADS) swap_apply_kernel(const DevParams 
 // rung, T = the carry received from the hotter shard, T+1 = the colder shard's top rung.
 // ---------------------------------------------------------------------------------------------
 
+// One hop of the neighbour exchange through peer memory (NVLink loads / stores from the kernels themselves instead of a
+// send / receive pair): a kernel that consumes a message spins on a flag in its OWN memory until the neighbour has set
+// it to this swap's sequence number; a kernel that produces one writes it straight into the neighbour's mailbox and the
+// last block to finish publishes the sequence number there.  A wait that times out sets *err and goes on (the run is
+// then invalid, but nothing hangs).
+struct P2PSync {
+    const unsigned long long *wait_flag;  // nullptr: nothing to wait for
+    unsigned long long *signal_flag;      // nullptr: nothing to publish
+    unsigned *done_ctr;                   // blocks that have finished writing (reset by the last one)
+    unsigned long long seq;
+    int *err;
+};
+constexpr long long P2P_TIMEOUT_CLOCKS = 4000000000ll;  // about two seconds
+
+__device__ __forceinline__ void p2p_wait(const P2PSync &s)
+{
+    if (s.wait_flag) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            while (*reinterpret_cast<const volatile unsigned long long *>(s.wait_flag) < s.seq) {
+                if (clock64() - t0 > P2P_TIMEOUT_CLOCKS) {
+                    *s.err = 1;
+                    break;
+                }
+                __nanosleep(64);
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void p2p_signal(const P2PSync &s)
+{
+    if (s.signal_flag) {
+        __threadfence_system();  // this thread's stores to the neighbour's memory
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(s.done_ctr, 1u) == gridDim.x - 1) {
+            *s.done_ctr = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(s.signal_flag) = s.seq;
+        }
+    }
+}
+
 // acceptance of the pair (lower rung: La at Ta, upper rung: Lb at Tb); ref :673-679, same term order.
 // One definition for every caller: both shards of a boundary must reach the same bit.
 __device__ __forceinline__ bool swap_accept(double La, double Lb, double Ta, double Tb, double u)
@@ -163,7 +208,7 @@ __device__ __forceinline__ bool swap_accept(double La, double Lb, double Ta, dou
     return u <= exp(lar);
 }
 
-__global__ void __launch_bounds__(256) swap_pack_top_kernel(const DevParams p, double *msg)
+__global__ void __launch_bounds__(256) swap_pack_top_kernel(const DevParams p, double *msg, const P2PSync sync)
 {
     const int d = p.d, W = p.W, T = p.T;
     const long long n = (long long)(d + 3) * W;
@@ -177,17 +222,19 @@ __global__ void __launch_bounds__(256) swap_pack_top_kernel(const DevParams p, d
         else v = (double)(p.temp_offset + T - 1);
         msg[idx] = v;
     }
+    p2p_signal(sync);
 }
 
 // thread per walker: boundary pair with the hotter shard (if any), then the local pairs, top-down, on the terms of
 // swap_prep_kernel (launched when the segment ended, long before the carry arrives).
 __global__ void __launch_bounds__(128) swap_sweep_kernel(const DevParams p, double ladder_above, const double *prep,
                                                          const double *carry_in, double *carry_out, int *map_out,
-                                                         int *carry_code, double *carry_L)
+                                                         int *carry_code, double *carry_L, const P2PSync sync)
 {
     const int d = p.d, W = p.W, T = p.T;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= W) return;
+    p2p_wait(sync);
+    if (w < W) {
     const size_t C = (size_t)T * W;
     int carry = T - 1;
     double Lcarry = p.lnl[(size_t)(T - 1) * W + w];
@@ -213,6 +260,8 @@ __global__ void __launch_bounds__(128) swap_sweep_kernel(const DevParams p, doub
             carry_out[(size_t)(d + 2) * W + w] = (double)(p.temp_offset + carry);
         }
     }
+    }
+    p2p_signal(sync);
 }
 
 // thread per chain: position 0 resolves the boundary pair with the colder shard (the same decision
@@ -223,10 +272,11 @@ __global__ void __launch_bounds__(MH_THREADS) swap_finish_kernel(const DevParams
                                                                   const int *carry_code, const double *carry_L,
                                                                   const double *carry_in, const double *below_top,
                                                                   double *x_new, double *lnl_new, double *lp_new,
-                                                                  short *swapmap_trace)
+                                                                  short *swapmap_trace, const P2PSync sync)
 {
     const int d = p.d, W = p.W, T = p.T;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    p2p_wait(sync);
     if (c >= (long long)T * W) return;
     const int t = (int)(c / W), w = (int)(c % W);
     int code;

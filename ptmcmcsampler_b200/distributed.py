@@ -169,11 +169,40 @@ class LadderComm(object):
             if ranks not in _BULK_GROUPS:  # one extra communicator per set of ranks, for the life of the process
                 _BULK_GROUPS[ranks] = dist.new_group(ranks=list(ranks))
             self.bulk_group = _BULK_GROUPS[ranks]
+        # swap messages through peer memory (the kernels store into the neighbour's mailbox over NVLink and spin on a flag
+        # in their own memory) instead of a send / receive pair per hop of the 8-stage carry chain; every shard must
+        # succeed in mapping its neighbours, else all keep the NCCL messages
+        self.p2p = False
+        if self.world > 1 and self.device.type == "cuda" and not os.environ.get("PTMCMC_NO_P2P"):
+            self.p2p = self._connect_p2p(engine)
         self.maint_done = -1
         self.am_sent = -1      # last iteration whose AM-ring slot has been broadcast from the cold shard
         self.am_works = []     # broadcasts in flight
         self._ring = None
         self._factor = None    # device views of the engine's eigen-factor
+
+    def _connect_p2p(self, engine):
+        handle, ok = None, 1
+        try:
+            handle, _ = engine.p2p_open()
+        except Exception:  # no CUDA IPC here (e.g. a restricted container)
+            ok = 0
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle if ok else None, group=self.group)
+        if any(h is None for h in handles):
+            return False
+        try:
+            engine.p2p_connect(None if self.hottest else handles[self.rank + 1], None if self.coldest else handles[self.rank - 1])
+        except Exception:
+            ok = 0
+        flags = [None] * self.world
+        self.dist.all_gather_object(flags, ok, group=self.group)
+        return all(flags)
+
+    def check(self, engine):
+        """Synchronise and raise if a neighbour's swap message never arrived (peer-memory exchange only)."""
+        if self.p2p:
+            engine.p2p_error()
 
     def _on_stream(self):
         import contextlib
@@ -216,6 +245,10 @@ class LadderComm(object):
 
 def ladder_swap(engine, comm):
     """One sharded swap sweep (the engine stopped at a swap iteration)."""
+    if comm.p2p:
+        for phase in (0, 1, 2):  # only enqueues: the flags in the mailboxes order the shards on the devices
+            engine.swap_p2p(phase)
+        return
     with comm._on_stream():
         if not comm.hottest:
             engine.swap_pack_top(comm.up_out.data_ptr())
@@ -351,10 +384,18 @@ class CudaMem(object):
         engine.sync()
 
 
-def run_ladder_local(engines, niter, tskip, mem):
+def connect_local_p2p(engines):
+    """Shards of one process on one device: the peer-memory exchange with plain device addresses."""
+    boxes = [e.p2p_open(want_handle=False)[1] for e in engines]
+    for g, e in enumerate(engines):
+        e.p2p_connect(boxes[g + 1] if g + 1 < len(engines) else None, boxes[g - 1] if g > 0 else None)
+
+
+def run_ladder_local(engines, niter, tskip, mem, p2p=False):
     """All shards of a ladder driven by ONE process (several shards on one device; also the reference
     implementation of the protocol for the tests): the same steps as ``run_ladder`` with the messages
-    handed over directly.  ``mem`` is a ``HostMem`` / ``CudaMem``."""
+    handed over directly.  ``mem`` is a ``HostMem`` / ``CudaMem``; ``p2p``: the shards were connected with
+    ``connect_local_p2p`` and exchange the messages themselves (phase by phase: they share the device)."""
     G = len(engines)
     n = engines[0].swap_msg_doubles
     up = [mem.alloc(n) for _ in range(G)]
@@ -381,7 +422,13 @@ def run_ladder_local(engines, niter, tskip, mem):
         for e in engines:
             e.run(step)
         done += step
-        if engines[0].swap_pending:
+        if engines[0].swap_pending and p2p:
+            for phase in (0, 1, 2):
+                for g in (reversed(range(G)) if phase == 1 else range(G)):
+                    engines[g].swap_p2p(phase)
+            for e in engines:
+                e.p2p_error()
+        elif engines[0].swap_pending:
             for g in range(G - 1):
                 engines[g].swap_pack_top(up[g][0])
                 mem.sync(engines[g])

@@ -46,7 +46,10 @@ def main():
     e.set_state(x0[sk["temp_offset"]:sk["temp_offset"] + T])
     comm = dm.LadderComm(e)
     dm.run_ladder(e, N, comm, 10)
+    comm.check(e)
     e.sync()
+    if rank == 0:
+        print("swap messages through", "peer memory (ptmcmc_swap_p2p)" if comm.p2p else "NCCL send / receive", flush=True)
     mine = dict(x=e.state()[0], tr=e.trace(N, N // 10)[0], sm=e.trace(N, N // 10)[1], sw=e.counters()[2], ch=e.chain()[0])
     parts = [None] * world
     dist.all_gather_object(parts, mine)

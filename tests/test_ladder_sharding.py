@@ -197,8 +197,11 @@ def test_merge_batches_is_chan_merge():
 
 # ------------------------------------------------------------------------------------ GPU -----
 @pytest.mark.gpu
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("d,W,Tg,G", [(5, 33, 6, 3), (20, 64, 8, 2), (8, 16, 4, 4)])
-def test_cuda_shards_on_one_device_match_unsharded_engine_and_oracle(d, W, Tg, G):
+def test_cuda_shards_on_one_device_match_unsharded_engine_and_oracle(d, W, Tg, G, p2p):
+    """p2p: the swap messages are stored into the neighbour's mailbox by the kernels themselves (ptmcmc_swap_p2p) instead
+    of being handed over between the three steps."""
     from ptmcmcsampler_b200 import _cabi
 
     N = 300
@@ -220,8 +223,10 @@ def test_cuda_shards_on_one_device_match_unsharded_engine_and_oracle(d, W, Tg, G
         shards.append(e)
     with pytest.raises(_cabi.EngineError):
         shards[0].run(kw["tskip"] + 1)
-    dist_mod.run_ladder_local(shards, 130, kw["tskip"], dist_mod.CudaMem(0))
-    dist_mod.run_ladder_local(shards, N - 130, kw["tskip"], dist_mod.CudaMem(0))
+    if p2p:
+        dist_mod.connect_local_p2p(shards)
+    dist_mod.run_ladder_local(shards, 130, kw["tskip"], dist_mod.CudaMem(0), p2p=p2p)
+    dist_mod.run_ladder_local(shards, N - 130, kw["tskip"], dist_mod.CudaMem(0), p2p=p2p)
     nsw = N // kw["tskip"]
     tr = np.concatenate([s.trace(N, nsw)[0] for s in shards], axis=1)
     sm = np.concatenate([s.trace(N, nsw)[1] for s in shards], axis=2)
