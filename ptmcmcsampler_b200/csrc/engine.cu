@@ -1562,10 +1562,11 @@ int32_t ptmcmc_swap_p2p(ptmcmc_engine *h, int32_t phase)
         if (e->d_swapmaps && e->swap_events < e->cfg.trace_iters) tr = e->d_swapmaps + (size_t)e->swap_events * e->W * e->T;
         const int nxt = e->cur ^ 1;
         {
-            LaunchTimer lt(e, PTMCMC_K_SWAP);
+            LaunchTimer lt(e, PTMCMC_K_SWAP, coldest ? 1 : 2);
+            if (!coldest) p2p_wait_kernel<<<1, 32, 0, e->stream>>>(sync);
             swap_finish_kernel<<<chain_blocks(e), MH_THREADS, 0, e->stream>>>(p, e->iter, e->Tg, e->cfg.ladder_below, e->d_map,
                                                                               e->d_carry_code, e->d_carry_L, e->carry_in, below_top,
-                                                                              e->x[nxt], e->lnl[nxt], e->lp[nxt], tr, sync);
+                                                                              e->x[nxt], e->lnl[nxt], e->lp[nxt], tr, P2PSync{});
         }
         e->cur = nxt;
         e->swap_proposed++;

@@ -197,6 +197,9 @@ __device__ __forceinline__ void p2p_signal(const P2PSync &s)
     }
 }
 
+// the wait alone, ahead of a kernel of many blocks (they would all spin on the flag and hold the SMs meanwhile)
+__global__ void p2p_wait_kernel(const P2PSync sync) { p2p_wait(sync); }
+
 // acceptance of the pair (lower rung: La at Ta, upper rung: Lb at Tb); ref :673-679, same term order.
 // One definition for every caller: both shards of a boundary must reach the same bit.
 __device__ __forceinline__ bool swap_accept(double La, double Lb, double Ta, double Tb, double u)
