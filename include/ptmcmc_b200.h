@@ -227,15 +227,18 @@ int32_t ptmcmc_swap_finish(ptmcmc_engine *e, const double *dev_below_top);
  * its own memory) instead of a send / receive pair per hop: replaces the same reference lines (:660-661, :689-691).
  *   ptmcmc_p2p_open(e, handle, &ptr)   allocates this shard's mailbox; handle receives its 64-byte CUDA IPC handle
  *                                      (NULL to skip), ptr its device address (for shards living in one process)
- *   ptmcmc_p2p_connect(e, above, below, ipc)  the hotter / colder neighbour's mailbox: IPC handles when ipc != 0, else
- *                                      device addresses; NULL exactly where there is no neighbour.  Collective: every shard
- *                                      connects between the same two swaps.
+ *   ptmcmc_p2p_connect(e, above, below, ipc, seq0)  the hotter / colder neighbour's mailbox: IPC handles when ipc != 0,
+ *                                      else device addresses; NULL exactly where there is no neighbour.  Collective: every
+ *                                      shard connects between the same two swaps and passes the same seq0 >= the largest
+ *                                      ptmcmc_p2p_seq() among them (mailboxes are reused by later engines of the process,
+ *                                      their flags only ever grow).
  *   ptmcmc_swap_p2p(e, phase)          phase 0: pack, 1: sweep, 2: finish -- only enqueues work; every shard issues the
  *                                      three in this order.  Shards sharing ONE device must issue phase by phase
  *                                      (all packs, all sweeps hottest first, all finishes).
  *   ptmcmc_p2p_error(e)                synchronises; an error if a message did not arrive within about two seconds */
 int32_t ptmcmc_p2p_open(ptmcmc_engine *e, void *ipc_handle_out, void **mailbox_out);
-int32_t ptmcmc_p2p_connect(ptmcmc_engine *e, const void *above, const void *below, int32_t ipc);
+int64_t ptmcmc_p2p_seq(const ptmcmc_engine *e);
+int32_t ptmcmc_p2p_connect(ptmcmc_engine *e, const void *above, const void *below, int32_t ipc, int64_t seq0);
 int32_t ptmcmc_swap_p2p(ptmcmc_engine *e, int32_t phase);
 int32_t ptmcmc_p2p_error(ptmcmc_engine *e);
 /* device address and length of the AM ring: the cold shard broadcasts it before a DE update, the

@@ -64,7 +64,7 @@ SYMBOLS = [
     "ptmcmc_snapshot", "ptmcmc_snapshot_wait", "ptmcmc_adapt_begin_dev", "ptmcmc_adapt_finish_dev", "ptmcmc_factor_dev",
     "ptmcmc_factor_refresh", "ptmcmc_user_compile_check", "ptmcmc_callback_buffers", "ptmcmc_propose_pinned",
     "ptmcmc_accept_pinned", "ptmcmc_state_seed", "ptmcmc_p2p_open", "ptmcmc_p2p_connect", "ptmcmc_swap_p2p",
-    "ptmcmc_p2p_error",
+    "ptmcmc_p2p_error", "ptmcmc_p2p_seq",
 ]
 
 _lib = None
@@ -134,7 +134,9 @@ def load():
     L.ptmcmc_swap_sweep.argtypes = [h, C.c_void_p, C.c_void_p]
     L.ptmcmc_swap_finish.argtypes = [h, C.c_void_p]
     L.ptmcmc_p2p_open.argtypes = [h, C.c_void_p, C.POINTER(C.c_void_p)]
-    L.ptmcmc_p2p_connect.argtypes = [h, C.c_void_p, C.c_void_p, C.c_int32]
+    L.ptmcmc_p2p_connect.argtypes = [h, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64]
+    L.ptmcmc_p2p_seq.restype = C.c_int64
+    L.ptmcmc_p2p_seq.argtypes = [h]
     L.ptmcmc_swap_p2p.argtypes = [h, C.c_int32]
     L.ptmcmc_p2p_error.argtypes = [h]
     L.ptmcmc_am_ring.argtypes = [h, C.POINTER(C.c_void_p), _i64p]
@@ -505,16 +507,21 @@ class Engine(object):
         self._check(self._L.ptmcmc_p2p_open(self._h, hd, C.byref(ptr)))
         return (bytes(hd) if want_handle else None), ptr.value
 
-    def p2p_connect(self, above, below):
+    @property
+    def p2p_seq(self):
+        return int(self._L.ptmcmc_p2p_seq(self._h))
+
+    def p2p_connect(self, above, below, seq0):
         """``above`` / ``below``: the hotter / colder neighbour's mailbox, as 64-byte IPC handles (other processes) or as
-        device addresses (same process); None where there is no neighbour."""
+        device addresses (same process); None where there is no neighbour.  ``seq0``: the shards' common sequence number
+        (at least the largest ``p2p_seq`` among them)."""
         ipc = isinstance(above if above is not None else below, (bytes, bytearray))
         if ipc:
             keep = [C.create_string_buffer(bytes(v), 64) if v is not None else None for v in (above, below)]
             args = [C.cast(k, C.c_void_p) if k is not None else None for k in keep]
         else:
             args = [C.c_void_p(v) if v is not None else None for v in (above, below)]
-        self._check(self._L.ptmcmc_p2p_connect(self._h, args[0], args[1], 1 if ipc else 0))
+        self._check(self._L.ptmcmc_p2p_connect(self._h, args[0], args[1], 1 if ipc else 0, int(seq0)))
 
     def swap_p2p(self, phase):
         self._check(self._L.ptmcmc_swap_p2p(self._h, phase))

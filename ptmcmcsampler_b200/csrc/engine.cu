@@ -14,6 +14,8 @@
 #include <cstring>
 #include <ctime>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -30,6 +32,22 @@ using namespace ptm;
 static_assert(PTMCMC_MAX_CYCLE == MAX_CYCLE, "cycle capacity mismatch");
 
 namespace {
+
+// Mailboxes and the mappings of the neighbours' mailboxes outlive the engines: a new engine of the same geometry (the
+// next PTSampler.sample() call) takes the mailbox of the last one together with its sequence number -- every shard has
+// made the same number of swaps, so the shards agree on it without talking -- and the IPC mappings are opened once.
+struct Mailbox {
+    int device;
+    size_t bytes;
+    double *box;
+    unsigned *ctr;
+    int *err;
+    unsigned long long seq;
+    bool in_use;
+};
+std::mutex g_p2p_mu;
+std::vector<Mailbox> g_mailboxes;
+std::map<std::string, void *> g_ipc_maps;  // 64-byte handle -> mapping in this process
 
 thread_local std::string g_create_error;
 
@@ -116,7 +134,7 @@ struct Engine {
     // neighbour exchange of the sharded swap through peer memory (ptmcmc_p2p_*): my mailbox holds, per parity of the
     // swap's sequence number, the carry from the hotter shard and the top rung of the colder one, then 8 flags
     double *p2p_box = nullptr, *p2p_above = nullptr, *p2p_below = nullptr;
-    bool p2p_above_ipc = false, p2p_below_ipc = false, p2p_on = false;
+    bool p2p_above_ipc = false, p2p_below_ipc = false, p2p_on = false;  // (the IPC mappings are process-wide, never closed)
     unsigned long long p2p_seq = 0;
     unsigned *d_p2p_ctr = nullptr;
     int *d_p2p_err = nullptr;
@@ -821,10 +839,14 @@ void ptmcmc_destroy(ptmcmc_engine *h)
         if (p) cudaFreeAsync(p, e->stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
-    if (e->p2p_above_ipc) cudaIpcCloseMemHandle(e->p2p_above);
-    if (e->p2p_below_ipc) cudaIpcCloseMemHandle(e->p2p_below);
-    for (void *pp : {(void *)e->p2p_box, (void *)e->d_p2p_ctr, (void *)e->d_p2p_err})
-        if (pp) cudaFree(pp);
+    if (e->p2p_box) {  // the mailbox goes back to the process-level cache with its sequence number
+        std::lock_guard<std::mutex> lock(g_p2p_mu);
+        for (Mailbox &m : g_mailboxes)
+            if (m.box == e->p2p_box) {
+                m.seq = e->p2p_seq;
+                m.in_use = false;
+            }
+    }
     for (void *hp : {(void *)e->h_q, (void *)e->h_qxy, (void *)e->h_lnl, (void *)e->h_lp, (void *)e->h_x, (void *)e->h_jump})
         if (hp) cudaFreeHost(hp);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -1459,6 +1481,7 @@ int32_t ptmcmc_swap_finish(ptmcmc_engine *h, const double *dev_below_top)
 
 // ---- the same three steps with the messages moved by the kernels themselves through peer memory ------------------
 namespace {
+
 inline double *p2p_slot(double *box, size_t n, int par, int kind) { return box + (size_t)(par * 2 + kind) * n; }
 inline unsigned long long *p2p_flag(double *box, size_t n, int par, int kind)
 {
@@ -1473,13 +1496,33 @@ int32_t ptmcmc_p2p_open(ptmcmc_engine *h, void *ipc_handle_out, void **mailbox_o
     if (!e->sharded) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_p2p_open on an engine that is not a ladder shard");
     const size_t n = (size_t)(e->d + 3) * e->W, bytes = 4 * n * sizeof(double) + 64;
     if (!e->p2p_box) {
-        // cudaMalloc, not the stream-ordered pool: the allocation is exported to the neighbours' processes
-        CUDA_TRY(e, cudaMalloc(&e->p2p_box, bytes));
-        CUDA_TRY(e, cudaMemset(e->p2p_box, 0, bytes));
-        CUDA_TRY(e, cudaMalloc(&e->d_p2p_ctr, 4 * sizeof(unsigned)));
-        CUDA_TRY(e, cudaMemset(e->d_p2p_ctr, 0, 4 * sizeof(unsigned)));
-        CUDA_TRY(e, cudaMalloc(&e->d_p2p_err, sizeof(int)));
-        CUDA_TRY(e, cudaMemset(e->d_p2p_err, 0, sizeof(int)));
+        std::lock_guard<std::mutex> lock(g_p2p_mu);
+        for (Mailbox &m : g_mailboxes) {
+            if (!m.in_use && m.device == e->cfg.device && m.bytes == bytes) {
+                m.in_use = true;
+                e->p2p_box = m.box;
+                e->d_p2p_ctr = m.ctr;
+                e->d_p2p_err = m.err;
+                e->p2p_seq = m.seq;
+                cudaMemset(m.err, 0, sizeof(int));
+                break;
+            }
+        }
+        if (!e->p2p_box) {
+            // cudaMalloc, not the stream-ordered pool: the allocation is exported to the neighbours' processes
+            Mailbox m{e->cfg.device, bytes, nullptr, nullptr, nullptr, 0ull, true};
+            CUDA_TRY(e, cudaMalloc(&m.box, bytes));
+            CUDA_TRY(e, cudaMemset(m.box, 0, bytes));
+            CUDA_TRY(e, cudaMalloc(&m.ctr, 4 * sizeof(unsigned)));
+            CUDA_TRY(e, cudaMemset(m.ctr, 0, 4 * sizeof(unsigned)));
+            CUDA_TRY(e, cudaMalloc(&m.err, sizeof(int)));
+            CUDA_TRY(e, cudaMemset(m.err, 0, sizeof(int)));
+            g_mailboxes.push_back(m);
+            e->p2p_box = m.box;
+            e->d_p2p_ctr = m.ctr;
+            e->d_p2p_err = m.err;
+            e->p2p_seq = 0;
+        }
     }
     if (mailbox_out) *mailbox_out = e->p2p_box;
     if (ipc_handle_out) {
@@ -1491,7 +1534,9 @@ int32_t ptmcmc_p2p_open(ptmcmc_engine *h, void *ipc_handle_out, void **mailbox_o
     return 0;
 }
 
-int32_t ptmcmc_p2p_connect(ptmcmc_engine *h, const void *above, const void *below, int32_t ipc)
+int64_t ptmcmc_p2p_seq(const ptmcmc_engine *h) { return h ? (int64_t)((const Engine *)h)->p2p_seq : -1; }
+
+int32_t ptmcmc_p2p_connect(ptmcmc_engine *h, const void *above, const void *below, int32_t ipc, int64_t seq0)
 {
     Engine *e = engine_of(h);
     if (!e) return PTMCMC_ERR_ARG;
@@ -1509,17 +1554,25 @@ int32_t ptmcmc_p2p_connect(ptmcmc_engine *h, const void *above, const void *belo
         }
         cudaIpcMemHandle_t hd;
         memcpy(&hd, src, sizeof hd);
+        const std::string key((const char *)src, sizeof hd);
+        std::lock_guard<std::mutex> lock(g_p2p_mu);
+        auto it = g_ipc_maps.find(key);
+        if (it != g_ipc_maps.end()) {
+            *dst = (double *)it->second;
+            return cudaSuccess;
+        }
         void *ptr = nullptr;
         cudaError_t st = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
         if (st == cudaSuccess) {
             *dst = (double *)ptr;
-            *is_ipc = true;
+            g_ipc_maps[key] = ptr;  // stays mapped for the life of the process
         }
         return st;
     };
     CUDA_TRY(e, map(above, &e->p2p_above, &e->p2p_above_ipc));
     CUDA_TRY(e, map(below, &e->p2p_below, &e->p2p_below_ipc));
-    e->p2p_seq = 0;
+    if (seq0 < (int64_t)e->p2p_seq) return fail(e, PTMCMC_ERR_ARG, "ptmcmc_p2p_connect: seq0 is behind this mailbox's sequence number");
+    e->p2p_seq = (unsigned long long)seq0;  // the shards' common starting point: flags only ever grow
     e->p2p_on = true;
     return 0;
 }

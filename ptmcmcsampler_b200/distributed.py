@@ -134,6 +134,7 @@ def ladder_shard_kwargs(ladder, world, rank):
 
 
 _BULK_GROUPS = {}
+_P2P_LINKS = {}  # (ranks, device, message size) -> every shard's mailbox handle, once all of them were mapped
 
 
 class LadderComm(object):
@@ -182,22 +183,37 @@ class LadderComm(object):
         self._factor = None    # device views of the engine's eigen-factor
 
     def _connect_p2p(self, engine):
-        handle, ok = None, 1
+        """Map the neighbours' mailboxes.  The library keeps mailboxes and mappings for the life of the process, so a later
+        engine of the same geometry gets the same mailbox back, with the sequence number every shard left it at: then
+        nothing is exchanged at all.  Otherwise one collective carries every shard's handle and sequence number (and, the
+        first time, a second one the verdict that every rank could map its neighbours)."""
+        mine = None
         try:
-            handle, _ = engine.p2p_open()
+            mine = (engine.p2p_open()[0], engine.p2p_seq)
         except Exception:  # no CUDA IPC here (e.g. a restricted container)
-            ok = 0
-        handles = [None] * self.world
-        self.dist.all_gather_object(handles, handle if ok else None, group=self.group)
-        if any(h is None for h in handles):
+            pass
+        ranks = tuple(self.dist.get_process_group_ranks(self.group) if self.group is not None else range(self.world))
+        key = (ranks, engine.device, engine.swap_msg_doubles)
+        known = _P2P_LINKS.get(key)
+        if mine is not None and known is not None and known[self.rank] == mine[0]:
+            engine.p2p_connect(None if self.hottest else known[self.rank + 1], None if self.coldest else known[self.rank - 1], mine[1])
+            return True
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, mine, group=self.group)
+        if any(q is None for q in parts):
             return False
+        ok = 1
         try:
-            engine.p2p_connect(None if self.hottest else handles[self.rank + 1], None if self.coldest else handles[self.rank - 1])
+            engine.p2p_connect(None if self.hottest else parts[self.rank + 1][0], None if self.coldest else parts[self.rank - 1][0],
+                               max(q[1] for q in parts))
         except Exception:
             ok = 0
         flags = [None] * self.world
         self.dist.all_gather_object(flags, ok, group=self.group)
-        return all(flags)
+        if all(flags):
+            _P2P_LINKS[key] = [q[0] for q in parts]
+            return True
+        return False
 
     def check(self, engine):
         """Synchronise and raise if a neighbour's swap message never arrived (peer-memory exchange only)."""
@@ -387,8 +403,9 @@ class CudaMem(object):
 def connect_local_p2p(engines):
     """Shards of one process on one device: the peer-memory exchange with plain device addresses."""
     boxes = [e.p2p_open(want_handle=False)[1] for e in engines]
+    seq0 = max(e.p2p_seq for e in engines)
     for g, e in enumerate(engines):
-        e.p2p_connect(boxes[g + 1] if g + 1 < len(engines) else None, boxes[g - 1] if g > 0 else None)
+        e.p2p_connect(boxes[g + 1] if g + 1 < len(engines) else None, boxes[g - 1] if g > 0 else None, seq0)
 
 
 def run_ladder_local(engines, niter, tskip, mem, p2p=False):
