@@ -138,7 +138,8 @@ int32_t ptmcmc_set_state_external(ptmcmc_engine *e, const double *x0, const doub
                                   const double *lnprior);
 
 /* The hot loop (ref :495-528 driver + :530-629 PTMCMCOneStep) for niter iterations, built-in
- * proposals and targets only, entirely on device. */
+ * proposals and targets only, entirely on device.  The random streams are keyed by (seed, iteration, purpose, walker,
+ * rung) with the iteration in one 32-bit counter word: a run ends at iteration 2^32 - 1 (PTMCMC_ERR_ARG beyond). */
 int32_t ptmcmc_run(ptmcmc_engine *e, int64_t niter);
 
 /* Slow path for Python callables, one iteration per propose/accept pair.

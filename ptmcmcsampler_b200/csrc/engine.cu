@@ -947,6 +947,8 @@ int32_t ptmcmc_run(ptmcmc_engine *h, int64_t niter)
     if (niter < 0) return fail(e, PTMCMC_ERR_ARG, "niter < 0");
     if (e->pending_swap) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_run with a sharded swap pending (ptmcmc_swap_*)");
     const long long end = e->iter + niter;
+    // the Philox counter carries the iteration in one 32-bit word: beyond that the draws would repeat
+    if (end > 0xFFFFFFFFll) return fail(e, PTMCMC_ERR_ARG, "iteration %lld is beyond 2^32 - 1, the range of the random streams", end);
     const long long cu = e->cfg.cov_update, burn = e->cfg.burn, tskip = e->cfg.tskip;
     if (e->sharded && niter > 0 && end > next_multiple(e->iter + 1, tskip))
         return fail(e, PTMCMC_ERR_STATE,
@@ -1006,6 +1008,7 @@ static int propose_core(Engine *e)
     if (!e->has_state) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose before set_state");
     if (e->sharded) return fail(e, PTMCMC_ERR_STATE, "host callbacks are not available on a ladder-sharded engine");
     if (e->pending_propose) return fail(e, PTMCMC_ERR_STATE, "ptmcmc_propose called twice");
+    if (e->iter + 1 > 0xFFFFFFFFll) return fail(e, PTMCMC_ERR_ARG, "iteration beyond 2^32 - 1, the range of the random streams");
     if (!e->d_q) {  // staging for the host round trip, allocated on first use
         g_alloc_stream = e->stream;
         const size_t C0 = (size_t)e->T * e->W;

@@ -301,3 +301,17 @@ def test_engines_on_two_devices_in_one_process():
     for u, v in zip(a, b):
         assert np.array_equal(u, v)
     assert np.array_equal(engs[0].chain()[0], engs[1].chain()[0])
+
+
+def test_run_refuses_iterations_beyond_the_random_streams_range():
+    """The Philox counter holds the iteration in 32 bits (round-1 advisor finding): a run that would pass 2^32 - 1 is
+    refused instead of repeating its draws."""
+    d, W, T = 3, 4, 2
+    e = _cabi.Engine(d, W, T, np.eye(d) * 0.1, orc.temperature_ladder(d, T), seed=1, logl_kind=orc.LOGL_GAUSSIAN,
+                     logl_params=orc.gaussian_params(np.zeros(d), np.eye(d)), logp_kind=orc.LOGP_UNIFORM,
+                     logp_params=orc.uniform_params(-5 * np.ones(d), 5 * np.ones(d)))
+    e.set_state(np.zeros((T, W, d)))
+    with pytest.raises(_cabi.EngineError):
+        e.run(2 ** 32)
+    e.run(10)
+    e.close()
