@@ -52,6 +52,56 @@ __global__ void __launch_bounds__(GRAM_THREADS) moments_gram_kernel(const double
 #pragma unroll
     for (int i = 0; i < MAXT; ++i) acc[i][0] = acc[i][1] = 0.0;
     const long long ntw = (W + GRAM_TW - 1) / GRAM_TW;
+    const double *base = tile + (lane >> 2) * GRAM_LDT + (lane & 3);
+    if constexpr (MAXT <= 4) {
+        // small KP: a thread's share of a tile fits in registers, so the loads of the NEXT item are in flight while the
+        // current one is multiplied (one memory round trip per item instead of two plus the compute)
+        constexpr int NV = (MAXT == 1 ? 24 : 56) * GRAM_TW / GRAM_THREADS;
+        // a thread's elements keep their parameter index k from item to item: shift, validity and the tile address are
+        // fixed, and the loads carry no dependent arithmetic (the shift is subtracted when the values are stored)
+        double v[NV], sh[NV];
+        int kk[NV];
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+            const int idx = tid + u * GRAM_THREADS, k = idx / GRAM_TW;
+            kk[u] = idx < KP * GRAM_TW ? k : KP;
+            sh[u] = k < d ? shift[k] : 0.0;
+        }
+        auto fetch = [&](long long item) {
+            const long long slot = item / ntw;
+            const int w0 = (int)(item % ntw) * GRAM_TW;
+            const double *src = am + (size_t)slot * d * W + w0;
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                const int ww = (tid + u * GRAM_THREADS) % GRAM_TW;
+                const bool in = w0 + ww < W;
+                // (a walker beyond W contributes nothing: its value is the shift itself)
+                v[u] = (in && kk[u] < d) ? __ldg(src + (size_t)kk[u] * W + ww) : ((in && kk[u] == d) ? 1.0 : sh[u]);
+            }
+        };
+        const long long total = nslots * ntw;
+        if (blockIdx.x < total) fetch(blockIdx.x);
+        for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+            __syncthreads();  // the previous tile has been multiplied
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                const int idx = tid + u * GRAM_THREADS;
+                if (kk[u] < KP) tile[(idx / GRAM_TW) * GRAM_LDT + idx % GRAM_TW] = v[u] - sh[u];
+            }
+            __syncthreads();
+            if (item + gridDim.x < total) fetch(item + gridDim.x);
+#pragma unroll 4
+            for (int s0 = 0; s0 < GRAM_TW; s0 += 4) {
+#pragma unroll
+                for (int i = 0; i < MAXT; ++i) {
+                    if (i < mine) {
+                        const double a = base[mtv[i] * 8 * GRAM_LDT + s0], b = base[ntv[i] * 8 * GRAM_LDT + s0];
+                        dmma884(acc[i][0], acc[i][1], a, b);
+                    }
+                }
+            }
+        }
+    } else
     for (long long item = blockIdx.x; item < nslots * ntw; item += gridDim.x) {
         const long long slot = item / ntw;
         const int w0 = (int)(item % ntw) * GRAM_TW;
@@ -74,7 +124,6 @@ __global__ void __launch_bounds__(GRAM_THREADS) moments_gram_kernel(const double
             }
         }
         __syncthreads();
-        const double *base = tile + (lane >> 2) * GRAM_LDT + (lane & 3);
 #pragma unroll 4
         for (int s0 = 0; s0 < GRAM_TW; s0 += 4) {
 #pragma unroll

@@ -729,6 +729,14 @@ static int create_impl(Engine *e, const ptmcmc_config *cfg)
     }
     e->gram_kp = ((d + 1) + 7) / 8 * 8;  // ndim + the column of ones, padded to the 8x8 tile
     e->mom_blocks = (e->gram_kp <= 56 ? 8 : e->gram_kp <= 104 ? 3 : 2) * e->sm_count;  // small tiles: many blocks per SM hide the staging latency
+    if (e->gram_kp <= 56) {
+        // persistent blocks: exactly the resident number (a partial second wave would run at a fraction of the occupancy)
+        int nb = 0;
+        const size_t smem = sizeof(double) * e->gram_kp * GRAM_LDT;
+        cudaError_t st = e->gram_kp <= 24 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, moments_gram_kernel<1>, GRAM_THREADS, smem)
+                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, moments_gram_kernel<4>, GRAM_THREADS, smem);
+        if (st == cudaSuccess && nb > 0) e->mom_blocks = nb * e->sm_count;
+    }
     CUDA_TRY(nullptr, dalloc(&e->d_part2, (size_t)e->mom_blocks * e->gram_kp * e->gram_kp));
     CUDA_TRY(nullptr, dalloc(&e->d_gram, (size_t)e->gram_kp * e->gram_kp));
     CUDA_TRY(nullptr, dalloc(&e->d_batch, (size_t)1 + d + (size_t)d * d));

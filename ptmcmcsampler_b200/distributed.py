@@ -216,9 +216,19 @@ class LadderComm(object):
         return False
 
     def check(self, engine):
-        """Synchronise and raise if a neighbour's swap message never arrived (peer-memory exchange only)."""
-        if self.p2p:
+        """Synchronise and raise -- on every rank together -- if a neighbour's swap message never arrived on any of them
+        (peer-memory exchange only)."""
+        if not self.p2p:
+            return
+        failed, msg = 0, ""
+        try:
             engine.p2p_error()
+        except Exception as exc:  # collective below first: the other ranks must not be left waiting
+            failed, msg = 1, str(exc)
+        flag = self.torch.tensor([failed], dtype=self.torch.int32, device=self.device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX, group=self.group)
+        if int(flag.item()):
+            raise RuntimeError("ladder sharding: " + (msg or "a swap message did not arrive on another rank"))
 
     def _on_stream(self):
         import contextlib
