@@ -382,24 +382,34 @@ __global__ void sqrt_kernel(const double *S, double *sqrtS, int n)
 // DE history append (ref :806-817): the reference shifts the buffer left by covUpdate rows and
 // copies the AM buffer into the freed tail; here the history is a ring (head advances by
 // covUpdate slots) and the AM ring am[slot][k][w] is transposed into de[slot'][w][k].
-__global__ void __launch_bounds__(256) de_append_kernel(const double *am, double *de, int d, int W, long long cu,
+// A block moves TWD walkers of one slot: d rows of TWD contiguous doubles in, one run of TWD*d contiguous doubles out
+// (consecutive walkers' history rows are adjacent), through a [d][TWD+1] shared-memory tile read conflict-free along k.
+// grid: (ceil(W/TWD), min(cu, 65535)); a block strides over the slots (gridDim.y is capped at 65535).
+__global__ void __launch_bounds__(256) de_append_kernel(const double *am, double *de, int d, int W, int TWD, long long cu,
                                                         long long burn, long long new_head)
 {
-    __shared__ double tile[32][33];
-    // grid: (ceil(W/32), ceil(d/32), min(cu, 65535)); a block strides over the slots (gridDim.z is capped at 65535)
-    const int w0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    for (long long slot = blockIdx.z; slot < cu; slot += gridDim.z) {
+    extern __shared__ double de_tile[];  // [d][TWD + 1]
+    const int w0 = blockIdx.x * TWD, nw = min(TWD, W - w0), ldt = TWD + 1, tid = threadIdx.x;
+    for (long long slot = blockIdx.y; slot < cu; slot += gridDim.y) {
         const long long dst_slot = (new_head + (burn - cu) + slot) % burn;
-        for (int kk = ty; kk < 32; kk += 8) {
-            const int k = k0 + kk, w = w0 + tx;
-            tile[kk][tx] = (k < d && w < W) ? am[((size_t)slot * d + k) * W + w] : 0.0;
+        const double *src = am + (size_t)slot * d * W + w0;
+        // four loads in flight per thread (the element count is a run-time value)
+        for (int e0 = tid; e0 < d * TWD; e0 += 4 * 256) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 256, k = e / TWD, ww = e % TWD;
+                v[u] = (e < d * TWD && ww < nw) ? src[(size_t)k * W + ww] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 256;
+                if (e < d * TWD) de_tile[(e / TWD) * ldt + e % TWD] = v[u];
+            }
         }
         __syncthreads();
-        for (int ww = ty; ww < 32; ww += 8) {
-            const int w = w0 + ww, k = k0 + tx;
-            if (w < W && k < d) de[((size_t)dst_slot * W + w) * d + k] = tile[tx][ww];
-        }
+        double *dst = de + ((size_t)dst_slot * W + w0) * d;
+        for (int e = tid; e < nw * d; e += 256) dst[e] = de_tile[(e % d) * ldt + e / d];
         __syncthreads();
     }
 }

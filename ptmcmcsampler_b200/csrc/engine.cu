@@ -395,8 +395,10 @@ int de_update(Engine *e)
     {
         LaunchTimer lt(e, PTMCMC_K_DE);
         const long long new_head = (e->de_head + cu) % burn;
-        dim3 grid((e->W + 31) / 32, (e->d + 31) / 32, (unsigned)std::min<long long>(cu, 65535));
-        de_append_kernel<<<grid, 256, 0, e->stream>>>(e->d_am, e->d_de, e->d, e->W, cu, burn, new_head);
+        const int twd = e->d <= 40 ? 128 : 32;  // walkers per block: the [d][twd + 1] tile stays under 48 KB
+        dim3 grid((e->W + twd - 1) / twd, (unsigned)std::min<long long>(cu, 65535));
+        de_append_kernel<<<grid, 256, sizeof(double) * e->d * (twd + 1), e->stream>>>(e->d_am, e->d_de, e->d, e->W, twd, cu, burn,
+                                                                                  new_head);
         e->de_head = new_head;
     }
     if (!e->de_in_cycle && e->cfg.de_weight > 0) {
