@@ -147,3 +147,23 @@ def test_bench_accounting_and_clock_parsing(tmp_path):
     out = cs.stop(rows[4][0].timestamp(), rows[9][0].timestamp())
     assert out["window"] == "timed region" and 6 <= out["samples"] <= 8
     assert out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+
+
+def test_log_comparison_decides_like_the_exponential_outside_the_band():
+    """The swap sweep on the device decides ``u <= exp(lar)`` (ref :679, the oracle's swap_accept) from ``lar - log(u)``
+    unless the two agree to 1e-12, where it evaluates the exponential (csrc/swap_kernels.cuh swap_accept_prep).  The
+    restated rule must agree with the reference's comparison everywhere, ties and non-finite values included."""
+    rng = np.random.default_rng(5)
+    u = rng.random(200000)
+    lar = np.concatenate([rng.normal(0, 3, 100000), np.log(u[100000:]) * (1 + rng.normal(0, 1e-13, 100000))])
+    u[::5000] = 0.0
+    lar[1::5000] = -np.inf
+    lar[2::5000] = np.inf
+    lar[3::5000] = np.nan
+    with np.errstate(all="ignore"):
+        ref = u <= np.exp(lar)
+        logu = np.log(u)
+        gap, band = lar - logu, 1e-12 * np.maximum(1.0, np.abs(lar))
+        rule = np.where(gap > band, True, np.where(gap < -band, False, ref))
+    assert np.array_equal(rule, ref)
+    assert ((np.abs(gap) <= band) & np.isfinite(gap)).sum() > 1000  # the band was exercised
