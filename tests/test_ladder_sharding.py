@@ -198,10 +198,11 @@ def test_merge_batches_is_chan_merge():
 # ------------------------------------------------------------------------------------ GPU -----
 @pytest.mark.gpu
 @pytest.mark.parametrize("p2p", [False, True])
-@pytest.mark.parametrize("d,W,Tg,G", [(5, 33, 6, 3), (20, 64, 8, 2), (8, 16, 4, 4)])
+@pytest.mark.parametrize("d,W,Tg,G", [(5, 33, 6, 3), (20, 64, 8, 2), (8, 16, 4, 4), (20, 48, 256, 8)])
 def test_cuda_shards_on_one_device_match_unsharded_engine_and_oracle(d, W, Tg, G, p2p):
     """p2p: the swap messages are stored into the neighbour's mailbox by the kernels themselves (ptmcmc_swap_p2p) instead
-    of being handed over between the three steps."""
+    of being handed over between the three steps.  The last case is BASELINE config 5's ladder: 256 rungs as 8 shards
+    of 32."""
     from ptmcmcsampler_b200 import _cabi
 
     N = 300
