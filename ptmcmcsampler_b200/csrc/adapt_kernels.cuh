@@ -180,7 +180,7 @@ __global__ void moments_gram_batch_kernel(const double *G, int KP, int d, const 
 // column phase (A J and V J) and a row phase (J^T A), each entry touched by exactly one rotation per phase, so
 // the result does not depend on the order in which a phase is executed: the CPU oracle (orc_sym_factor) runs
 // the same phases sequentially with the same explicitly fused operations and gets the same bits.
-constexpr int JAC_THREADS = 256;
+constexpr int JAC_THREADS = 1024;  // one block, alone on its SM: the rotation phases are latency bound (256 threads: 14 ms at n = 100)
 constexpr int JAC_MAXPAIRS = 64;  // n <= 128
 
 __device__ inline void jacobi_block(int n, double *a, double *v, double *scratch)
