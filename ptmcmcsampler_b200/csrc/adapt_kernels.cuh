@@ -181,7 +181,7 @@ __global__ void moments_gram_batch_kernel(const double *G, int KP, int d, const 
 // the result does not depend on the order in which a phase is executed: the CPU oracle (orc_sym_factor) runs
 // the same phases sequentially with the same explicitly fused operations and gets the same bits.
 constexpr int JAC_THREADS = 1024;  // one block, alone on its SM: the rotation phases are latency bound (256 threads: 14 ms at n = 100)
-constexpr int JAC_MAXPAIRS = 64;  // n <= 128
+constexpr int JAC_MAXPAIRS = 64;  // n <= 128 (a power of two: the phase loops index pairs by tid & 63)
 
 __device__ inline void jacobi_block(int n, double *a, double *v, double *scratch)
 {
@@ -231,34 +231,33 @@ __device__ inline void jacobi_block(int n, double *a, double *v, double *scratch
                 s_p[k] = p; s_q[k] = q; s_s[k] = sn; s_tau[k] = tau; s_rot[k] = rot;
             }
             __syncthreads();
+            // thread (k, r0): pair k = tid mod 64, rows / columns r0, r0 + nth/64, ... (no division in the loops)
+            const int k = tid & (JAC_MAXPAIRS - 1), r0 = tid / JAC_MAXPAIRS, rstep = nth / JAC_MAXPAIRS;
+            const int rot = k < npair ? s_rot[k] : 0;
+            const int p = k < npair ? s_p[k] : 0, q = k < npair ? s_q[k] : 0;
+            const double sn = k < npair ? s_s[k] : 0.0, tau = k < npair ? s_tau[k] : 0.0;
             // ---- column phase: A <- A J, V <- V J
-            for (int idx = tid; idx < n * npair; idx += nth) {
-                const int k = idx % npair, r = idx / npair;
-                if (s_rot[k] != 1) continue;
-                const int p = s_p[k], q = s_q[k];
-                const double sn = s_s[k], tau = s_tau[k];
-                double g = a[r * n + p], h = a[r * n + q];
-                a[r * n + p] = fma(-sn, fma(g, tau, h), g);
-                a[r * n + q] = fma(sn, fma(-h, tau, g), h);
-                g = v[r * n + p]; h = v[r * n + q];
-                v[r * n + p] = fma(-sn, fma(g, tau, h), g);
-                v[r * n + q] = fma(sn, fma(-h, tau, g), h);
+            if (rot == 1) {
+                for (int r = r0; r < n; r += rstep) {
+                    double g = a[r * n + p], h = a[r * n + q];
+                    a[r * n + p] = fma(-sn, fma(g, tau, h), g);
+                    a[r * n + q] = fma(sn, fma(-h, tau, g), h);
+                    g = v[r * n + p]; h = v[r * n + q];
+                    v[r * n + p] = fma(-sn, fma(g, tau, h), g);
+                    v[r * n + q] = fma(sn, fma(-h, tau, g), h);
+                }
             }
             __syncthreads();
-            // ---- row phase: A <- J^T A, then the rotated pair's off-diagonal is zero by construction
-            for (int idx = tid; idx < n * npair; idx += nth) {
-                const int k = idx % npair, c = idx / npair;
-                if (s_rot[k] != 1) continue;
-                const int p = s_p[k], q = s_q[k];
-                const double sn = s_s[k], tau = s_tau[k];
-                const double g = a[p * n + c], h = a[q * n + c];
-                a[p * n + c] = fma(-sn, fma(g, tau, h), g);
-                a[q * n + c] = fma(sn, fma(-h, tau, g), h);
-            }
-            __syncthreads();
-            if (tid < npair && s_rot[tid] != 0) {
-                a[s_p[tid] * n + s_q[tid]] = 0.0;
-                a[s_q[tid] * n + s_p[tid]] = 0.0;
+            // ---- row phase: A <- J^T A; the rotated (or negligible) pair's off-diagonal is zero by construction
+            if (rot == 1) {
+                for (int c = r0; c < n; c += rstep) {
+                    const double g = a[p * n + c], h = a[q * n + c];
+                    a[p * n + c] = (c == q) ? 0.0 : fma(-sn, fma(g, tau, h), g);
+                    a[q * n + c] = (c == p) ? 0.0 : fma(sn, fma(-h, tau, g), h);
+                }
+            } else if (rot == 2 && r0 == 0) {
+                a[p * n + q] = 0.0;
+                a[q * n + p] = 0.0;
             }
             __syncthreads();
         }
