@@ -9,23 +9,24 @@
 //   * two blocks of <= 32 chains per SM at <= 128 registers: one block's draw phases run under the other's tensor phases.
 //     Shared memory per block: the chains' rows and the form's fragment image (packed lower triangle of the Cholesky
 //     factor when the form is positive definite); the factor's image is read through L1 / L2;
-//   * everything random about a step except the AM normals is state-free and small, so it is drawn one iteration AHEAD by
-//     warps that are idle while the others run the Hastings tests: the jump kinds and per-kind lists of iteration it+1
-//     (one warp), then its DE chains' history rows / scales / accept words, the rows prefetched into L2 a whole
-//     iteration before the gather (same warp), and its SCAM chains' component / coefficient / accept word (another warp),
-//     each branch-free with its Philox blocks generated side by side.  Lists, jump ids and these scalars are
-//     double-buffered by the parity of the iteration;
-//   * phase R is then evenly spread tasks only: gathers (loads issued first) and (AM chain, Philox block) normals;
+//   * everything random about a step except the AM normals is state-free and small, so it is drawn AHEAD by warps that are
+//     idle while the others run the Hastings tests of iteration it: the jump kinds and per-kind lists of iteration it+2
+//     (warp 7), and for iteration it+1 the DE chains' history rows / scales / accept words, the rows prefetched into L2 a
+//     whole iteration before the gather (warp 6), the SCAM chains' component / coefficient / accept word (warp 5) and the
+//     AM chains' jump scale (warp 4), each branch-free with its Philox blocks generated side by side.  Lists and jump ids
+//     are triple-buffered (iteration mod 3), these scalars double-buffered by the parity of the iteration;
+//   * phase R is then evenly spread tasks only: gathers (loads issued first) and (AM chain, two Philox blocks) tasks that
+//     store the normals already scaled, delta = z cd sqrt(S);
 //   * phase P: every warp takes <= 2 n-tiles of ALL AM tiles, so each fragment of the factor is fetched once per block
-//     and feeds up to 16 DMMAs; fragments are prefetched PD k-tiles ahead;
+//     and feeds up to 8 DMMAs; fragments are prefetched PD k-tiles ahead;
 //   * phase L: two warps per 8-chain tile, each a balanced part of the (triangular) quadratic form.
 //
 // Per iteration, per block (5 block barriers):
 //   R   warp 0: buffers / record of iteration it-1; all: gather tasks (DE or SCAM chain, 8 columns) -> the step into the
-//       chain's zq row, and (AM chain, Philox block) tasks -> normals into zq
-//   P   zq <- U (z * cd * sqrt(S)) for the AM chains by DMMA (results written after a barrier)
+//       chain's zq row, and AM tasks -> delta into zq
+//   P   zq <- U delta for the AM chains by DMMA (results written after a barrier)
 //   L   per (tile, half): proposal, box test, part of the quadratic form by DMMA; barrier; per tile: Hastings test, state
-//       update, while warps 7 and 6 make the draws of iteration it+1
+//       update, while warps 4..7 make the draws of the next iterations
 #pragma once
 #include "mh_mma_kernel.cuh"
 
