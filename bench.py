@@ -590,8 +590,8 @@ def run_engine(args, rank, world, local_rank):
                 "fraction_of_walker_sharded": r5["value"] / run["value"], "gpu_launches": r5["launches"],
                 "roofline": roofline_of(wl, r5, hbm_peak, hbm_src, fp64_peak),
                 "e2e": e2e_run(wl, rank, world, local_rank, 2, ladder_mode=True, Tg=r5["Tg"])}
-        except RuntimeError as exc:
-            extra["c5_ladder"] = {"error": str(exc)[:300]}
+        except Exception as exc:  # noqa: BLE001 -- whatever it is, the headline line is still printed
+            extra["c5_ladder"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
 
     cpu = None
     if rank == 0 and world == 1:
